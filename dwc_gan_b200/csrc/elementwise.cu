@@ -1,0 +1,764 @@
+// Vectorised NHWC element-wise / reduction kernels around the convolutions: per-(n,c) statistics,
+// normalisation (+activation, +residual, +reflect padding) forward and backward, bilinear 2x upsampling,
+// image <-> haloed-buffer conversion, decoder heads, attention blend, global average pooling.
+// All are HBM-bound: 16-byte (bf16) / 32-byte (fp32) accesses along the channel axis, fp32 math.
+#include "common.cuh"
+
+#define DISPATCH_T(dtype, ...)                     \
+  do {                                             \
+    if ((dtype) == DWC_F32) {                      \
+      typedef float T;                             \
+      __VA_ARGS__;                                 \
+    } else {                                       \
+      typedef bf16 T;                              \
+      __VA_ARGS__;                                 \
+    }                                              \
+  } while (0)
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == 1) return z > 0.f ? z : 0.f;
+  if (act == 2) return z > 0.f ? z : 0.1f * z;
+  return z;
+}
+__device__ __forceinline__ float act_grad(float z, int act) {
+  if (act == 1) return z > 0.f ? 1.f : 0.f;
+  if (act == 2) return z > 0.f ? 1.f : 0.1f;
+  return 1.f;
+}
+
+// sum of dout over all padded positions that reflect onto interior (y,x): 8 channels starting at c0
+template <typename T>
+__device__ __forceinline__ void fold_read8(const HB& d, int n, int y, int x, int c0, float* f) {
+  const T* base = reinterpret_cast<const T*>(d.ptr);
+  int ys[3], xs[3], ny = 0, nx = 0;
+  ys[ny++] = y;
+  xs[nx++] = x;
+  if (d.halo > 0) {
+    if (y >= 1 && y <= d.halo) ys[ny++] = -y;
+    if (y >= d.h - 1 - d.halo && y <= d.h - 2) ys[ny++] = 2 * (d.h - 1) - y;
+    if (x >= 1 && x <= d.halo) xs[nx++] = -x;
+    if (x >= d.w - 1 - d.halo && x <= d.w - 2) xs[nx++] = 2 * (d.w - 1) - x;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = 0.f;
+  for (int i = 0; i < ny; ++i)
+    for (int j = 0; j < nx; ++j) {
+      float t[8];
+      Vec8<T>::load(base + d.off(n, ys[i], xs[j]) + c0, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += t[e];
+    }
+}
+
+// scalar version (any channel count)
+template <typename T>
+__device__ __forceinline__ float fold_read1(const HB& d, int n, int y, int x, int c) {
+  const T* base = reinterpret_cast<const T*>(d.ptr);
+  int ys[3], xs[3], ny = 0, nx = 0;
+  ys[ny++] = y;
+  xs[nx++] = x;
+  if (d.halo > 0) {
+    if (y >= 1 && y <= d.halo) ys[ny++] = -y;
+    if (y >= d.h - 1 - d.halo && y <= d.h - 2) ys[ny++] = 2 * (d.h - 1) - y;
+    if (x >= 1 && x <= d.halo) xs[nx++] = -x;
+    if (x >= d.w - 1 - d.halo && x <= d.w - 2) xs[nx++] = 2 * (d.w - 1) - x;
+  }
+  float s = 0.f;
+  for (int i = 0; i < ny; ++i)
+    for (int j = 0; j < nx; ++j) s += to_f<T>(base[d.off(n, ys[i], xs[j]) + c]);
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-(n,c) statistics.  grid (C/32, splits, N); block 256 = 4 channel-vectors x 64 pixel lanes.
+// MODE 0: {sum y, sum y^2}.  MODE 1: {sum dz, sum dz*y} (backward).
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+    nc_reduce_kernel(HB y, HB dout, const float4* __restrict__ coef, int act, int splits, float2* __restrict__ out) {
+  __shared__ float s0[64][33], s1[64][33];
+  const int cv = threadIdx.x & 3, pl = threadIdx.x >> 2;
+  const int c0 = blockIdx.x * 32 + cv * 8;
+  const int split = blockIdx.y, n = blockIdx.z;
+  const int hw = y.h * y.w;
+  const int per = (hw + splits - 1) / splits;
+  const int p_begin = split * per, p_end = min(hw, p_begin + per);
+  const T* yb = reinterpret_cast<const T*>(y.ptr);
+  float a0[8], a1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a0[e] = a1[e] = 0.f;
+  float sc[8], sh[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (coef) {
+        float4 q = coef[(long long)n * y.c + c0 + e];
+        sc[e] = q.x; sh[e] = q.y;
+      } else { sc[e] = 1.f; sh[e] = 0.f; }
+    }
+  }
+  if (c0 < y.c) {
+    for (int p = p_begin + pl; p < p_end; p += 64) {
+      int py = p / y.w, px = p - py * y.w;
+      float v[8];
+      Vec8<T>::load(yb + y.off(n, py, px) + c0, v);
+      if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a0[e] += v[e]; a1[e] += v[e] * v[e]; }
+      } else {
+        float g[8];
+        fold_read8<T>(dout, n, py, px, c0, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float dz = g[e] * act_grad(sc[e] * v[e] + sh[e], act);
+          a0[e] += dz; a1[e] += dz * v[e];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s0[pl][cv * 8 + e] = a0[e]; s1[pl][cv * 8 + e] = a1[e]; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int i = 0; i < 64; ++i) { t0 += s0[i][threadIdx.x]; t1 += s1[i][threadIdx.x]; }
+    int c = blockIdx.x * 32 + threadIdx.x;
+    if (c < y.c) out[((long long)n * splits + split) * y.c + c] = make_float2(t0, t1);
+  }
+}
+
+extern "C" int dwc_nc_stats(const dwc_hbuf_t* y, int splits, float* stats, dwc_stream_t stream) {
+  DWC_CHECK(y->c % 8 == 0 && y->layout == 0, "dwc_nc_stats: needs C %% 8 == 0 and plain layout");
+  HB hy(*y);
+  dim3 grid(cdiv(y->c, 32), splits, y->n);
+  DISPATCH_T(y->dtype, (nc_reduce_kernel<T, 0><<<grid, 256, 0, as_stream(stream)>>>(hy, hy, nullptr, 0, splits,
+                                                                                       reinterpret_cast<float2*>(stats))));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dwc_post_bwd_reduce(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, int act, int splits,
+                                   float* red, dwc_stream_t stream) {
+  DWC_CHECK(y->c % 8 == 0 && y->layout == 0, "dwc_post_bwd_reduce: needs C %% 8 == 0 and plain y");
+  DWC_CHECK(dout->n == y->n && dout->h == y->h && dout->w == y->w && dout->c == y->c && dout->dtype == y->dtype,
+            "dwc_post_bwd_reduce: geometry mismatch");
+  HB hy(*y), hd(*dout);
+  dim3 grid(cdiv(y->c, 32), splits, y->n);
+  DISPATCH_T(y->dtype, (nc_reduce_kernel<T, 1><<<grid, 256, 0, as_stream(stream)>>>(
+                           hy, hd, reinterpret_cast<const float4*>(coef), act, splits, reinterpret_cast<float2*>(red))));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// statistics -> scale/shift   (one block per sample)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_d(double v, double* sm) {
+  const int tid = threadIdx.x;
+  sm[tid] = v;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (tid < o) sm[tid] += sm[tid + o];
+    __syncthreads();
+  }
+  double r = sm[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+    norm_finalize_kernel(int kind, const float2* __restrict__ stats, int splits, int C, int hw, float eps,
+                         const float* __restrict__ weight, const float* __restrict__ bias, float4* __restrict__ coef) {
+  __shared__ double sm[256];
+  const int n = blockIdx.x;
+  if (kind == 1 || kind == 2) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double s = 0, q = 0;
+      for (int k = 0; k < splits; ++k) {
+        float2 v = stats[((long long)n * splits + k) * C + c];
+        s += v.x; q += v.y;
+      }
+      double mean = s / hw;
+      double var = q / hw - mean * mean;
+      if (var < 0) var = 0;
+      float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      float w = kind == 2 ? weight[(long long)n * C + c] : 1.f;
+      float b = kind == 2 ? bias[(long long)n * C + c] : 0.f;
+      coef[(long long)n * C + c] = make_float4(w * rstd, b - (float)mean * rstd * w, (float)mean, rstd);
+    }
+  } else if (kind == 3) {
+    double s = 0, q = 0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      for (int k = 0; k < splits; ++k) {
+        float2 v = stats[((long long)n * splits + k) * C + c];
+        s += v.x; q += v.y;
+      }
+    s = block_sum_d(s, sm);
+    q = block_sum_d(q, sm);
+    const double M = (double)C * hw;
+    double mean = s / M;
+    double var = (q - M * mean * mean) / (M - 1.0);
+    if (var < 0) var = 0;
+    double sd = sqrt(var);
+    float inv = (float)(1.0 / (sd + (double)eps));
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float g = weight[c], b = bias[c];
+      coef[(long long)n * C + c] = make_float4(g * inv, b - (float)mean * g * inv, (float)mean, inv);
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) coef[(long long)n * C + c] = make_float4(1.f, 0.f, 0.f, 1.f);
+  }
+}
+
+extern "C" int dwc_norm_finalize(int kind, const float* stats, int splits, int n, int c, int hw, float eps,
+                                 const float* weight, const float* bias, float* coef, dwc_stream_t stream) {
+  DWC_CHECK(kind >= 0 && kind <= 3, "dwc_norm_finalize: bad kind");
+  norm_finalize_kernel<<<n, 256, 0, as_stream(stream)>>>(kind, reinterpret_cast<const float2*>(stats), splits, c, hw,
+                                                          eps, weight, bias, reinterpret_cast<float4*>(coef));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// backward coefficients: dy = a*dz + b*y + c.   IN/AdaIN: one block per sample.  LN: single block.
+__global__ void __launch_bounds__(256)
+    norm_bwd_finalize_kernel(int kind, const float2* __restrict__ red, int splits, const float4* __restrict__ coef,
+                             int N, int C, int hw, float eps, const float* __restrict__ weight,
+                             float* __restrict__ dweight, float* __restrict__ dbias, float4* __restrict__ bco) {
+  __shared__ double sm[256];
+  if (kind == 1 || kind == 2) {
+    const int n = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double S1 = 0, S2 = 0;
+      for (int k = 0; k < splits; ++k) {
+        float2 v = red[((long long)n * splits + k) * C + c];
+        S1 += v.x; S2 += v.y;
+      }
+      float4 q = coef[(long long)n * C + c];
+      double mean = q.z, rstd = q.w;
+      double w = kind == 2 ? (double)weight[(long long)n * C + c] : 1.0;
+      double m1 = S1 / hw;
+      double m2 = rstd * (S2 / hw - mean * m1);
+      if (kind == 2) {
+        dbias[(long long)n * C + c] = (float)S1;
+        dweight[(long long)n * C + c] = (float)(rstd * (S2 - mean * S1));
+      }
+      double a = w * rstd;
+      double b = -rstd * rstd * w * m2;
+      double cc = -rstd * w * m1 - b * mean;
+      bco[(long long)n * C + c] = make_float4((float)a, (float)b, (float)cc, 0.f);
+    }
+  } else if (kind == 3) {
+    // per-sample coefficients
+    const double M = (double)C * hw;
+    for (int n = 0; n < N; ++n) {
+      double g1 = 0, g2 = 0;
+      const double mean = coef[(long long)n * C].z;
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double S1 = 0, S2 = 0;
+        for (int k = 0; k < splits; ++k) {
+          float2 v = red[((long long)n * splits + k) * C + c];
+          S1 += v.x; S2 += v.y;
+        }
+        double g = weight[c];
+        g1 += g * S1;
+        g2 += g * (S2 - mean * S1);
+      }
+      g1 = block_sum_d(g1, sm);
+      g2 = block_sum_d(g2, sm);
+      const double inv = coef[(long long)n * C].w;
+      const double sd = 1.0 / inv - (double)eps;
+      const double K = sd > 0 ? g2 * inv * inv / ((M - 1.0) * sd) : 0.0;
+      const double b = -K;
+      const double cc = -g1 * inv / M + K * mean;
+      for (int c = threadIdx.x; c < C; c += blockDim.x)
+        bco[(long long)n * C + c] = make_float4((float)(weight[c] * inv), (float)b, (float)cc, 0.f);
+    }
+    // parameter gradients (accumulated)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double dg = 0, db = 0;
+      for (int n = 0; n < N; ++n) {
+        double S1 = 0, S2 = 0;
+        for (int k = 0; k < splits; ++k) {
+          float2 v = red[((long long)n * splits + k) * C + c];
+          S1 += v.x; S2 += v.y;
+        }
+        float4 q = coef[(long long)n * C + c];
+        dg += (double)q.w * (S2 - (double)q.z * S1);
+        db += S1;
+      }
+      dweight[c] += (float)dg;
+      dbias[c] += (float)db;
+    }
+  }
+}
+
+extern "C" int dwc_norm_bwd_finalize(int kind, const float* red, int splits, const float* coef, int n, int c, int hw,
+                                     float eps, const float* weight, float* dweight, float* dbias, float* bco,
+                                     dwc_stream_t stream) {
+  DWC_CHECK(kind >= 1 && kind <= 3, "dwc_norm_bwd_finalize: bad kind");
+  norm_bwd_finalize_kernel<<<kind == 3 ? 1 : n, 256, 0, as_stream(stream)>>>(
+      kind, reinterpret_cast<const float2*>(red), splits, reinterpret_cast<const float4*>(coef), n, c, hw, eps, weight,
+      dweight, dbias, reinterpret_cast<float4*>(bco));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward post pass: out(padded) = reflect_pad(act(scale*y+shift) + res)
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+    post_fwd_kernel(HB y, const float4* __restrict__ coef, int act, HB res, int has_res, HB out) {
+  const int cvs = out.c >> 3;
+  const long long total = out.padded_pixels() * cvs;
+  const T* yb = reinterpret_cast<const T*>(y.ptr);
+  const T* rb = reinterpret_cast<const T*>(res.ptr);
+  T* ob = reinterpret_cast<T*>(out.ptr);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % cvs);
+    long long pix = i / cvs;
+    int X = (int)(pix % out.wp);
+    long long r = pix / out.wp;
+    int Y = (int)(r % out.hp);
+    int n = (int)(r / out.hp);
+    int iy = reflect_idx(Y - out.halo, out.h), ix = reflect_idx(X - out.halo, out.w);
+    const int c0 = cv * 8;
+    float v[8];
+    Vec8<T>::load(yb + y.off(n, iy, ix) + c0, v);
+    if (coef) {
+      const float4* q = coef + (long long)n * out.c + c0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = act_fwd(q[e].x * v[e] + q[e].y, act);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = act_fwd(v[e], act);
+    }
+    if (has_res) {
+      float rr[8];
+      Vec8<T>::load(rb + res.off(n, iy, ix) + c0, rr);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += rr[e];
+    }
+    Vec8<T>::store(ob + out.off_padded(n, Y, X) + c0, v);
+  }
+}
+
+static inline int ew_grid(long long total) {
+  long long b = (total + 255) / 256;
+  long long cap = (long long)dwc_num_sms() * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+extern "C" int dwc_post_fwd(const dwc_hbuf_t* y, const float* coef, int act, const dwc_hbuf_t* res,
+                            const dwc_hbuf_t* out, dwc_stream_t stream) {
+  DWC_CHECK(y->c % 8 == 0, "dwc_post_fwd: needs C %% 8 == 0");
+  DWC_CHECK(y->n == out->n && y->h == out->h && y->w == out->w && y->c == out->c && y->dtype == out->dtype,
+            "dwc_post_fwd: geometry mismatch");
+  DWC_CHECK(out->layout == 0 || ((out->h + 2 * out->halo) % 2 == 0 && (out->w + 2 * out->halo) % 2 == 0),
+            "dwc_post_fwd: plane layout needs even padded extent");
+  HB hy(*y), ho(*out), hr = res ? HB(*res) : HB(*y);
+  long long total = ho.padded_pixels() * (out->c / 8);
+  DISPATCH_T(y->dtype, (post_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
+                           hy, reinterpret_cast<const float4*>(coef), act, hr, res != nullptr, ho)));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward post pass: dy = a*dz + b*y + c (zero halo), dres = fold(dout) (zero halo)
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+    post_bwd_apply_kernel(HB dout, HB y, const float4* __restrict__ coef, const float4* __restrict__ bco, int act, HB dy,
+                          HB dres, int has_dres) {
+  const int hmax = max(dy.halo, has_dres ? dres.halo : 0);
+  const int HP = y.h + 2 * hmax, WP = y.w + 2 * hmax;
+  const int cvs = y.c >> 3;
+  const long long total = (long long)y.n * HP * WP * cvs;
+  const T* yb = reinterpret_cast<const T*>(y.ptr);
+  T* dyb = reinterpret_cast<T*>(dy.ptr);
+  T* drb = reinterpret_cast<T*>(dres.ptr);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % cvs);
+    long long pix = i / cvs;
+    int X = (int)(pix % WP);
+    long long r = pix / WP;
+    int Y = (int)(r % HP);
+    int n = (int)(r / HP);
+    const int iy = Y - hmax, ix = X - hmax;     // interior coordinates (may be outside)
+    const int c0 = cv * 8;
+    const bool interior = iy >= 0 && iy < y.h && ix >= 0 && ix < y.w;
+    float g[8], o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = o[e] = 0.f;
+    if (interior) {
+      fold_read8<T>(dout, n, iy, ix, c0, g);
+      float v[8];
+      Vec8<T>::load(yb + y.off(n, iy, ix) + c0, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float z = v[e], dz = g[e];
+        if (coef) {
+          float4 q = coef[(long long)n * y.c + c0 + e];
+          z = q.x * v[e] + q.y;
+        }
+        dz *= act_grad(z, act);
+        if (bco) {
+          float4 q = bco[(long long)n * y.c + c0 + e];
+          o[e] = q.x * dz + q.y * v[e] + q.z;
+        } else {
+          o[e] = dz;
+        }
+      }
+    }
+    // dy extent
+    {
+      int py = iy + dy.halo, px = ix + dy.halo;
+      if (py >= 0 && py < dy.hp && px >= 0 && px < dy.wp) Vec8<T>::store(dyb + dy.off_padded(n, py, px) + c0, o);
+    }
+    if (has_dres) {
+      int py = iy + dres.halo, px = ix + dres.halo;
+      if (py >= 0 && py < dres.hp && px >= 0 && px < dres.wp) Vec8<T>::store(drb + dres.off_padded(n, py, px) + c0, g);
+    }
+  }
+}
+
+extern "C" int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, const float* bco,
+                                  int act, const dwc_hbuf_t* dy, const dwc_hbuf_t* dres, dwc_stream_t stream) {
+  DWC_CHECK(y->c % 8 == 0 && y->layout == 0 && dy->layout == 0, "dwc_post_bwd_apply: needs C %% 8 == 0, plain y/dy");
+  DWC_CHECK(dout->n == y->n && dout->h == y->h && dout->w == y->w && dout->c == y->c, "dwc_post_bwd_apply: geometry mismatch");
+  HB hd(*dout), hy(*y), hdy(*dy), hr = dres ? HB(*dres) : HB(*dy);
+  int hmax = dy->halo;
+  if (dres && dres->halo > hmax) hmax = dres->halo;
+  long long total = (long long)y->n * (y->h + 2 * hmax) * (y->w + 2 * hmax) * (y->c / 8);
+  DISPATCH_T(y->dtype, (post_bwd_apply_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
+                           hd, hy, reinterpret_cast<const float4*>(coef), reinterpret_cast<const float4*>(bco), act,
+                           hdy, hr, dres != nullptr)));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bilinear 2x upsample (align_corners = False) + reflect pad
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void up_taps(int o, int size_in, int* i0, int* i1, float* w0, float* w1) {
+  float src = (o + 0.5f) * 0.5f - 0.5f;
+  if (src < 0.f) src = 0.f;
+  int a = (int)src;
+  int b = a + 1 < size_in ? a + 1 : size_in - 1;
+  float l1 = src - a;
+  *i0 = a; *i1 = b; *w0 = 1.f - l1; *w1 = l1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_pad_fwd_kernel(HB x, HB out) {
+  const int cvs = out.c >> 3;
+  const long long total = out.padded_pixels() * cvs;
+  const T* xb = reinterpret_cast<const T*>(x.ptr);
+  T* ob = reinterpret_cast<T*>(out.ptr);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % cvs);
+    long long pix = i / cvs;
+    int X = (int)(pix % out.wp);
+    long long r = pix / out.wp;
+    int Y = (int)(r % out.hp);
+    int n = (int)(r / out.hp);
+    int oy = reflect_idx(Y - out.halo, out.h), ox = reflect_idx(X - out.halo, out.w);
+    int y0, y1, x0, x1;
+    float wy0, wy1, wx0, wx1;
+    up_taps(oy, x.h, &y0, &y1, &wy0, &wy1);
+    up_taps(ox, x.w, &x0, &x1, &wx0, &wx1);
+    const int c0 = cv * 8;
+    float a[8], b[8], c[8], d[8], o[8];
+    Vec8<T>::load(xb + x.off(n, y0, x0) + c0, a);
+    Vec8<T>::load(xb + x.off(n, y0, x1) + c0, b);
+    Vec8<T>::load(xb + x.off(n, y1, x0) + c0, c);
+    Vec8<T>::load(xb + x.off(n, y1, x1) + c0, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = wy0 * (wx0 * a[e] + wx1 * b[e]) + wy1 * (wx0 * c[e] + wx1 * d[e]);
+    Vec8<T>::store(ob + out.off_padded(n, Y, X) + c0, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_pad_bwd_kernel(HB dout, HB dx) {
+  // dx interior (h,w); dout interior (2h,2w) with reflect halo to fold
+  const int cvs = dx.c >> 3;
+  const long long total = dx.padded_pixels() * cvs;
+  T* dxb = reinterpret_cast<T*>(dx.ptr);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % cvs);
+    long long pix = i / cvs;
+    int X = (int)(pix % dx.wp);
+    long long r = pix / dx.wp;
+    int Y = (int)(r % dx.hp);
+    int n = (int)(r / dx.hp);
+    const int iy = Y - dx.halo, ix = X - dx.halo;
+    const int c0 = cv * 8;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    if (iy >= 0 && iy < dx.h && ix >= 0 && ix < dx.w) {
+      for (int oy = max(0, 2 * iy - 1); oy <= min(dout.h - 1, 2 * iy + 2); ++oy) {
+        int y0, y1;
+        float wy0, wy1;
+        up_taps(oy, dx.h, &y0, &y1, &wy0, &wy1);
+        float wy = (y0 == iy ? wy0 : 0.f) + (y1 == iy ? wy1 : 0.f);
+        if (wy == 0.f) continue;
+        for (int ox = max(0, 2 * ix - 1); ox <= min(dout.w - 1, 2 * ix + 2); ++ox) {
+          int x0, x1;
+          float wx0, wx1;
+          up_taps(ox, dx.w, &x0, &x1, &wx0, &wx1);
+          float wx = (x0 == ix ? wx0 : 0.f) + (x1 == ix ? wx1 : 0.f);
+          if (wx == 0.f) continue;
+          float g[8];
+          fold_read8<T>(dout, n, oy, ox, c0, g);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += wy * wx * g[e];
+        }
+      }
+    }
+    Vec8<T>::store(dxb + dx.off_padded(n, Y, X) + c0, acc);
+  }
+}
+
+extern "C" int dwc_upsample_pad_fwd(const dwc_hbuf_t* x, const dwc_hbuf_t* out, dwc_stream_t stream) {
+  DWC_CHECK(x->c % 8 == 0 && out->h == 2 * x->h && out->w == 2 * x->w && out->c == x->c && out->n == x->n,
+            "dwc_upsample_pad_fwd: geometry mismatch");
+  HB hx(*x), ho(*out);
+  long long total = ho.padded_pixels() * (out->c / 8);
+  DISPATCH_T(x->dtype, (upsample_pad_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(hx, ho)));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int dwc_upsample_pad_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* dx, dwc_stream_t stream) {
+  DWC_CHECK(dx->c % 8 == 0 && dout->h == 2 * dx->h && dout->w == 2 * dx->w && dout->c == dx->c && dout->n == dx->n,
+            "dwc_upsample_pad_bwd: geometry mismatch");
+  HB hd(*dout), hx(*dx);
+  long long total = hx.padded_pixels() * (dx->c / 8);
+  DISPATCH_T(dx->dtype, (upsample_pad_bwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(hd, hx)));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// NCHW fp32 image <-> haloed NHWC buffer (optional 2x2 average pooling)
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void image_pad_fwd_kernel(const float* __restrict__ img, int C, int H, int W, int pool, HB out) {
+  const long long total = out.padded_pixels() * out.c;
+  T* ob = reinterpret_cast<T*>(out.ptr);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % out.c);
+    long long pix = i / out.c;
+    int X = (int)(pix % out.wp);
+    long long r = pix / out.wp;
+    int Y = (int)(r % out.hp);
+    int n = (int)(r / out.hp);
+    int iy = reflect_idx(Y - out.halo, out.h), ix = reflect_idx(X - out.halo, out.w);
+    float v = 0.f;
+    if (c < C) {
+      const float* p = img + ((long long)n * C + c) * H * W;
+      if (pool == 1) v = p[(long long)iy * W + ix];
+      else {
+        const float* q = p + (long long)(2 * iy) * W + 2 * ix;
+        v = 0.25f * (q[0] + q[1] + q[W] + q[W + 1]);
+      }
+    }
+    ob[out.off_padded(n, Y, X) + c] = from_f<T>(v);
+  }
+}
+
+template <typename T>
+__global__ void image_pad_bwd_kernel(HB dout, int pool, float* __restrict__ dimg, int C, int H, int W, int accumulate) {
+  const long long total = (long long)dout.n * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % W);
+    long long r = i / W;
+    int y = (int)(r % H);
+    r /= H;
+    int c = (int)(r % C);
+    int n = (int)(r / C);
+    float g = fold_read1<T>(dout, n, y / pool, x / pool, c);
+    if (pool == 2) g *= 0.25f;
+    dimg[i] = accumulate ? dimg[i] + g : g;
+  }
+}
+
+extern "C" int dwc_image_pad_fwd(const float* img, int n, int c, int h, int w, int pool, const dwc_hbuf_t* out,
+                                 dwc_stream_t stream) {
+  DWC_CHECK((pool == 1 || pool == 2) && out->h * pool == h && out->w * pool == w && out->n == n && out->c >= c,
+            "dwc_image_pad_fwd: geometry mismatch");
+  HB ho(*out);
+  long long total = ho.padded_pixels() * out->c;
+  DISPATCH_T(out->dtype, (image_pad_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(img, c, h, w, pool, ho)));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int dwc_image_pad_bwd(const dwc_hbuf_t* dout, int pool, float* dimg, int n, int c, int h, int w,
+                                 int accumulate, dwc_stream_t stream) {
+  DWC_CHECK((pool == 1 || pool == 2) && dout->h * pool == h && dout->w * pool == w && dout->n == n && dout->c >= c,
+            "dwc_image_pad_bwd: geometry mismatch");
+  HB hd(*dout);
+  long long total = (long long)n * c * h * w;
+  DISPATCH_T(dout->dtype,
+             (image_pad_bwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(hd, pool, dimg, c, h, w, accumulate)));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decoder heads (tanh | sigmoid) and attention blend
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void heads_fwd_kernel(HB y, float* __restrict__ img, float* __restrict__ att) {
+  const long long hw = (long long)y.h * y.w;
+  const long long total = (long long)y.n * hw;
+  const T* yb = reinterpret_cast<const T*>(y.ptr);
+  const int nc = y.c - 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(i / hw);
+    long long p = i - n * hw;
+    int py = (int)(p / y.w), px = (int)(p % y.w);
+    const T* q = yb + y.off(n, py, px);
+    for (int c = 0; c < nc; ++c) img[((long long)n * nc + c) * hw + p] = tanhf(to_f<T>(q[c]));
+    att[i] = 1.f / (1.f + __expf(-to_f<T>(q[nc])));
+  }
+}
+template <typename T>
+__global__ void heads_bwd_kernel(const float* __restrict__ dimg, const float* __restrict__ datt,
+                                 const float* __restrict__ img, const float* __restrict__ att, HB dy) {
+  const long long total = dy.padded_pixels();
+  const long long hw = (long long)dy.h * dy.w;
+  T* db = reinterpret_cast<T*>(dy.ptr);
+  const int nc = dy.c - 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int X = (int)(i % dy.wp);
+    long long r = i / dy.wp;
+    int Y = (int)(r % dy.hp);
+    int n = (int)(r / dy.hp);
+    int iy = Y - dy.halo, ix = X - dy.halo;
+    T* q = db + dy.off_padded(n, Y, X);
+    if (iy >= 0 && iy < dy.h && ix >= 0 && ix < dy.w) {
+      long long p = (long long)iy * dy.w + ix;
+      for (int c = 0; c < nc; ++c) {
+        long long k = ((long long)n * nc + c) * hw + p;
+        float t = img[k];
+        q[c] = from_f<T>(dimg ? dimg[k] * (1.f - t * t) : 0.f);
+      }
+      float a = att[(long long)n * hw + p];
+      q[nc] = from_f<T>(datt ? datt[(long long)n * hw + p] * a * (1.f - a) : 0.f);
+    } else {
+      for (int c = 0; c <= nc; ++c) q[c] = from_f<T>(0.f);
+    }
+  }
+}
+extern "C" int dwc_heads_fwd(const dwc_hbuf_t* y, float* img, float* att, dwc_stream_t stream) {
+  HB hy(*y);
+  long long total = (long long)y->n * y->h * y->w;
+  DISPATCH_T(y->dtype, (heads_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(hy, img, att)));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int dwc_heads_bwd(const float* dimg, const float* datt, const float* img, const float* att,
+                             const dwc_hbuf_t* dy, dwc_stream_t stream) {
+  HB hd(*dy);
+  DISPATCH_T(dy->dtype,
+             (heads_bwd_kernel<T><<<ew_grid(hd.padded_pixels()), 256, 0, as_stream(stream)>>>(dimg, datt, img, att, hd)));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void blend_fwd_kernel(const float* __restrict__ img, const float* __restrict__ att,
+                                 const float* __restrict__ real, float* __restrict__ out, int C, long long hw, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long n = i / (C * hw);
+    long long p = i % hw;
+    float a = att[n * hw + p];
+    out[i] = img[i] * a + real[i] * (1.f - a);
+  }
+}
+// one thread per (n, pixel): datt needs the sum over channels
+__global__ void blend_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ img,
+                                 const float* __restrict__ att, const float* __restrict__ real, float* __restrict__ dimg,
+                                 float* __restrict__ datt, int C, long long hw, long long total_np) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_np; i += (long long)gridDim.x * blockDim.x) {
+    long long n = i / hw, p = i % hw;
+    float a = att[i], s = 0.f;
+    for (int c = 0; c < C; ++c) {
+      long long k = (n * C + c) * hw + p;
+      float g = dout[k];
+      dimg[k] = g * a;
+      s += g * (img[k] - real[k]);
+    }
+    datt[i] = s;
+  }
+}
+extern "C" int dwc_blend_fwd(const float* img, const float* att, const float* real, float* out, int n, int c, int hw,
+                             dwc_stream_t stream) {
+  long long total = (long long)n * c * hw;
+  blend_fwd_kernel<<<ew_grid(total), 256, 0, as_stream(stream)>>>(img, att, real, out, c, hw, total);
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int dwc_blend_bwd(const float* dout, const float* img, const float* att, const float* real, float* dimg,
+                             float* datt, int n, int c, int hw, dwc_stream_t stream) {
+  long long total = (long long)n * hw;
+  blend_bwd_kernel<<<ew_grid(total), 256, 0, as_stream(stream)>>>(dout, img, att, real, dimg, datt, c, hw, total);
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ReLU + global average pool (style-encoder tail)
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void relu_gap_fwd_kernel(HB y, float* __restrict__ out) {
+  // one thread per (n, c)
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= y.n * y.c) return;
+  int n = i / y.c, c = i % y.c;
+  const T* yb = reinterpret_cast<const T*>(y.ptr);
+  float s = 0.f;
+  for (int py = 0; py < y.h; ++py)
+    for (int px = 0; px < y.w; ++px) {
+      float v = to_f<T>(yb[y.off(n, py, px) + c]);
+      s += v > 0.f ? v : 0.f;
+    }
+  out[i] = s / (float)(y.h * y.w);
+}
+template <typename T>
+__global__ void relu_gap_bwd_kernel(const float* __restrict__ dout, HB y, HB dy) {
+  const long long total = dy.padded_pixels() * dy.c;
+  const T* yb = reinterpret_cast<const T*>(y.ptr);
+  T* db = reinterpret_cast<T*>(dy.ptr);
+  const float inv = 1.f / (float)(y.h * y.w);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % dy.c);
+    long long pix = i / dy.c;
+    int X = (int)(pix % dy.wp);
+    long long r = pix / dy.wp;
+    int Y = (int)(r % dy.hp);
+    int n = (int)(r / dy.hp);
+    int iy = Y - dy.halo, ix = X - dy.halo;
+    float g = 0.f;
+    if (iy >= 0 && iy < dy.h && ix >= 0 && ix < dy.w) {
+      float v = to_f<T>(yb[y.off(n, iy, ix) + c]);
+      g = v > 0.f ? dout[(long long)n * dy.c + c] * inv : 0.f;
+    }
+    db[dy.off_padded(n, Y, X) + c] = from_f<T>(g);
+  }
+}
+extern "C" int dwc_relu_gap_fwd(const dwc_hbuf_t* y, float* out, dwc_stream_t stream) {
+  HB hy(*y);
+  DISPATCH_T(y->dtype, (relu_gap_fwd_kernel<T><<<cdiv(y->n * y->c, 128), 128, 0, as_stream(stream)>>>(hy, out)));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int dwc_relu_gap_bwd(const float* dout, const dwc_hbuf_t* y, const dwc_hbuf_t* dy, dwc_stream_t stream) {
+  HB hy(*y), hd(*dy);
+  long long total = hd.padded_pixels() * dy->c;
+  DISPATCH_T(y->dtype, (relu_gap_bwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(dout, hy, hd)));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}

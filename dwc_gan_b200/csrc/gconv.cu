@@ -1,0 +1,381 @@
+// gconv: convolution forward / data-gradient as a multi-tap shifted GEMM over haloed NHWC buffers.
+//
+//  * gconv_tc_kernel   : tcgen05 (UMMA) implicit GEMM.  A tiles (128 pixels x 64 channels) and weight tiles
+//                        (BN x 64) are staged by TMA (128B swizzle) through a 4-stage mbarrier ring, the
+//                        fp32 accumulator lives in TMEM, the epilogue reads it back with tcgen05.ld.
+//  * gconv_simt_kernel : CUDA-core version of the same abstract operation (fp32 validation mode, the
+//                        3-channel image layers and the 4-channel head gradients).
+#include "common.cuh"
+
+struct GConvDev {
+  const void* a;
+  const void* w;
+  const float* bias;
+  void* out;
+  long long a_dim[5];
+  long long a_str[5];
+  long long o_str[3];
+  int box_x, box_y, box_n;
+  int tiles_x, tiles_y, tiles_n;
+  int valid_x, valid_y, valid_n;
+  int flat, flat_img, flat_pitch, flat_h, flat_w;
+  int ntaps, C, K, ncols, ncols_padded;
+  int out_dtype, accumulate;
+  int taps[DWC_MAX_TAPS][3];
+};
+
+struct RowCoord {
+  int x, y, n;
+};
+
+__device__ __forceinline__ RowCoord tile_row(const GConvDev& p, int tile, int r) {
+  int tx = tile % p.tiles_x;
+  int t2 = tile / p.tiles_x;
+  int ty = t2 % p.tiles_y;
+  int tn = t2 / p.tiles_y;
+  RowCoord rc;
+  rc.x = tx * p.box_x + r % p.box_x;
+  int r2 = r / p.box_x;
+  rc.y = ty * p.box_y + r2 % p.box_y;
+  rc.n = tn * p.box_n + r2 / p.box_y;
+  return rc;
+}
+
+// where (and whether) a row is stored
+__device__ __forceinline__ bool out_offset(const GConvDev& p, const RowCoord& rc, long long* off) {
+  if (p.flat) {
+    int n = rc.x / p.flat_img;
+    int rem = rc.x - n * p.flat_img;
+    int yy = rem / p.flat_pitch;
+    int xx = rem - yy * p.flat_pitch;
+    if (n >= p.valid_n || yy >= p.flat_h || xx >= p.flat_w) return false;
+    *off = (long long)n * p.o_str[2] + (long long)yy * p.o_str[1] + (long long)xx * p.o_str[0];
+    return true;
+  }
+  if (rc.x >= p.valid_x || rc.y >= p.valid_y || rc.n >= p.valid_n) return false;
+  *off = (long long)rc.n * p.o_str[2] + (long long)rc.y * p.o_str[1] + (long long)rc.x * p.o_str[0];
+  return true;
+}
+
+// =====================================================================================================
+// SIMT kernel: 128 x 64 tile, 256 threads, each thread 8 rows x 4 columns, fp32 accumulate
+// =====================================================================================================
+constexpr int S_BM = 128, S_BN = 64, S_BK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) gconv_simt_kernel(const __grid_constant__ GConvDev p) {
+  __shared__ float As[S_BK][S_BM + 4];
+  __shared__ float Bs[S_BK][S_BN + 4];
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int col0 = blockIdx.y * S_BN;
+  const T* __restrict__ A = reinterpret_cast<const T*>(p.a);
+  const T* __restrict__ W = reinterpret_cast<const T*>(p.w);
+
+  // loader roles
+  const int lrow = tid >> 1;         // 0..127
+  const int lk = (tid & 1) * 8;      // 0 or 8
+  const RowCoord lrc = tile_row(p, tile, lrow);
+  const int bcol = tid >> 2;         // 0..63
+  const int bk = (tid & 3) * 4;      // 0,4,8,12
+  // compute roles
+  const int ty = tid >> 4, tx = tid & 15;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int C = p.C;
+  for (int t = 0; t < p.ntaps; ++t) {
+    const long long X = lrc.x + p.taps[t][0], Y = lrc.y + p.taps[t][1], Z = p.taps[t][2];
+    const bool inb = X >= 0 && X < p.a_dim[1] && Y >= 0 && Y < p.a_dim[2] && lrc.n < p.a_dim[4];
+    const long long abase = inb ? (lrc.n * p.a_str[4] + Z * p.a_str[3] + Y * p.a_str[2] + X * p.a_str[1]) : 0;
+    for (int c0 = 0; c0 < C; c0 += S_BK) {
+      // ---- stage A chunk
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int c = c0 + lk + j;
+        float v = 0.f;
+        if (inb && c < C) v = to_f<T>(A[abase + c]);
+        As[lk + j][lrow] = v;
+      }
+      // ---- stage B chunk
+      {
+        int col = col0 + bcol;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int c = c0 + bk + j;
+          float v = 0.f;
+          if (col < p.ncols_padded && c < C) v = to_f<T>(W[(long long)col * p.K + (long long)t * C + c]);
+          Bs[bk + j][bcol] = v;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < S_BK; ++k) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  // ---- epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    RowCoord rc = tile_row(p, tile, ty * 8 + i);
+    long long off;
+    if (!out_offset(p, rc, &off)) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int col = col0 + tx * 4 + j;
+      if (col >= p.ncols) continue;
+      float v = acc[i][j] + (p.bias ? p.bias[col] : 0.f);
+      if (p.out_dtype == DWC_F32) {
+        float* o = reinterpret_cast<float*>(p.out) + off + col;
+        *o = p.accumulate ? (*o + v) : v;
+      } else {
+        bf16* o = reinterpret_cast<bf16*>(p.out) + off + col;
+        *o = __float2bfloat16_rn(p.accumulate ? (__bfloat162float(*o) + v) : v);
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// tcgen05 kernel
+// =====================================================================================================
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;   // bf16 elements = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+
+template <int BN> struct TcCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int B_BYTES_AL = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES_AL) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS)
+    gconv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ GConvDev p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * (Cfg::A_BYTES + Cfg::B_BYTES_AL));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int col0 = blockIdx.y * BN;
+  const int cblocks = p.C / TC_BK;
+  const int num_kb = p.ntaps * cblocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int tx = tile % p.tiles_x;
+      int t2 = tile / p.tiles_x;
+      int ty = t2 % p.tiles_y;
+      int tn = t2 / p.tiles_y;
+      const int x0 = tx * p.box_x, y0 = ty * p.box_y, n0 = tn * p.box_n;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int cx = x0 + p.taps[t][0], cy = y0 + p.taps[t][1], cz = p.taps[t][2];
+        for (int cb = 0; cb < cblocks; ++cb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          tma_load_5d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * TC_BK, cx, cy, cz, n0);
+          tma_load_2d(sB + stage * Cfg::B_BYTES_AL, &tmB, &full_bar[stage], t * p.C + cb * TC_BK, col0);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN < 16 ? 16 : BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+        const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES_AL);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+          uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs retire
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ================= epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const RowCoord rc = tile_row(p, tile, r);
+    long long off = 0;
+    const bool valid = out_offset(p, rc, &off);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    constexpr int CHUNK = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+    for (int cc = 0; cc < BN; cc += CHUNK) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
+      if (CHUNK == 32) tmem_ld32(taddr, v);
+      else tmem_ld16(taddr, v);
+      tmem_ld_wait();
+      if (valid) {
+        const int cbase = col0 + cc;
+        if (p.out_dtype == DWC_BF16) {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + off + cbase;
+          if (cbase + CHUNK <= p.ncols && (p.ncols & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; j += 8) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + (p.bias ? __ldg(p.bias + cbase + j + e) : 0.f);
+              if (p.accumulate) {
+                float old[8];
+                Vec8<bf16>::load(o + j, old);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += old[e];
+              }
+              Vec8<bf16>::store(o + j, f);
+            }
+          } else {
+            for (int j = 0; j < CHUNK; ++j) {
+              if (cbase + j < p.ncols) {
+                float f = __uint_as_float(v[j]) + (p.bias ? p.bias[cbase + j] : 0.f);
+                if (p.accumulate) f += __bfloat162float(o[j]);
+                o[j] = __float2bfloat16_rn(f);
+              }
+            }
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + off + cbase;
+          for (int j = 0; j < CHUNK; ++j) {
+            if (cbase + j < p.ncols) {
+              float f = __uint_as_float(v[j]) + (p.bias ? p.bias[cbase + j] : 0.f);
+              if (p.accumulate) f += o[j];
+              o[j] = f;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// =====================================================================================================
+// host entry
+// =====================================================================================================
+template <int BN>
+static int launch_tc(const dwc_gconv_t* g, const GConvDev& d, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  CUtensorMap tmA, tmB;
+  if (dwc_make_tmap5(&tmA, g->a, g->a_dim, g->a_str, g->box[0], g->box[1], 1, g->box[2])) return 1;
+  if (dwc_make_tmap2(&tmB, g->w, g->ncols_padded, d.K, d.K, BN, TC_BK)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DWC_CUDA(cudaFuncSetAttribute(gconv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  dim3 grid(d.tiles_x * d.tiles_y * d.tiles_n, cdiv(g->ncols_padded, BN));
+  gconv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, d);
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
+  DWC_CHECK(g != nullptr, "dwc_gconv: null params");
+  DWC_CHECK(g->ntaps > 0 && g->ntaps <= DWC_MAX_TAPS, "dwc_gconv: ntaps %d out of range", g->ntaps);
+  DWC_CHECK(g->box[0] * g->box[1] * g->box[2] == 128, "dwc_gconv: box must cover 128 rows");
+  DWC_CHECK(g->a_str[0] == 1, "dwc_gconv: channel stride must be 1");
+  GConvDev d;
+  memset(&d, 0, sizeof(d));
+  d.a = g->a; d.w = g->w; d.bias = g->bias; d.out = g->out;
+  for (int i = 0; i < 5; ++i) { d.a_dim[i] = g->a_dim[i]; d.a_str[i] = g->a_str[i]; }
+  for (int i = 0; i < 3; ++i) d.o_str[i] = g->o_str[i];
+  d.box_x = g->box[0]; d.box_y = g->box[1]; d.box_n = g->box[2];
+  d.tiles_x = g->tiles[0]; d.tiles_y = g->tiles[1]; d.tiles_n = g->tiles[2];
+  d.valid_x = g->valid[0]; d.valid_y = g->valid[1]; d.valid_n = g->valid[2];
+  d.flat = g->flat; d.flat_img = g->flat_img; d.flat_pitch = g->flat_pitch; d.flat_h = g->flat_h; d.flat_w = g->flat_w;
+  d.ntaps = g->ntaps; d.C = (int)g->a_dim[0]; d.K = g->ntaps * d.C;
+  d.ncols = g->ncols; d.ncols_padded = g->ncols_padded;
+  d.out_dtype = g->out_dtype; d.accumulate = g->accumulate;
+  for (int t = 0; t < g->ntaps; ++t)
+    for (int j = 0; j < 3; ++j) d.taps[t][j] = g->taps[t * 3 + j];
+  cudaStream_t st = as_stream(stream);
+  const long long ntiles = (long long)d.tiles_x * d.tiles_y * d.tiles_n;
+  DWC_CHECK(ntiles > 0 && ntiles < 2147483647LL, "dwc_gconv: bad tile count");
+
+  if (g->backend == DWC_TC) {
+    DWC_CHECK(g->dtype == DWC_BF16, "dwc_gconv: tcgen05 backend needs bf16 operands");
+    DWC_CHECK(d.C % TC_BK == 0, "dwc_gconv: tcgen05 backend needs C %% 64 == 0 (C=%d)", d.C);
+    const int np = g->ncols_padded;
+    if (np % 256 == 0) return launch_tc<256>(g, d, st);
+    if (np % 128 == 0) return launch_tc<128>(g, d, st);
+    if (np % 64 == 0) return launch_tc<64>(g, d, st);
+    if (np == 16) return launch_tc<16>(g, d, st);
+    DWC_CHECK(false, "dwc_gconv: unsupported padded column count %d for tcgen05", np);
+  }
+  dim3 grid((unsigned)ntiles, cdiv(g->ncols, S_BN));
+  if (g->dtype == DWC_F32)
+    gconv_simt_kernel<float><<<grid, 256, 0, st>>>(d);
+  else
+    gconv_simt_kernel<bf16><<<grid, 256, 0, st>>>(d);
+  DWC_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,440 @@
+// wgrad: convolution weight gradient  dW[ia, tap, ib] = sum_pixels dY[pix, ia] * Xpad[pix + tap, ib]
+//
+//  * wgrad_tc_kernel   : tcgen05 GEMM whose K dimension is the pixel index.  Both operands are NHWC tiles
+//                        (64 pixels x 64 channels, channel-contiguous) staged by TMA, i.e. "MN-major" UMMA
+//                        operands; the 128 x BN fp32 accumulator of one (tap, channel-block) pair lives in
+//                        TMEM while the CTA streams its share of the pixels (split-K).
+//  * wgrad_simt_kernel : CUDA-core version (fp32 validation mode and the 3 / 4 channel layers).
+//  Partial sums are written to a workspace and reduced in a fixed order (deterministic).
+#include "common.cuh"
+
+struct WgradDev {
+  const void* m_ptr;   // operand whose channels become accumulator rows
+  const void* n_ptr;   // operand whose channels become accumulator columns
+  long long m_dim[5], m_str[5], n_dim[5], n_str[5];
+  int m_tap, n_tap;    // which operand the tap offsets apply to
+  int cm, cn;
+  int box_x, box_y, box_n;
+  int tiles_x, tiles_y, tiles_n;
+  int ntiles, splits, tiles_per_split;
+  int ntaps;
+  float* ws;           // [split][tap][cm][cn]
+  int taps[DWC_MAX_TAPS][3];
+};
+
+__device__ __forceinline__ void wg_tile_origin(const WgradDev& p, int tile, int* x0, int* y0, int* n0) {
+  int tx = tile % p.tiles_x;
+  int t2 = tile / p.tiles_x;
+  *x0 = tx * p.box_x;
+  *y0 = (t2 % p.tiles_y) * p.box_y;
+  *n0 = (t2 / p.tiles_y) * p.box_n;
+}
+
+// =====================================================================================================
+// SIMT: 64 x 64 output tile per CTA, 256 threads x (4 x 4), K = pixels in chunks of 16
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(const __grid_constant__ WgradDev p) {
+  __shared__ float Ms[16][64 + 4];
+  __shared__ float Ns[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int mblocks = (p.cm + 63) / 64, nblocks = (p.cn + 63) / 64;
+  int wid = blockIdx.x;
+  const int mb = wid % mblocks; wid /= mblocks;
+  const int nb = wid % nblocks; wid /= nblocks;
+  const int t = wid;
+  const int split = blockIdx.y;
+  const T* __restrict__ Mp = reinterpret_cast<const T*>(p.m_ptr);
+  const T* __restrict__ Np = reinterpret_cast<const T*>(p.n_ptr);
+  const int ty = tid >> 4, tx = tid & 15;
+  const int lpix = tid >> 4;          // 0..15 pixel within chunk
+  const int lch = (tid & 15) * 4;     // 4 channels
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int mdx = p.m_tap ? p.taps[t][0] : 0, mdy = p.m_tap ? p.taps[t][1] : 0, mdz = p.m_tap ? p.taps[t][2] : 0;
+  const int ndx = p.n_tap ? p.taps[t][0] : 0, ndy = p.n_tap ? p.taps[t][1] : 0, ndz = p.n_tap ? p.taps[t][2] : 0;
+  const int tile_begin = split * p.tiles_per_split;
+  const int tile_end = min(p.ntiles, tile_begin + p.tiles_per_split);
+  const int rows = p.box_x * p.box_y * p.box_n;
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    int x0, y0, n0;
+    wg_tile_origin(p, tile, &x0, &y0, &n0);
+    for (int r0 = 0; r0 < rows; r0 += 16) {
+      int r = r0 + lpix;
+      int x = x0 + r % p.box_x;
+      int r2 = r / p.box_x;
+      int y = y0 + r2 % p.box_y;
+      int n = n0 + r2 / p.box_y;
+      {
+        long long X = x + mdx, Y = y + mdy;
+        bool inb = r < rows && X >= 0 && X < p.m_dim[1] && Y >= 0 && Y < p.m_dim[2] && n < p.m_dim[4];
+        long long base = n * p.m_str[4] + (long long)mdz * p.m_str[3] + Y * p.m_str[2] + X * p.m_str[1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int ch = mb * 64 + lch + j;
+          Ms[lpix][lch + j] = (inb && ch < p.cm) ? to_f<T>(Mp[base + ch]) : 0.f;
+        }
+      }
+      {
+        long long X = x + ndx, Y = y + ndy;
+        bool inb = r < rows && X >= 0 && X < p.n_dim[1] && Y >= 0 && Y < p.n_dim[2] && n < p.n_dim[4];
+        long long base = n * p.n_str[4] + (long long)ndz * p.n_str[3] + Y * p.n_str[2] + X * p.n_str[1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int ch = nb * 64 + lch + j;
+          Ns[lpix][lch + j] = (inb && ch < p.cn) ? to_f<T>(Np[base + ch]) : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float4 a = *reinterpret_cast<const float4*>(&Ms[k][ty * 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Ns[k][tx * 4]);
+        float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  float* ws = p.ws + ((long long)split * p.ntaps + t) * p.cm * p.cn;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = mb * 64 + ty * 4 + i;
+    if (m >= p.cm) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = nb * 64 + tx * 4 + j;
+      if (n < p.cn) ws[(long long)m * p.cn + n] = acc[i][j];
+    }
+  }
+}
+
+// =====================================================================================================
+// tcgen05: M = 128 channels of the M operand, N = BN channels of the N operand, K = 64 pixels / stage
+// =====================================================================================================
+constexpr int WG_PIX = 64;                      // pixels per stage (K extent)
+constexpr int WG_BOX_BYTES = WG_PIX * 128;      // one (64 pixel x 64 channel) TMA box = 8 KB
+constexpr int WG_THREADS = 192;
+
+template <int BN> struct WgCfg {
+  static constexpr int M_BYTES = 2 * WG_BOX_BYTES;          // 128 channels
+  static constexpr int N_BYTES = (BN / 64) * WG_BOX_BYTES;
+  static constexpr int STAGE = M_BYTES + N_BYTES;
+  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 5 : 6);
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS)
+    wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
+                    const __grid_constant__ WgradDev p) {
+  using Cfg = WgCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mblocks = p.cm / 128, nblocks = p.cn / BN;
+  int wid = blockIdx.x;
+  const int mb = wid % mblocks; wid /= mblocks;
+  const int nb = wid % nblocks; wid /= nblocks;
+  const int t = wid;
+  const int split = blockIdx.y;
+  const int tile_begin = split * p.tiles_per_split;
+  const int tile_end = min(p.ntiles, tile_begin + p.tiles_per_split);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmM);
+    tma_prefetch_desc(&tmN);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int mdx = p.m_tap ? p.taps[t][0] : 0, mdy = p.m_tap ? p.taps[t][1] : 0, mdz = p.m_tap ? p.taps[t][2] : 0;
+      const int ndx = p.n_tap ? p.taps[t][0] : 0, ndy = p.n_tap ? p.taps[t][1] : 0, ndz = p.n_tap ? p.taps[t][2] : 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        int x0, y0, n0;
+        wg_tile_origin(p, tile, &x0, &y0, &n0);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], Cfg::STAGE);
+        uint8_t* s = smem + stage * Cfg::STAGE;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tma_load_5d(s + j * WG_BOX_BYTES, &tmM, &full_bar[stage], mb * 128 + j * 64, x0 + mdx, y0 + mdy, mdz, n0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_5d(s + Cfg::M_BYTES + j * WG_BOX_BYTES, &tmN, &full_bar[stage], nb * BN + j * 64, x0 + ndx,
+                      y0 + ndy, ndz, n0);
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);   // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t first = 1;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t m_addr = smem_u32(smem + stage * Cfg::STAGE);
+        const uint32_t n_addr = m_addr + Cfg::M_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_PIX / 16; ++k) {
+          // MN-major SW128: 64-channel atoms LBO apart, 8-pixel groups SBO = 1024 B apart
+          uint64_t da = umma_desc_sw128(m_addr + k * 2048, WG_BOX_BYTES, 1024);
+          uint64_t db = umma_desc_sw128(n_addr + k * 2048, WG_BOX_BYTES, 1024);
+          umma_bf16(tmem_base, da, db, idesc, first ? 0u : 1u);
+          first = 0;
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = mb * 128 + q * 32 + lane;
+    float* ws = p.ws + (((long long)split * p.ntaps + t) * p.cm + m) * p.cn + nb * BN;
+    if (tile_end > tile_begin) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(ws + cc + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                          __uint_as_float(v[j + 3]));
+      }
+    } else {
+      for (int cc = 0; cc < BN; cc += 4) *reinterpret_cast<float4*>(ws + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// dw[m*s_m + t*s_t + n*s_n] (+)= sum_s ws[s][t][m][n]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int ntaps, int cm, int cn, float* dw,
+                                    long long s_m, long long s_t, long long s_n, int accumulate) {
+  const long long total = (long long)ntaps * cm * cn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += ws[k * total + i];
+    int n = (int)(i % cn);
+    long long r = i / cn;
+    int m = (int)(r % cm);
+    int t = (int)(r / cm);
+    float* o = dw + m * s_m + t * s_t + n * s_n;
+    *o = accumulate ? (*o + s) : s;
+  }
+}
+
+// bias gradient: column sums of A over all pixels, two deterministic stages
+constexpr int DB_SPLITS = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) dbias_partial_kernel(const __grid_constant__ WgradDev p, const T* __restrict__ A,
+                                                            const long long* dimstr /*unused*/, float* part, int ca) {
+  // grid: (ceil(ca/32), DB_SPLITS); thread = (pixel lane 0..7, channel 0..31)
+  __shared__ float red[8][33];
+  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int pl = threadIdx.x >> 5;
+  const int rows = p.box_x * p.box_y * p.box_n;
+  float s = 0.f;
+  for (int tile = blockIdx.y; tile < p.ntiles; tile += DB_SPLITS) {
+    int x0, y0, n0;
+    wg_tile_origin(p, tile, &x0, &y0, &n0);
+    for (int r = pl; r < rows; r += 8) {
+      int x = x0 + r % p.box_x;
+      int r2 = r / p.box_x;
+      int y = y0 + r2 % p.box_y;
+      int n = n0 + r2 / p.box_y;
+      // dY is always the untapped operand
+      const long long* dim = p.m_tap ? p.n_dim : p.m_dim;
+      const long long* str = p.m_tap ? p.n_str : p.m_str;
+      if (ch < ca && x < dim[1] && y < dim[2] && n < dim[4]) s += to_f<T>(A[n * str[4] + y * str[2] + x * str[1] + ch]);
+    }
+  }
+  red[pl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (pl == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x];
+    if (ch < ca) part[(long long)blockIdx.y * ca + ch] = tot;
+  }
+}
+__global__ void dbias_final_kernel(const float* part, int ca, float* dbias, int accumulate) {
+  int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= ca) return;
+  float s = 0.f;
+  for (int k = 0; k < DB_SPLITS; ++k) s += part[(long long)k * ca + ch];
+  dbias[ch] = accumulate ? dbias[ch] + s : s;
+}
+
+// =====================================================================================================
+// host
+// =====================================================================================================
+struct WgPlan {
+  bool swap;
+  int cm, cn, bn, splits, tiles_per_split, ntiles, items;
+};
+
+static int wg_plan(const dwc_wgrad_t* g, WgPlan* pl) {
+  pl->ntiles = g->tiles[0] * g->tiles[1] * g->tiles[2];
+  if (g->backend == DWC_TC) {
+    // accumulator rows need a multiple of 128 channels
+    pl->swap = (g->ca % 128 != 0);
+    pl->cm = pl->swap ? g->cb : g->ca;
+    pl->cn = pl->swap ? g->ca : g->cb;
+    DWC_CHECK(pl->cm % 128 == 0 && pl->cn % 64 == 0, "dwc_wgrad: tcgen05 needs channel counts (%d,%d) with one %%128==0, other %%64==0",
+              g->ca, g->cb);
+    pl->bn = pl->cn % 256 == 0 ? 256 : (pl->cn % 128 == 0 ? 128 : 64);
+    pl->items = (pl->cm / 128) * (pl->cn / pl->bn) * g->ntaps;
+  } else {
+    pl->swap = false;
+    pl->cm = g->ca;
+    pl->cn = g->cb;
+    pl->bn = 64;
+    pl->items = cdiv(pl->cm, 64) * cdiv(pl->cn, 64) * g->ntaps;
+  }
+  int want = cdiv(2 * dwc_num_sms(), pl->items);
+  if (want < 1) want = 1;
+  if (want > pl->ntiles) want = pl->ntiles;
+  if (want > 64) want = 64;
+  pl->tiles_per_split = cdiv(pl->ntiles, want);
+  pl->splits = cdiv(pl->ntiles, pl->tiles_per_split);
+  return 0;
+}
+
+extern "C" int64_t dwc_wgrad_workspace_bytes(const dwc_wgrad_t* g) {
+  WgPlan pl;
+  if (wg_plan(g, &pl)) return -1;
+  int64_t ws = (int64_t)pl.splits * g->ntaps * pl.cm * pl.cn * 4;
+  ws += (int64_t)DB_SPLITS * g->ca * 4;
+  return ws;
+}
+
+template <int BN>
+static int launch_wg_tc(const dwc_wgrad_t* g, const WgradDev& d, const WgPlan& pl, cudaStream_t st) {
+  using Cfg = WgCfg<BN>;
+  CUtensorMap tmM, tmN;
+  const bool sw = pl.swap;
+  if (dwc_make_tmap5(&tmM, sw ? g->b : g->a, sw ? g->b_dim : g->a_dim, sw ? g->b_str : g->a_str, g->box[0], g->box[1],
+                     1, g->box[2]))
+    return 1;
+  if (dwc_make_tmap5(&tmN, sw ? g->a : g->b, sw ? g->a_dim : g->b_dim, sw ? g->a_str : g->b_str, g->box[0], g->box[1],
+                     1, g->box[2]))
+    return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DWC_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  dim3 grid(pl.items, pl.splits);
+  wgrad_tc_kernel<BN><<<grid, WG_THREADS, Cfg::SMEM, st>>>(tmM, tmN, d);
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dwc_wgrad(const dwc_wgrad_t* g, dwc_stream_t stream) {
+  DWC_CHECK(g != nullptr, "dwc_wgrad: null params");
+  DWC_CHECK(g->ntaps > 0 && g->ntaps <= DWC_MAX_TAPS, "dwc_wgrad: ntaps out of range");
+  WgPlan pl;
+  if (wg_plan(g, &pl)) return 1;
+  const int64_t need = dwc_wgrad_workspace_bytes(g);
+  DWC_CHECK(g->workspace != nullptr && g->workspace_bytes >= need, "dwc_wgrad: workspace too small (%lld < %lld)",
+            (long long)g->workspace_bytes, (long long)need);
+  if (g->backend == DWC_TC)
+    DWC_CHECK(g->box[0] * g->box[1] * g->box[2] == WG_PIX && g->dtype == DWC_BF16,
+              "dwc_wgrad: tcgen05 needs bf16 and 64-pixel boxes");
+  WgradDev d;
+  memset(&d, 0, sizeof(d));
+  const bool sw = pl.swap;
+  d.m_ptr = sw ? g->b : g->a;
+  d.n_ptr = sw ? g->a : g->b;
+  for (int i = 0; i < 5; ++i) {
+    d.m_dim[i] = sw ? g->b_dim[i] : g->a_dim[i];
+    d.m_str[i] = sw ? g->b_str[i] : g->a_str[i];
+    d.n_dim[i] = sw ? g->a_dim[i] : g->b_dim[i];
+    d.n_str[i] = sw ? g->a_str[i] : g->b_str[i];
+  }
+  d.m_tap = sw ? 1 : 0;
+  d.n_tap = sw ? 0 : 1;
+  d.cm = pl.cm; d.cn = pl.cn;
+  d.box_x = g->box[0]; d.box_y = g->box[1]; d.box_n = g->box[2];
+  d.tiles_x = g->tiles[0]; d.tiles_y = g->tiles[1]; d.tiles_n = g->tiles[2];
+  d.ntiles = pl.ntiles; d.splits = pl.splits; d.tiles_per_split = pl.tiles_per_split;
+  d.ntaps = g->ntaps;
+  d.ws = g->workspace;
+  for (int t = 0; t < g->ntaps; ++t)
+    for (int j = 0; j < 3; ++j) d.taps[t][j] = g->taps[t * 3 + j];
+  cudaStream_t st = as_stream(stream);
+
+  if (g->backend == DWC_TC) {
+    int rc;
+    if (pl.bn == 256) rc = launch_wg_tc<256>(g, d, pl, st);
+    else if (pl.bn == 128) rc = launch_wg_tc<128>(g, d, pl, st);
+    else rc = launch_wg_tc<64>(g, d, pl, st);
+    if (rc) return rc;
+  } else {
+    dim3 grid(pl.items, pl.splits);
+    if (g->dtype == DWC_F32) wgrad_simt_kernel<float><<<grid, 256, 0, st>>>(d);
+    else wgrad_simt_kernel<bf16><<<grid, 256, 0, st>>>(d);
+    DWC_LAUNCH_CHECK();
+  }
+  const long long total = (long long)g->ntaps * pl.cm * pl.cn;
+  wgrad_reduce_kernel<<<cdiv(total, 256 * 4) > 1184 ? 1184 : cdiv(total, 256 * 4), 256, 0, st>>>(
+      g->workspace, pl.splits, g->ntaps, pl.cm, pl.cn, g->dw, sw ? g->s_b : g->s_a, g->s_t, sw ? g->s_a : g->s_b,
+      g->accumulate);
+  DWC_LAUNCH_CHECK();
+  if (g->dbias) {
+    float* part = g->workspace + (int64_t)pl.splits * g->ntaps * pl.cm * pl.cn;
+    dim3 grid(cdiv(g->ca, 32), DB_SPLITS);
+    if (g->dtype == DWC_F32)
+      dbias_partial_kernel<float><<<grid, 256, 0, st>>>(d, reinterpret_cast<const float*>(g->a), nullptr, part, g->ca);
+    else
+      dbias_partial_kernel<bf16><<<grid, 256, 0, st>>>(d, reinterpret_cast<const bf16*>(g->a), nullptr, part, g->ca);
+    DWC_LAUNCH_CHECK();
+    dbias_final_kernel<<<cdiv(g->ca, 128), 128, 0, st>>>(part, g->ca, g->dbias, g->accumulate);
+    DWC_LAUNCH_CHECK();
+  }
+  return 0;
+}

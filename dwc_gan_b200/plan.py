@@ -1,0 +1,289 @@
+"""Geometry of the haloed NHWC buffers and the gconv / wgrad launch plans.
+
+A convolution of the reference (reflect-pad + nn.Conv2d, networks/networks.py:531,577-580) becomes
+  forward : gconv over the reflect-haloed input (4-D boxes of 128 output pixels),
+  dgrad   : gconv over the zero-haloed output gradient in "flat" mode (tap = constant row offset);
+            stride-2 4x4 convs split into the four parity planes of the padded input,
+  wgrad   : pixel-reduction GEMM between the output gradient and the shifted padded input.
+The plans are plain Python objects so that tests can execute them with a CPU emulator
+(tests/emu.py) without a GPU; `launch()` turns them into the C-ABI structs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _pow2_floor(v: int) -> int:
+    p = 1
+    while p * 2 <= v:
+        p *= 2
+    return p
+
+
+def choose_box(w: int, h: int, n: int, rows: int) -> Tuple[int, int, int]:
+    """(bx, by, bn) with bx*by*bn == rows covering a (w, h, n) pixel grid with little waste."""
+    bx = min(_pow2_floor(w), rows)
+    by = min(_pow2_floor(h), rows // bx)
+    bn = rows // (bx * by)
+    return bx, by, bn
+
+
+class HB:
+    """Haloed NHWC activation buffer.  layout 0: [N, H+2h, W+2h, C]; layout 1: four parity planes
+    [N, 4, (H+2h)/2, (W+2h)/2, C] (input of a stride-2 conv)."""
+
+    __slots__ = ("t", "n", "h", "w", "c", "halo", "layout")
+
+    def __init__(self, t, n, h, w, c, halo, layout=0):
+        self.t, self.n, self.h, self.w, self.c, self.halo, self.layout = t, n, h, w, c, halo, layout
+
+    @staticmethod
+    def shape_of(n, h, w, c, halo, layout=0):
+        hp, wp = h + 2 * halo, w + 2 * halo
+        if layout == 0:
+            return (n, hp, wp, c)
+        assert hp % 2 == 0 and wp % 2 == 0
+        return (n, 4, hp // 2, wp // 2, c)
+
+    @classmethod
+    def empty(cls, n, h, w, c, halo, layout, dtype, device, zero=False):
+        shape = cls.shape_of(n, h, w, c, halo, layout)
+        t = torch.zeros(shape, dtype=dtype, device=device) if zero else torch.empty(shape, dtype=dtype, device=device)
+        return cls(t, n, h, w, c, halo, layout)
+
+    def like(self, t):
+        return HB(t, self.n, self.h, self.w, self.c, self.halo, self.layout)
+
+    @property
+    def hp(self):
+        return self.h + 2 * self.halo
+
+    @property
+    def wp(self):
+        return self.w + 2 * self.halo
+
+    def struct(self):
+        assert self.t.is_contiguous()
+        return L.HBuf(self.t.data_ptr(), self.n, self.h, self.w, self.c, self.halo, self.layout, L.dt(self.t))
+
+    def interior(self):
+        """[N, H, W, C] strided view of the interior (plain layout only)."""
+        assert self.layout == 0
+        h = self.halo
+        return self.t[:, h:h + self.h, h:h + self.w, :]
+
+    def interior_offset(self):
+        assert self.layout == 0
+        return (self.halo * self.wp + self.halo) * self.c
+
+    def padded_nhwc(self):
+        """[N, Hp, Wp, C] tensor of the padded image (gathers the parity planes if needed)."""
+        if self.layout == 0:
+            return self.t
+        n, _, hq, wq, c = self.t.shape
+        out = self.t.new_empty(n, hq * 2, wq * 2, c)
+        for py in range(2):
+            for px in range(2):
+                out[:, py::2, px::2, :] = self.t[:, py * 2 + px]
+        return out
+
+
+@dataclass
+class GConvPlan:
+    a: torch.Tensor                # storage tensor of the A operand
+    a_off: int                     # element offset of the view origin inside `a`
+    a_dim: Tuple[int, ...]         # C, X, Y, Z, N
+    a_str: Tuple[int, ...]
+    box: Tuple[int, int, int]
+    tiles: Tuple[int, int, int]
+    valid: Tuple[int, int, int]
+    flat: Tuple[int, int, int, int, int]   # flag, img rows, pitch, h, w
+    taps: List[Tuple[int, int, int]]
+    w: torch.Tensor                # [ncols_padded, ntaps*C]
+    w_off: int
+    ncols: int
+    ncols_padded: int
+    bias: Optional[torch.Tensor]
+    out: torch.Tensor
+    out_off: int
+    o_str: Tuple[int, int, int]
+    accumulate: bool = False
+    backend: int = L.SIMT
+
+    def launch(self):
+        g = L.GConv()
+        es = self.a.element_size()
+        g.dtype = L.dt(self.a)
+        g.backend = self.backend
+        g.a = self.a.data_ptr() + self.a_off * es
+        g.a_dim = (C.c_int64 * 5)(*self.a_dim)
+        g.a_str = (C.c_int64 * 5)(*self.a_str)
+        g.box = (C.c_int32 * 3)(*self.box)
+        g.tiles = (C.c_int32 * 3)(*self.tiles)
+        g.valid = (C.c_int32 * 3)(*self.valid)
+        g.flat, g.flat_img, g.flat_pitch, g.flat_h, g.flat_w = self.flat
+        g.ntaps = len(self.taps)
+        flat_taps = [v for t in self.taps for v in t]
+        taps_arr = (C.c_int32 * len(flat_taps))(*flat_taps)
+        g.taps = C.cast(taps_arr, C.POINTER(C.c_int32))
+        g.w = self.w.data_ptr() + self.w_off * self.w.element_size()
+        g.ncols, g.ncols_padded = self.ncols, self.ncols_padded
+        g.bias = self.bias.data_ptr() if self.bias is not None else 0
+        g.out = self.out.data_ptr() + self.out_off * self.out.element_size()
+        g.o_str = (C.c_int64 * 3)(*self.o_str)
+        g.out_dtype = L.dt(self.out)
+        g.accumulate = int(self.accumulate)
+        L.check(L.lib().dwc_gconv(C.byref(g), L.stream()), "gconv")
+
+
+@dataclass
+class WGradPlan:
+    a: torch.Tensor
+    a_off: int
+    a_dim: Tuple[int, ...]
+    a_str: Tuple[int, ...]
+    b: torch.Tensor
+    b_off: int
+    b_dim: Tuple[int, ...]
+    b_str: Tuple[int, ...]
+    box: Tuple[int, int, int]
+    tiles: Tuple[int, int, int]
+    taps: List[Tuple[int, int, int]]
+    ca: int
+    cb: int
+    dw: torch.Tensor               # fp32 gradient buffer, element (ia, t, ib) at ia*s_a + t*s_t + ib*s_b
+    s_a: int
+    s_t: int
+    s_b: int
+    dbias: Optional[torch.Tensor]
+    accumulate: bool = True
+    backend: int = L.SIMT
+
+    def _struct(self, workspace=None):
+        g = L.WGrad()
+        es = self.a.element_size()
+        g.dtype = L.dt(self.a)
+        g.backend = self.backend
+        g.a = self.a.data_ptr() + self.a_off * es
+        g.a_dim = (C.c_int64 * 5)(*self.a_dim)
+        g.a_str = (C.c_int64 * 5)(*self.a_str)
+        g.b = self.b.data_ptr() + self.b_off * es
+        g.b_dim = (C.c_int64 * 5)(*self.b_dim)
+        g.b_str = (C.c_int64 * 5)(*self.b_str)
+        g.box = (C.c_int32 * 3)(*self.box)
+        g.tiles = (C.c_int32 * 3)(*self.tiles)
+        g.ntaps = len(self.taps)
+        flat_taps = [v for t in self.taps for v in t]
+        self._taps_arr = (C.c_int32 * len(flat_taps))(*flat_taps)
+        g.taps = C.cast(self._taps_arr, C.POINTER(C.c_int32))
+        g.ca, g.cb = self.ca, self.cb
+        g.dw = self.dw.data_ptr()
+        g.s_a, g.s_t, g.s_b = self.s_a, self.s_t, self.s_b
+        g.dbias = self.dbias.data_ptr() if self.dbias is not None else 0
+        g.accumulate = int(self.accumulate)
+        if workspace is not None:
+            g.workspace = workspace.data_ptr()
+            g.workspace_bytes = workspace.numel() * workspace.element_size()
+        return g
+
+    def workspace_bytes(self):
+        return int(L.lib().dwc_wgrad_workspace_bytes(C.byref(self._struct())))
+
+    def launch(self, workspace_fn):
+        need = self.workspace_bytes()
+        ws = workspace_fn(need)
+        L.check(L.lib().dwc_wgrad(C.byref(self._struct(ws)), L.stream()), "wgrad")
+
+
+# --------------------------------------------------------------------------------------------
+# plan builders
+# --------------------------------------------------------------------------------------------
+
+def conv_taps(k: int, stride: int) -> List[Tuple[int, int, int]]:
+    """(dx, dy, z) per filter tap in (kh, kw) order for the forward / wgrad B operand."""
+    taps = []
+    for kh in range(k):
+        for kw in range(k):
+            if stride == 1:
+                taps.append((kw, kh, 0))
+            else:
+                taps.append((kw // 2, kh // 2, (kh % 2) * 2 + (kw % 2)))
+    return taps
+
+
+def input_view(xp: HB):
+    """rank-5 (C, X, Y, Z, N) dims/strides of a padded input buffer."""
+    c = xp.c
+    if xp.layout == 0:
+        return (c, xp.wp, xp.hp, 1, xp.n), (1, c, xp.wp * c, xp.hp * xp.wp * c, xp.hp * xp.wp * c)
+    hq, wq = xp.hp // 2, xp.wp // 2
+    return (c, wq, hq, 4, xp.n), (1, c, wq * c, hq * wq * c, 4 * hq * wq * c)
+
+
+def out_size(xp: HB, k: int, stride: int):
+    return (xp.hp - k) // stride + 1, (xp.wp - k) // stride + 1
+
+
+def plan_conv_fwd(xp: HB, w_packed, ncols, ncols_padded, bias, y: HB, k, stride, backend) -> GConvPlan:
+    ho, wo = out_size(xp, k, stride)
+    assert (y.h, y.w, y.n) == (ho, wo, xp.n) and y.layout == 0, ((y.h, y.w), (ho, wo))
+    assert (stride == 1 and xp.layout == 0) or (stride == 2 and xp.layout == 1 and k == 4)
+    dims, strs = input_view(xp)
+    box = choose_box(wo, ho, xp.n, 128)
+    tiles = (-(-wo // box[0]), -(-ho // box[1]), -(-xp.n // box[2]))
+    cy = y.c
+    return GConvPlan(a=xp.t, a_off=0, a_dim=dims, a_str=strs, box=box, tiles=tiles, valid=(wo, ho, xp.n),
+                     flat=(0, 0, 0, 0, 0), taps=conv_taps(k, stride), w=w_packed, w_off=0, ncols=ncols,
+                     ncols_padded=ncols_padded, bias=bias, out=y.t, out_off=y.interior_offset(),
+                     o_str=(cy, y.wp * cy, y.hp * y.wp * cy), backend=backend)
+
+
+def plan_conv_dgrad(dy: HB, w_packed, dxp: HB, k, stride, backend, cin_padded=None) -> List[GConvPlan]:
+    """dy: zero-haloed output gradient (halo k-1 for stride 1, 1 for the stride-2 4x4 conv).
+    dxp: gradient of the padded input (same geometry as the forward input buffer); fully overwritten."""
+    cout, cin = dy.c, dxp.c
+    cin_padded = cin_padded or cin
+    rows = dy.n * dy.hp * dy.wp
+    tiles = (-(-rows // 128), 1, 1)
+    a_dim = (cout, rows, 1, 1, 1)
+    a_str = (1, cout, rows * cout, rows * cout, rows * cout)
+    plans = []
+    if stride == 1:
+        assert dy.halo == k - 1 and dxp.layout == 0
+        taps = [(kh * dy.wp + kw, 0, 0) for kh in range(k) for kw in range(k)]
+        plans.append(GConvPlan(a=dy.t, a_off=0, a_dim=a_dim, a_str=a_str, box=(128, 1, 1), tiles=tiles,
+                               valid=(rows, 1, dy.n), flat=(1, dy.hp * dy.wp, dy.wp, dxp.hp, dxp.wp), taps=taps,
+                               w=w_packed, w_off=0, ncols=cin, ncols_padded=cin_padded, bias=None, out=dxp.t, out_off=0,
+                               o_str=(cin, dxp.wp * cin, dxp.hp * dxp.wp * cin), backend=backend))
+    else:
+        assert k == 4 and dy.halo == 1 and dxp.layout == 1
+        hq, wq = dxp.hp // 2, dxp.wp // 2
+        taps = [(i * dy.wp + j, 0, 0) for i in range(2) for j in range(2)]
+        kk = 4 * cout
+        for phase in range(4):
+            plans.append(GConvPlan(a=dy.t, a_off=0, a_dim=a_dim, a_str=a_str, box=(128, 1, 1), tiles=tiles,
+                                   valid=(rows, 1, dy.n), flat=(1, dy.hp * dy.wp, dy.wp, hq, wq), taps=taps,
+                                   w=w_packed, w_off=phase * cin_padded * kk, ncols=cin, ncols_padded=cin_padded,
+                                   bias=None, out=dxp.t, out_off=phase * hq * wq * cin,
+                                   o_str=(cin, wq * cin, 4 * hq * wq * cin), backend=backend))
+    return plans
+
+
+def plan_conv_wgrad(dy: HB, xp: HB, dw, dbias, k, stride, backend, accumulate=True) -> WGradPlan:
+    """dw: fp32 [Cout, k, k, Cin] contiguous (channels_last storage of the OIHW parameter)."""
+    cout, cin = dy.c, xp.c
+    b_dim, b_str = input_view(xp)
+    a_dim = (cout, dy.w, dy.h, 1, dy.n)
+    a_str = (1, cout, dy.wp * cout, dy.hp * dy.wp * cout, dy.hp * dy.wp * cout)
+    rows = 64
+    box = choose_box(dy.w, dy.h, dy.n, rows)
+    tiles = (-(-dy.w // box[0]), -(-dy.h // box[1]), -(-dy.n // box[2]))
+    return WGradPlan(a=dy.t, a_off=dy.interior_offset(), a_dim=a_dim, a_str=a_str, b=xp.t, b_off=0, b_dim=b_dim,
+                     b_str=b_str, box=box, tiles=tiles, taps=conv_taps(k, stride), ca=cout, cb=cin, dw=dw,
+                     s_a=k * k * cin, s_t=cin, s_b=1, dbias=dbias, accumulate=accumulate, backend=backend)

@@ -1,0 +1,262 @@
+/*
+ * dwc_b200.h -- C ABI of the B200-native DWC-GAN training hot path.
+ *
+ * The reference (yhlleo/DWC-GAN) has no FFI layer: its hot path is stock torch.nn calls
+ * (SURVEY.md 2.3).  This header is the net-new boundary those calls are replaced through
+ * (level L2).  Each entry point cites the reference line(s) whose arithmetic
+ * it takes over.  Conventions:
+ *   - plain pointers and sizes only, no torch types; all pointers are DEVICE pointers
+ *     unless a field says "host";
+ *   - every call enqueues on `stream` and never synchronises or allocates;
+ *   - return 0 on success, non-zero on error; dwc_last_error() gives the message
+ *     (thread-local);
+ *   - re-entrant and thread-safe (forward runs on the Python main thread, backward on
+ *     autograd's device thread).
+ *   - dtype codes: 0 = float32, 1 = bfloat16.  Activations are NHWC ("haloed buffers":
+ *     [N, H+2h, W+2h, C], or four parity planes [N, 4, (H+2h)/2, (W+2h)/2, C] in front of
+ *     a stride-2 convolution).
+ */
+#ifndef DWC_B200_H_
+#define DWC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dwc_stream_t; /* cudaStream_t */
+
+const char* dwc_last_error(void);
+int dwc_abi_version(void);
+/* 1 if the current device can run the tcgen05/TMA kernels (sm_100) and the driver exposes
+ * cuTensorMapEncodeTiled. */
+int dwc_tc_available(void);
+
+#define DWC_F32 0
+#define DWC_BF16 1
+#define DWC_SIMT 0
+#define DWC_TC 1
+#define DWC_MAX_TAPS 64
+
+/* ------------------------------------------------------------------------------------------
+ * Generalised convolution as a multi-tap shifted GEMM ("gconv").
+ *
+ *   out[row, :] (+)= bias + sum_t  A[coord(row) + tap_t, 0:C] . W[:, t*C:(t+1)*C]^T
+ *
+ * A is a rank-5 element-strided view (C, X, Y, Z, N) of a haloed NHWC buffer, read with
+ * zero fill outside [0, a_dim).  A tile is 128 rows, row r <-> (x, y, n) =
+ * (x0 + r % bx, y0 + (r / bx) % by, n0 + r / (bx*by)).  With flat != 0, X is a flattened
+ * (n, y, x) index over the input grid (image rows flat_img, pitch flat_pitch) and a row is
+ * stored iff its decoded (y, x) lies inside flat_h x flat_w.
+ *
+ * Replaces: nn.Conv2d forward inside Conv2dBlock (networks/networks.py:531,577-580) and its
+ * data gradient (aten::convolution_backward): the same kernel runs the
+ * forward (reflect halo in A), the stride-1 dgrad (zero halo, flipped taps) and the four
+ * parity phases of the stride-2 dgrad.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t dtype;        /* of A and W */
+  int32_t backend;      /* DWC_SIMT or DWC_TC (TC needs bf16 and C % 64 == 0) */
+  const void* a;
+  int64_t a_dim[5];     /* C, X, Y, Z, N */
+  int64_t a_str[5];     /* element strides, a_str[0] == 1 */
+  int32_t box[3];       /* bx, by, bn ; bx*by*bn == 128 */
+  int32_t tiles[3];     /* tiles along X, Y, N */
+  int32_t valid[3];     /* rows with x >= valid[0] || y >= valid[1] || n >= valid[2] are dropped */
+  int32_t flat, flat_img, flat_pitch, flat_h, flat_w;
+  int32_t ntaps;
+  const int32_t* taps;  /* HOST pointer: ntaps * 3 ints (dx, dy, z) */
+  const void* w;        /* [ncols_padded][ntaps*C] */
+  int32_t ncols, ncols_padded;
+  const float* bias;    /* [ncols] or NULL */
+  void* out;
+  int64_t o_str[3];     /* element strides of out for x, y, n (columns contiguous) */
+  int32_t out_dtype;
+  int32_t accumulate;   /* out += ... */
+} dwc_gconv_t;
+
+int dwc_gconv(const dwc_gconv_t* p, dwc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight gradient: dw[ia*s_a + t*s_t + ib*s_b] (+)= sum_pixels A[pix, ia] * B[pix + tap_t, ib]
+ * and optionally dbias[ia] += sum_pixels A[pix, ia].   A = dY view, B = padded input view,
+ * both rank-5 (C, X, Y, Z, N); pixel tiles enumerated exactly as in gconv.
+ * Replaces the weight/bias part of aten::convolution_backward.
+ * Split-K partial sums go through `workspace` and are reduced in a fixed order
+ * (deterministic).  dwc_wgrad_workspace_bytes() returns the size to provide.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t dtype, backend;
+  const void* a; int64_t a_dim[5]; int64_t a_str[5];
+  const void* b; int64_t b_dim[5]; int64_t b_str[5];
+  int32_t box[3];
+  int32_t tiles[3];
+  int32_t ntaps;
+  const int32_t* taps;  /* HOST pointer, (dx, dy, z) applied to B */
+  int32_t ca, cb;       /* channels of A and of B */
+  float* dw; int64_t s_a, s_t, s_b;
+  float* dbias;         /* NULL to skip */
+  int32_t accumulate;   /* dw/dbias += (else overwritten) */
+  float* workspace; int64_t workspace_bytes;
+} dwc_wgrad_t;
+
+int64_t dwc_wgrad_workspace_bytes(const dwc_wgrad_t* p);
+int dwc_wgrad(const dwc_wgrad_t* p, dwc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Haloed-buffer geometry shared by the element-wise kernels.
+ * layout 0: [N, H+2*halo, W+2*halo, C]; layout 1: parity planes [N, 4, (H+2*halo)/2, ...].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  void* ptr;            /* start of the allocation (not the interior) */
+  int32_t n, h, w, c;   /* interior extent */
+  int32_t halo;
+  int32_t layout;
+  int32_t dtype;
+} dwc_hbuf_t;
+
+/* per-(n,c) sum and sum of squares over the interior, in `splits` pixel slices that the finalize
+ * kernels add up in a fixed order: stats[(n*splits+s)*C+c] = {sum, sumsq} (float2).
+ * First half of nn.InstanceNorm2d / AdaIN / LayerNorm statistics (networks.py:545,706-719,736-752). */
+int dwc_nc_stats(const dwc_hbuf_t* y, int splits, float* stats, dwc_stream_t stream);
+
+/* Turn statistics into per-(n,c) scale/shift.  kind: 0 none (scale 1, shift 0), 1 instance norm,
+ * 2 AdaIN (weight,bias [N,C]), 3 MUNIT LayerNorm (gamma,beta [C]; unbiased std, eps added to std).
+ * coef[n*C+c] = {scale, shift, mean, rstd}   (float4) */
+int dwc_norm_finalize(int kind, const float* stats, int splits, int n, int c, int hw, float eps,
+                      const float* weight, const float* bias, float* coef, dwc_stream_t stream);
+
+/* out = reflect_pad( act(scale*y + shift) + residual ).  act: 0 none 1 relu 2 lrelu(0.1).
+ * `res` may be NULL.  The whole haloed extent of `out` is written.
+ * Replaces norm + activation + residual add + nn.ReflectionPad2d of the next Conv2dBlock
+ * (networks.py:514-522,531,580-585). */
+int dwc_post_fwd(const dwc_hbuf_t* y, const float* coef, int act, const dwc_hbuf_t* res,
+                 const dwc_hbuf_t* out, dwc_stream_t stream);
+
+/* Backward, pass 1: red[(n*splits+s)*C+c] = {sum dz, sum dz*y} with dz = fold(dout) * act'(scale*y+shift). */
+int dwc_post_bwd_reduce(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, int act, int splits,
+                        float* red, dwc_stream_t stream);
+/* Backward, pass 1b: per-(n,c) coefficients bco = {a, b, c, 0} so that dy = a*dz + b*y + c,
+ * plus parameter gradients: AdaIN dweight/dbias [N,C] (overwritten), LayerNorm dgamma/dbeta [C]
+ * (accumulated). */
+int dwc_norm_bwd_finalize(int kind, const float* red, int splits, const float* coef, int n, int c, int hw, float eps,
+                          const float* weight, float* dweight, float* dbias, float* bco,
+                          dwc_stream_t stream);
+/* Backward, pass 2: dy = a*dz + b*y + c written with a ZERO halo; dres (optional, same geometry
+ * as the forward `res`) = fold(dout) in the interior and zero in the halo. */
+int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, const float* bco,
+                       int act, const dwc_hbuf_t* dy, const dwc_hbuf_t* dres, dwc_stream_t stream);
+
+/* nn.Upsample(2, bilinear, align_corners=False) + reflect pad (networks_v2.py:154, networks.py:531). */
+int dwc_upsample_pad_fwd(const dwc_hbuf_t* x, const dwc_hbuf_t* out, dwc_stream_t stream);
+int dwc_upsample_pad_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* dx, dwc_stream_t stream);
+
+/* NCHW float32 image -> haloed NHWC buffer, optional 2x2 average pooling first
+ * (F.interpolate(0.5, bilinear) == avg_pool2d, networks.py:113) and reflect padding. */
+int dwc_image_pad_fwd(const float* img, int n, int c, int h, int w, int pool, const dwc_hbuf_t* out,
+                      dwc_stream_t stream);
+int dwc_image_pad_bwd(const dwc_hbuf_t* dout, int pool, float* dimg, int n, int c, int h, int w,
+                      int accumulate, dwc_stream_t stream);
+
+/* Decoder heads: y[..., 0:3] -> tanh -> img NCHW f32 ; y[..., 3] -> sigmoid -> att NCHW f32
+ * (networks_v2.py:162-169).  Backward writes dy (zero halo). */
+int dwc_heads_fwd(const dwc_hbuf_t* y, float* img, float* att, dwc_stream_t stream);
+int dwc_heads_bwd(const float* dimg, const float* datt, const float* img, const float* att,
+                  const dwc_hbuf_t* dy, dwc_stream_t stream);
+
+/* x = img*att + real*(1-att)   (solver.py:160-161).  Backward: dimg, datt. */
+int dwc_blend_fwd(const float* img, const float* att, const float* real, float* out, int n, int c, int hw,
+                  dwc_stream_t stream);
+int dwc_blend_bwd(const float* dout, const float* img, const float* att, const float* real, float* dimg,
+                  float* datt, int n, int c, int hw, dwc_stream_t stream);
+
+/* Global average pool of relu(y) (StyleEncoder tail: ReLU + AdaptiveAvgPool2d(1), networks_v2.py:113). */
+int dwc_relu_gap_fwd(const dwc_hbuf_t* y, float* out, dwc_stream_t stream);
+int dwc_relu_gap_bwd(const float* dout, const dwc_hbuf_t* y, const dwc_hbuf_t* dy, dwc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small dense algebra (style MLP, mapping network, heads, text encoder): fp32 accumulate.
+ *   C[m,n] = act( alpha * sum_k A[m,k]*B[k,n] + bias[n] + beta*C[m,n] )
+ * with arbitrary element strides.  a_dtype applies to A only (B, C, bias are float32).
+ * Replaces nn.Linear stacks (networks.py:496-499, networks_v2.py:117-127,208-210).
+ * ------------------------------------------------------------------------------------------ */
+int dwc_sgemm(int m, int n, int k, float alpha, const void* a, int a_dtype, int64_t a_sm, int64_t a_sk,
+              const float* b, int64_t b_sk, int64_t b_sn, float beta, float* c, int64_t c_sm, int64_t c_sn,
+              const float* bias, int act, dwc_stream_t stream);
+/* out[n] (+)= sum_m A[m,n]  (bias gradients) */
+int dwc_colsum(int m, int n, const float* a, int64_t a_sm, int64_t a_sn, float* out, int accumulate,
+               dwc_stream_t stream);
+/* element-wise helpers on float32: relu backward from output, dropout-mask multiply */
+int dwc_relu_bwd(const float* dout, const float* out, float* din, int64_t count, dwc_stream_t stream);
+int dwc_mul(const float* a, const float* b, float* out, int64_t count, dwc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Text encoder (networks_v2.py:213-254): embedding + style concat, one LSTM time step for both
+ * directions (gate order i,f,g,o; per-sample lengths give pack_padded_sequence semantics).
+ * ------------------------------------------------------------------------------------------ */
+int dwc_embed_concat_fwd(const int64_t* tokens /*[B,T]*/, const float* emb, const float* style, const float* mask,
+                         float* x /*[T,B,E+S]*/, int b, int t, int e, int s, dwc_stream_t stream);
+int dwc_embed_concat_bwd(const int64_t* tokens, const float* dx, const float* mask, float* demb, float* dstyle,
+                         int b, int t, int e, int s, int pad_idx, dwc_stream_t stream);
+/* step index `step`: direction 0 handles time t=step, direction 1 handles t=T-1-step.
+ * xproj [T,B,2,4H] (input projection + both biases), whh [2,4H,H], h/c state [2,B,H] (in place),
+ * out [T,B,2H], gates_save [T,B,2,4H] (activated gates i,f,g,o) and c_save [T,B,2,H] (cell state
+ * after the step) for the backward pass (may be NULL in inference). */
+int dwc_lstm_step_fwd(int step, int t_total, int b, int h, const float* xproj, const float* whh,
+                      const int64_t* lens, const float* h_in, const float* c_in, float* h_out, float* c_out,
+                      float* out, float* gates_save, float* c_save, dwc_stream_t stream);
+/* backward of one step: consumes dh/dc state [2,B,H] (+ dout[t]), the NEXT processed step's gate
+ * gradients are folded in through whh.  Writes dgates [T,B,2,4H] for the step. */
+int dwc_lstm_step_bwd(int step, int t_total, int b, int h, const float* whh, const int64_t* lens,
+                      const float* dout /*[T,B,2H] or NULL*/, const float* gates_save, const float* c_save,
+                      const float* dh_in, const float* dc_in, float* dh_out, float* dc_out,
+                      float* dgates, dwc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GMM style space (tools.py:65-70, gmm.py:13-22) and losses.
+ * ------------------------------------------------------------------------------------------ */
+/* z[b, j*cdim+k] = mu[b,j] + stddev * eps[k, b, j]   (eps laid out (1, cdim, B, ncls)) */
+int dwc_gmm_sample(const float* mu, const float* eps, float stddev, float* z, int b, int ncls, int cdim,
+                   dwc_stream_t stream);
+/* loss = sum_i mean_b sum_k 0.5*(log(sigma/exp(lv)) + (exp(lv)+(mu-c[b,i])^2)/sigma - 1);
+ * mu, lv [B, ncls*cdim]; also writes dmu, dlv (gradient of the loss, unscaled). */
+int dwc_gmm_kl(const float* mu, const float* lv, const float* c, float sigma, float* loss, float* dmu,
+               float* dlv, int b, int ncls, int cdim, dwc_stream_t stream);
+/* loss[0] += mean |a-b| (caller zeroes loss; a,b flat of a_dtype/b_dtype)  (solver.py:113-114,127-132).
+ * Backward: da = gscale[0]*sign(a-b)/count, db = -da; either may be NULL; gscale is a device scalar. */
+int dwc_l1_loss_fwd(const void* a, int a_dtype, const void* b, int b_dtype, int64_t count, float* loss,
+                    dwc_stream_t stream);
+int dwc_l1_loss_bwd(const void* a, int a_dtype, const void* b, int b_dtype, int64_t count, const float* gscale,
+                    void* da, void* db, dwc_stream_t stream);
+/* loss[0] = mean (x - target)^2 ; dx = gscale*2(x-target)/count  (LSGAN, networks.py:131,158) */
+int dwc_mse_const_loss_fwd(const float* x, float target, int64_t count, float* loss, dwc_stream_t stream);
+int dwc_mse_const_loss_bwd(const float* x, float target, int64_t count, const float* gscale, float* dx,
+                           dwc_stream_t stream);
+/* loss[0] = mean BCE-with-logits(x, y); dx = gscale*(sigmoid(x)-y)/count (networks.py:83) */
+int dwc_bce_logits_loss_fwd(const float* x, const float* y, int64_t count, float* loss, dwc_stream_t stream);
+int dwc_bce_logits_loss_bwd(const float* x, const float* y, int64_t count, const float* gscale, float* dx,
+                            dwc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer: torch.optim.Adam with coupled L2 (solver.py:65-68) + EMA (utils.py:52-54) on flat
+ * buffers, chunked.  chunk table entries: {offset, length, active}.  hyper (device, float[8]):
+ * {lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, grad_scale}.
+ * ------------------------------------------------------------------------------------------ */
+int dwc_adam_step(float* param, const float* grad, float* m, float* v, int64_t count,
+                  const uint8_t* active /*per 1024-element chunk, device, may be NULL*/,
+                  const float* hyper, dwc_stream_t stream);
+int dwc_ema_step(const float* param, float* avg, int64_t count, float beta, dwc_stream_t stream);
+/* master float32 weights [Cout][taps][Cin] -> packed compute-dtype GEMM operands.
+ * mode 0: forward  wf[co][t][ci]                (cast only, rows padded to ncols_padded)
+ * mode 1: stride-1 dgrad  wd[ci][T-1-t][co]     (taps reversed)
+ * mode 2: stride-2 k4 dgrad, 4 parity phases  wd[phase][ci][(i,j)][co] */
+int dwc_pack_weights(const float* w, int cout, int taps_h, int taps_w, int cin, int mode, void* out,
+                     int out_dtype, int rows_padded, dwc_stream_t stream);
+int dwc_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t count, dwc_stream_t stream);
+int dwc_fill(void* dst, int dtype, float value, int64_t count, dwc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DWC_B200_H_ */

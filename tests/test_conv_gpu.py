@@ -1,0 +1,119 @@
+"""GPU parity of the gconv / wgrad kernels (SIMT fp32, SIMT bf16, tcgen05 bf16) against
+F.conv2d(F.pad(x, reflect)) and its autograd gradients, through the C ABI."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dwc_gan_b200 import _lib as L
+from dwc_gan_b200 import plan as P
+from dwc_gan_b200.plan import HB
+from tests import emu
+
+pytestmark = pytest.mark.gpu
+
+_ws = {}
+
+
+def workspace(nbytes):
+    t = _ws.get("t")
+    if t is None or t.numel() * 4 < nbytes:
+        t = torch.empty((nbytes + 3) // 4 + 1024, dtype=torch.float32, device="cuda")
+        _ws["t"] = t
+    return t
+
+
+def pack(w_krsc_dev, mode, dtype, rows_padded, cout, k, cin):
+    if mode == 0:
+        out = torch.empty(rows_padded, k * k * cin, dtype=dtype, device="cuda")
+    elif mode == 1:
+        out = torch.empty(rows_padded, k * k * cout, dtype=dtype, device="cuda")
+    else:
+        out = torch.empty(4, rows_padded, 4 * cout, dtype=dtype, device="cuda")
+    L.check(L.lib().dwc_pack_weights(L.ptr(w_krsc_dev), cout, k, k, cin, mode, L.ptr(out), L.dt(dtype), rows_padded,
+                                     L.stream()), "pack")
+    return out
+
+
+CASES = [
+    # n, h, w, cin, cout, k, s, p
+    (2, 16, 16, 64, 128, 3, 1, 1),
+    (2, 16, 16, 128, 256, 3, 1, 1),
+    (1, 32, 32, 64, 64, 5, 1, 2),
+    (2, 16, 16, 64, 4, 7, 1, 3),
+    (2, 16, 16, 64, 128, 4, 2, 1),
+    (3, 8, 8, 128, 64, 4, 2, 1),
+    (9, 4, 4, 256, 512, 4, 2, 1),
+    (2, 16, 16, 3, 64, 7, 1, 3),
+    (2, 16, 16, 3, 64, 4, 2, 1),
+    (1, 32, 32, 256, 256, 3, 1, 1),
+]
+MODES = [("simt", torch.float32), ("simt", torch.bfloat16), ("tc", torch.bfloat16)]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,s,p", CASES)
+@pytest.mark.parametrize("backend,dtype", MODES)
+def test_conv_fwd_dgrad_wgrad(n, h, w, cin, cout, k, s, p, backend, dtype):
+    tc = backend == "tc"
+    be = L.TC if tc else L.SIMT
+    if tc and not L.lib().dwc_tc_available():
+        pytest.fail("tcgen05 path unavailable on this device")
+    torch.manual_seed(1)
+    x = torch.randn(n, cin, h, w).to(dtype).double()
+    wt = (torch.randn(cout, cin, k, k) * (1.0 / (cin * k * k) ** 0.5)).to(dtype).double()
+    bias = torch.randn(cout)
+    xpad = F.pad(x, (p, p, p, p), mode="reflect").requires_grad_(True)
+    wt_r = wt.clone().requires_grad_(True)
+    y_ref = F.conv2d(xpad, wt_r, bias.double(), stride=s)
+    ho, wo = y_ref.shape[2:]
+    dy = torch.randn(n, cout, ho, wo).to(dtype).double()
+    y_ref.backward(dy)
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    layout = 0 if s == 1 else 1
+    hy = k - 1 if s == 1 else 1
+    w_krsc = wt.permute(0, 2, 3, 1).contiguous().float().cuda()
+
+    # forward
+    fwd_tc = tc and cin % 64 == 0
+    rows_p = cout if cout % 64 == 0 else 16
+    xp = emu.make_padded(x, p, layout, dtype)
+    xp = xp.like(xp.t.cuda())
+    y = HB.empty(n, ho, wo, cout, hy, 0, dtype, "cuda", zero=True)
+    wf = pack(w_krsc, 0, dtype, rows_p, cout, k, cin)
+    assert torch.equal(wf.cpu().double(), emu.pack_fwd(w_krsc.cpu(), rows_p).to(dtype).double())
+    pl = P.plan_conv_fwd(xp, wf, cout, rows_p, bias.cuda(), y, k, s, L.TC if fwd_tc else L.SIMT)
+    pl.launch()
+    torch.cuda.synchronize()
+    got = y.interior().permute(0, 3, 1, 2).double().cpu()
+    err = (got - y_ref.detach()).abs().max().item() / y_ref.abs().max().item()
+    assert err < tol, "fwd rel err %g" % err
+
+    # dgrad
+    dg_tc = tc and cout % 64 == 0 and cin % 64 == 0
+    dyz = emu.make_zero_haloed(dy, hy, dtype)
+    dyz = dyz.like(dyz.t.cuda())
+    dxp = HB.empty(n, h, w, cin, p, layout, dtype, "cuda")
+    dxp.t.fill_(float("nan"))
+    wd = pack(w_krsc, 1 if s == 1 else 2, dtype, cin, cout, k, cin)
+    ref_pack = emu.pack_dgrad_s1(w_krsc.cpu()) if s == 1 else emu.pack_dgrad_s2(w_krsc.cpu())
+    assert torch.equal(wd.cpu().double(), ref_pack.to(dtype).double())
+    for q in P.plan_conv_dgrad(dyz, wd, dxp, k, s, L.TC if dg_tc else L.SIMT):
+        q.launch()
+    torch.cuda.synchronize()
+    got = dxp.padded_nhwc().permute(0, 3, 1, 2).double().cpu()
+    err = (got - xpad.grad).abs().max().item() / xpad.grad.abs().max().item()
+    assert err < tol, "dgrad rel err %g" % err
+
+    # wgrad + dbias (accumulate on top of ones)
+    wg_tc = tc and cin % 64 == 0 and cout % 64 == 0 and (cin % 128 == 0 or cout % 128 == 0)
+    dw = torch.ones(cout, k, k, cin, device="cuda")
+    db = torch.ones(cout, device="cuda")
+    wp = P.plan_conv_wgrad(dyz, xp, dw, db, k, s, L.TC if wg_tc else L.SIMT)
+    if not wg_tc:
+        wp.box = P.choose_box(wo, ho, n, 64)
+    wp.launch(workspace)
+    torch.cuda.synchronize()
+    got = (dw.cpu().double() - 1).permute(0, 3, 1, 2)
+    err = (got - wt_r.grad).abs().max().item() / wt_r.grad.abs().max().item()
+    assert err < tol, "wgrad rel err %g" % err
+    errb = ((db.cpu().double() - 1) - dy.sum((0, 2, 3))).abs().max().item() / dy.sum((0, 2, 3)).abs().max().item()
+    assert errb < tol, "dbias rel err %g" % errb
