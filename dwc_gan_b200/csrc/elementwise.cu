@@ -561,8 +561,12 @@ __global__ void image_pad_fwd_kernel(const float* __restrict__ img, int C, int H
       const float* p = img + ((long long)n * C + c) * H * W;
       if (pool == 1) v = p[(long long)iy * W + ix];
       else {
-        const float* q = p + (long long)(2 * iy) * W + 2 * ix;
-        v = 0.25f * (q[0] + q[1] + q[W] + q[W + 1]);
+        // repeated F.interpolate(0.5, bilinear) == repeated 2x2 average == pool x pool average
+        const float* q = p + (long long)(pool * iy) * W + pool * ix;
+        float acc = 0.f;
+        for (int a = 0; a < pool; ++a)
+          for (int b = 0; b < pool; ++b) acc += q[(long long)a * W + b];
+        v = acc / (float)(pool * pool);
       }
     }
     ob[out.off_padded(n, Y, X) + c] = from_f<T>(v);
@@ -580,14 +584,14 @@ __global__ void image_pad_bwd_kernel(HB dout, int pool, float* __restrict__ dimg
     int c = (int)(r % C);
     int n = (int)(r / C);
     float g = fold_read1<T>(dout, n, y / pool, x / pool, c);
-    if (pool == 2) g *= 0.25f;
+    if (pool > 1) g *= 1.f / (float)(pool * pool);
     dimg[i] = accumulate ? dimg[i] + g : g;
   }
 }
 
 extern "C" int dwc_image_pad_fwd(const float* img, int n, int c, int h, int w, int pool, const dwc_hbuf_t* out,
                                  dwc_stream_t stream) {
-  DWC_CHECK((pool == 1 || pool == 2) && out->h * pool == h && out->w * pool == w && out->n == n && out->c >= c,
+  DWC_CHECK(pool >= 1 && out->h * pool == h && out->w * pool == w && out->n == n && out->c >= c,
             "dwc_image_pad_fwd: geometry mismatch");
   HB ho(*out);
   long long total = ho.padded_pixels() * out->c;
@@ -597,7 +601,7 @@ extern "C" int dwc_image_pad_fwd(const float* img, int n, int c, int h, int w, i
 }
 extern "C" int dwc_image_pad_bwd(const dwc_hbuf_t* dout, int pool, float* dimg, int n, int c, int h, int w,
                                  int accumulate, dwc_stream_t stream) {
-  DWC_CHECK((pool == 1 || pool == 2) && dout->h * pool == h && dout->w * pool == w && dout->n == n && dout->c >= c,
+  DWC_CHECK(pool >= 1 && dout->h * pool == h && dout->w * pool == w && dout->n == n && dout->c >= c,
             "dwc_image_pad_bwd: geometry mismatch");
   HB hd(*dout);
   long long total = (long long)n * c * h * w;

@@ -1,0 +1,583 @@
+"""torch.autograd.Function wrappers around the C ABI (include/dwc_b200.h).
+
+PyTorch is plumbing here (device memory, streams, the autograd tape); every arithmetic step of
+the hot path is one of our CUDA kernels.  Conventions:
+  * activations travel as haloed NHWC buffers (plan.HB); gradient buffers handed to a
+    convolution's backward always carry a ZERO halo (written by the producer kernels);
+  * parameter gradients are accumulated by the kernels straight into ``param.grad`` (views of a
+    flat fp32 buffer, see flat.py); the parameter is still passed to the Function as an anchor so
+    that the tape is built when only parameters require grad;
+  * there is no CPU fallback: every entry point raises if the CUDA library is not usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from . import plan as P
+from .plan import HB
+
+# --------------------------------------------------------------------------------------------
+# runtime configuration
+# --------------------------------------------------------------------------------------------
+
+
+class Runtime:
+    """Process-wide knobs: compute dtype (bf16 product mode / fp32 validation mode), kernel backend."""
+
+    def __init__(self):
+        self.dtype = torch.bfloat16
+        self.use_tc = True
+        self._ws = {}
+        self.launches = 0
+
+    def set_mode(self, mode: str):
+        if mode == "bf16":
+            self.dtype, self.use_tc = torch.bfloat16, True
+        elif mode == "bf16_simt":
+            self.dtype, self.use_tc = torch.bfloat16, False
+        elif mode == "fp32":
+            self.dtype, self.use_tc = torch.float32, False
+        else:
+            raise ValueError("mode must be bf16, bf16_simt or fp32")
+
+    def tc_ok(self, *channels):
+        return self.use_tc and self.dtype == torch.bfloat16 and all(c % 64 == 0 for c in channels)
+
+    def workspace(self, nbytes, device=None):
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        key = (device.index, torch.cuda.current_stream().cuda_stream)
+        t = self._ws.get(key)
+        if t is None or t.numel() * 4 < nbytes:
+            t = torch.empty(max(nbytes // 4 + 1024, 16 << 20), dtype=torch.float32, device=device)
+            self._ws[key] = t
+        return t
+
+
+RT = Runtime()
+
+
+def _require_cuda(t):
+    if not t.is_cuda:
+        raise RuntimeError("dwc_gan_b200: the hot path runs on CUDA only (got a %s tensor); "
+                           "there is no CPU fallback" % t.device)
+
+
+def _call(fn_name, *args):
+    RT.launches += 1
+    L.check(getattr(L.lib(), fn_name)(*args), fn_name)
+
+
+def _stats_splits(hw):
+    return max(1, min(16, hw // 512))
+
+
+# --------------------------------------------------------------------------------------------
+# image boundary
+# --------------------------------------------------------------------------------------------
+
+class ImagePadFn(torch.autograd.Function):
+    """NCHW fp32 image -> reflect-haloed NHWC buffer (optional 2x avg-pool): networks.py:113,531."""
+
+    @staticmethod
+    def forward(ctx, img, pool, pad, layout):
+        _require_cuda(img)
+        img = img.contiguous().float()
+        n, c, h, w = img.shape
+        out = HB.empty(n, h // pool, w // pool, c, pad, layout, RT.dtype, img.device)
+        hs = out.struct()
+        _call("dwc_image_pad_fwd", L.ptr(img), n, c, h, w, pool, C.byref(hs), L.stream())
+        ctx.meta = (n, c, h, w, pool, pad, layout)
+        return out.t
+
+    @staticmethod
+    def backward(ctx, dout):
+        n, c, h, w, pool, pad, layout = ctx.meta
+        d = HB(dout.contiguous(), n, h // pool, w // pool, c, pad, layout)
+        dimg = torch.empty(n, c, h, w, dtype=torch.float32, device=dout.device)
+        hs = d.struct()
+        _call("dwc_image_pad_bwd", C.byref(hs), pool, L.ptr(dimg), n, c, h, w, 0, L.stream())
+        return dimg, None, None, None
+
+
+def image_pad(img, pool, pad, layout) -> HB:
+    n, c, h, w = img.shape
+    t = ImagePadFn.apply(img, pool, pad, layout)
+    return HB(t, n, h // pool, w // pool, c, pad, layout)
+
+
+# --------------------------------------------------------------------------------------------
+# convolution
+# --------------------------------------------------------------------------------------------
+
+class ConvFn(torch.autograd.Function):
+    """reflect-padded conv + bias as gconv; backward = gconv dgrad + pixel-reduction wgrad
+    (networks.py:577-580 and aten::convolution_backward)."""
+
+    @staticmethod
+    def forward(ctx, xp_t, weight, layer, xp: HB):
+        _require_cuda(xp_t)
+        k, s, cout = layer.k, layer.stride, layer.total_cout()
+        ho, wo = P.out_size(xp, k, s)
+        hy = k - 1 if s == 1 else 1
+        y = HB.empty(xp.n, ho, wo, cout, hy, 0, xp_t.dtype, xp_t.device)
+        wf, rows_p = layer.packed_fwd(xp_t.dtype)
+        tc = RT.tc_ok(xp.c) and (rows_p % 64 == 0 or rows_p == 16)
+        pl = P.plan_conv_fwd(HB(xp_t, xp.n, xp.h, xp.w, xp.c, xp.halo, xp.layout), wf, cout, rows_p, layer.bias_f32(),
+                             y, k, s, L.TC if tc else L.SIMT)
+        RT.launches += 1
+        pl.launch()
+        ctx.layer, ctx.xp_meta, ctx.y_meta = layer, (xp.n, xp.h, xp.w, xp.c, xp.halo, xp.layout), (ho, wo, hy)
+        ctx.save_for_backward(xp_t)
+        return y.t
+
+    @staticmethod
+    def backward(ctx, dy_t):
+        layer = ctx.layer
+        (xp_t,) = ctx.saved_tensors
+        n, h, w, c, halo, layout = ctx.xp_meta
+        ho, wo, hy = ctx.y_meta
+        k, s, cout = layer.k, layer.stride, layer.total_cout()
+        dy = HB(dy_t.contiguous(), n, ho, wo, cout, hy, 0)
+        xp = HB(xp_t, n, h, w, c, halo, layout)
+        dxp_t = None
+        if ctx.needs_input_grad[0]:
+            dxp = HB.empty(n, h, w, c, halo, layout, dy_t.dtype, dy_t.device)
+            wd = layer.packed_dgrad(dy_t.dtype)
+            tc = RT.tc_ok(c, cout)
+            for q in P.plan_conv_dgrad(dy, wd, dxp, k, s, L.TC if tc else L.SIMT):
+                RT.launches += 1
+                q.launch()
+            dxp_t = dxp.t
+        if ctx.needs_input_grad[1]:
+            gw, gb = layer.grad_buffers()
+            tc = RT.tc_ok(c, cout) and (c % 128 == 0 or cout % 128 == 0)
+            wp = P.plan_conv_wgrad(dy, xp, gw, gb, k, s, L.TC if tc else L.SIMT, accumulate=True)
+            RT.launches += 3
+            wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device))
+        return dxp_t, None, None, None
+
+
+def conv(xp: HB, layer) -> HB:
+    k, s = layer.k, layer.stride
+    ho, wo = P.out_size(xp, k, s)
+    t = ConvFn.apply(xp.t, layer.weight_param, layer, xp)
+    return HB(t, xp.n, ho, wo, layer.total_cout(), k - 1 if s == 1 else 1, 0)
+
+
+# --------------------------------------------------------------------------------------------
+# norm + activation + residual + reflect pad
+# --------------------------------------------------------------------------------------------
+NORM_NONE, NORM_IN, NORM_ADAIN, NORM_LN = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+
+
+class PostFn(torch.autograd.Function):
+    """out = reflect_pad(act(norm(y)) + residual): InstanceNorm2d / AdaIN / MUNIT LayerNorm, ReLU /
+    LeakyReLU(0.1), ResBlock residual and the next block's ReflectionPad2d in one pass
+    (networks.py:514-522,531,545,580-585,706-719,736-752)."""
+
+    @staticmethod
+    def forward(ctx, y_t, nw, nb, res_t, anchor, y: HB, kind, act, res: Optional[HB], out_halo, out_layout, ln_mod,
+                eps):
+        _require_cuda(y_t)
+        yh = HB(y_t, y.n, y.h, y.w, y.c, y.halo, 0)
+        n, c, hw = y.n, y.c, y.h * y.w
+        dev = y_t.device
+        coef = None
+        splits = _stats_splits(hw)
+        if kind != NORM_NONE:
+            stats = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
+            ys = yh.struct()
+            _call("dwc_nc_stats", C.byref(ys), splits, L.ptr(stats), L.stream())
+            coef = torch.empty(n * c * 4, dtype=torch.float32, device=dev)
+            if kind == NORM_ADAIN:
+                nw = nw.contiguous().float()
+                nb = nb.contiguous().float()
+            _call("dwc_norm_finalize", kind, L.ptr(stats), splits, n, c, hw, L.f32(eps), L.ptr(nw), L.ptr(nb),
+                  L.ptr(coef), L.stream())
+        out = HB.empty(n, y.h, y.w, c, out_halo, out_layout, y_t.dtype, dev)
+        ys, os_ = yh.struct(), out.struct()
+        rs = HB(res_t, res.n, res.h, res.w, res.c, res.halo, res.layout).struct() if res is not None else None
+        _call("dwc_post_fwd", C.byref(ys), L.ptr(coef), act, C.byref(rs) if rs is not None else None, C.byref(os_),
+              L.stream())
+        ctx.meta = (y.n, y.h, y.w, y.c, y.halo, kind, act, out_halo, out_layout, eps, splits,
+                    (res.n, res.h, res.w, res.c, res.halo, res.layout) if res is not None else None)
+        ctx.ln_mod = ln_mod
+        ctx.save_for_backward(y_t, coef, nw if kind in (NORM_ADAIN, NORM_LN) else None)
+        return out.t
+
+    @staticmethod
+    def backward(ctx, dout_t):
+        n, h, w, c, yhalo, kind, act, out_halo, out_layout, eps, splits, res_meta = ctx.meta
+        y_t, coef, nw = ctx.saved_tensors
+        dev = dout_t.device
+        dout = HB(dout_t.contiguous(), n, h, w, c, out_halo, out_layout)
+        yh = HB(y_t, n, h, w, c, yhalo, 0)
+        ds, ys = dout.struct(), yh.struct()
+        bco = None
+        dnw = dnb = None
+        if kind != NORM_NONE:
+            red = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
+            _call("dwc_post_bwd_reduce", C.byref(ds), C.byref(ys), L.ptr(coef), act, splits, L.ptr(red), L.stream())
+            bco = torch.empty(n * c * 4, dtype=torch.float32, device=dev)
+            if kind == NORM_ADAIN:
+                dnw = torch.empty(n, c, dtype=torch.float32, device=dev)
+                dnb = torch.empty(n, c, dtype=torch.float32, device=dev)
+                gw, gb = dnw, dnb
+            elif kind == NORM_LN:
+                gw, gb = ctx.ln_mod.grad_buffers()
+            else:
+                gw = gb = None
+            _call("dwc_norm_bwd_finalize", kind, L.ptr(red), splits, L.ptr(coef), n, c, h * w, L.f32(eps), L.ptr(nw),
+                  L.ptr(gw), L.ptr(gb), L.ptr(bco), L.stream())
+        dy = HB.empty(n, h, w, c, yhalo, 0, dout_t.dtype, dev)
+        dys = dy.struct()
+        dres = drs = None
+        if res_meta is not None and ctx.needs_input_grad[3]:
+            dres = HB.empty(*res_meta[:5], res_meta[5], dout_t.dtype, dev)
+            assert dres.layout == 0
+            drs = dres.struct()
+        _call("dwc_post_bwd_apply", C.byref(ds), C.byref(ys), L.ptr(coef), L.ptr(bco), act, C.byref(dys),
+              C.byref(drs) if drs is not None else None, L.stream())
+        return (dy.t, dnw, dnb, dres.t if dres is not None else None, None, None, None, None, None, None, None, None,
+                None)
+
+
+def post(y: HB, kind=NORM_NONE, act=ACT_NONE, nw=None, nb=None, res: Optional[HB] = None, out_halo=0, out_layout=0,
+         ln_mod=None, eps=1e-5, anchor=None) -> HB:
+    t = PostFn.apply(y.t, nw, nb, res.t if res is not None else None, anchor, y, kind, act, res, out_halo, out_layout,
+                     ln_mod, eps)
+    return HB(t, y.n, y.h, y.w, y.c, out_halo, out_layout)
+
+
+class UpsamplePadFn(torch.autograd.Function):
+    """nn.Upsample(2, bilinear) + ReflectionPad2d of the next block (networks_v2.py:154)."""
+
+    @staticmethod
+    def forward(ctx, x_t, x: HB, out_halo):
+        xh = HB(x_t, x.n, x.h, x.w, x.c, x.halo, x.layout)
+        out = HB.empty(x.n, 2 * x.h, 2 * x.w, x.c, out_halo, 0, x_t.dtype, x_t.device)
+        xs, os_ = xh.struct(), out.struct()
+        _call("dwc_upsample_pad_fwd", C.byref(xs), C.byref(os_), L.stream())
+        ctx.meta = (x.n, x.h, x.w, x.c, x.halo, x.layout, out_halo)
+        return out.t
+
+    @staticmethod
+    def backward(ctx, dout_t):
+        n, h, w, c, halo, layout, out_halo = ctx.meta
+        dout = HB(dout_t.contiguous(), n, 2 * h, 2 * w, c, out_halo, 0)
+        dx = HB.empty(n, h, w, c, halo, layout, dout_t.dtype, dout_t.device)
+        ds, xs = dout.struct(), dx.struct()
+        _call("dwc_upsample_pad_bwd", C.byref(ds), C.byref(xs), L.stream())
+        return dx.t, None, None
+
+
+def upsample_pad(x: HB, out_halo) -> HB:
+    t = UpsamplePadFn.apply(x.t, x, out_halo)
+    return HB(t, x.n, 2 * x.h, 2 * x.w, x.c, out_halo, 0)
+
+
+class HeadsFn(torch.autograd.Function):
+    """fused decoder heads: tanh(image_content) | sigmoid(image_attention) (networks_v2.py:162-169)."""
+
+    @staticmethod
+    def forward(ctx, y_t, y: HB, on_att_grad):
+        ctx.set_materialize_grads(False)
+        ctx.on_att_grad = on_att_grad
+        yh = HB(y_t, y.n, y.h, y.w, y.c, y.halo, 0)
+        img = torch.empty(y.n, y.c - 1, y.h, y.w, dtype=torch.float32, device=y_t.device)
+        att = torch.empty(y.n, 1, y.h, y.w, dtype=torch.float32, device=y_t.device)
+        ys = yh.struct()
+        _call("dwc_heads_fwd", C.byref(ys), L.ptr(img), L.ptr(att), L.stream())
+        ctx.meta = (y.n, y.h, y.w, y.c, y.halo, y_t.dtype)
+        ctx.save_for_backward(img, att)
+        return img, att
+
+    @staticmethod
+    def backward(ctx, dimg, datt):
+        n, h, w, c, halo, dtype = ctx.meta
+        img, att = ctx.saved_tensors
+        dy = HB.empty(n, h, w, c, halo, 0, dtype, img.device)
+        dys = dy.struct()
+        dimg = dimg.contiguous() if dimg is not None else None
+        datt = datt.contiguous() if datt is not None else None
+        if datt is not None and ctx.on_att_grad is not None:
+            ctx.on_att_grad()
+        _call("dwc_heads_bwd", L.ptr(dimg), L.ptr(datt), L.ptr(img), L.ptr(att), C.byref(dys), L.stream())
+        return dy.t, None, None
+
+
+def heads(y: HB, on_att_grad=None):
+    return HeadsFn.apply(y.t, y, on_att_grad)
+
+
+class BlendFn(torch.autograd.Function):
+    """x = img*att + real*(1-att)  (solver.py:160-161)."""
+
+    @staticmethod
+    def forward(ctx, img, att, real):
+        _require_cuda(img)
+        img, att, real = img.contiguous(), att.contiguous(), real.contiguous().float()
+        n, c, h, w = img.shape
+        out = torch.empty_like(img)
+        _call("dwc_blend_fwd", L.ptr(img), L.ptr(att), L.ptr(real), L.ptr(out), n, c, h * w, L.stream())
+        ctx.save_for_backward(img, att, real)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        img, att, real = ctx.saved_tensors
+        n, c, h, w = img.shape
+        dimg, datt = torch.empty_like(img), torch.empty_like(att)
+        _call("dwc_blend_bwd", L.ptr(dout.contiguous()), L.ptr(img), L.ptr(att), L.ptr(real), L.ptr(dimg), L.ptr(datt),
+              n, c, h * w, L.stream())
+        return dimg, datt, None
+
+
+def blend(img, att, real):
+    return BlendFn.apply(img, att, real)
+
+
+class ReluGapFn(torch.autograd.Function):
+    """ReLU + AdaptiveAvgPool2d(1) at the end of the style encoder (networks_v2.py:113)."""
+
+    @staticmethod
+    def forward(ctx, y_t, y: HB):
+        yh = HB(y_t, y.n, y.h, y.w, y.c, y.halo, 0)
+        out = torch.empty(y.n, y.c, dtype=torch.float32, device=y_t.device)
+        ys = yh.struct()
+        _call("dwc_relu_gap_fwd", C.byref(ys), L.ptr(out), L.stream())
+        ctx.meta = (y.n, y.h, y.w, y.c, y.halo)
+        ctx.save_for_backward(y_t)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n, h, w, c, halo = ctx.meta
+        (y_t,) = ctx.saved_tensors
+        yh = HB(y_t, n, h, w, c, halo, 0)
+        dy = HB.empty(n, h, w, c, halo, 0, y_t.dtype, y_t.device)
+        ys, dys = yh.struct(), dy.struct()
+        _call("dwc_relu_gap_bwd", L.ptr(dout.contiguous()), C.byref(ys), C.byref(dys), L.stream())
+        return dy.t, None
+
+
+def relu_gap(y: HB):
+    return ReluGapFn.apply(y.t, y)
+
+
+# --------------------------------------------------------------------------------------------
+# dense layers
+# --------------------------------------------------------------------------------------------
+
+def sgemm(m, n, k, alpha, a, a_sm, a_sk, b, b_sk, b_sn, beta, c, c_sm, c_sn, bias=None, act=0):
+    _call("dwc_sgemm", m, n, k, alpha, L.ptr(a), L.dt(a), a_sm, a_sk, L.ptr(b), b_sk, b_sn, beta, L.ptr(c), c_sm, c_sn,
+          L.ptr(bias), act, L.stream())
+
+
+class LinearFn(torch.autograd.Function):
+    """out = act(x @ W^T + b) with fp32 accumulation (nn.Linear: networks.py:496-499, networks_v2.py:117-127).
+    x may be fp32 or the compute dtype; W [N,K], b [N] are fp32 (views of the flat parameter buffer)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, owner, anchor):
+        _require_cuda(x)
+        x = x.contiguous()
+        m, k = x.shape
+        n = weight.shape[0]
+        out = torch.empty(m, n, dtype=torch.float32, device=x.device)
+        sgemm(m, n, k, 1.0, x, k, 1, weight, 1, k, 0.0, out, n, 1, bias, act)
+        ctx.act, ctx.owner = act, owner
+        ctx.save_for_backward(x, weight, out if act else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, out = ctx.saved_tensors
+        m, k = x.shape
+        n = weight.shape[0]
+        dout = dout.contiguous()
+        if ctx.act:
+            dz = torch.empty_like(dout)
+            _call("dwc_relu_bwd", L.ptr(dout), L.ptr(out), L.ptr(dz), L.i64(dz.numel()), L.stream())
+            dout = dz
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxf = torch.empty(m, k, dtype=torch.float32, device=x.device)
+            sgemm(m, k, n, 1.0, dout, n, 1, weight, k, 1, 0.0, dxf, k, 1)
+            dx = dxf if x.dtype == torch.float32 else _cast(dxf, x.dtype)
+        if ctx.needs_input_grad[5]:
+            gw, gb = ctx.owner()
+            # dW[n,k] += sum_m dout[m,n] x[m,k]   ->  A = x^T? use A = dout^T (fp32): C[n,k] = sum_m dout[m,n] x[m,k]
+            xf = x if x.dtype == torch.float32 else _cast(x, torch.float32)
+            sgemm(n, k, m, 1.0, dout, 1, n, xf, k, 1, 1.0, gw, k, 1)
+            if gb is not None:
+                _call("dwc_colsum", m, n, L.ptr(dout), n, 1, L.ptr(gb), 1, L.stream())
+        return dx, None, None, None, None, None
+
+
+def _cast(t, dtype):
+    out = torch.empty(t.shape, dtype=dtype, device=t.device)
+    _call("dwc_cast", L.ptr(t.contiguous()), L.dt(t), L.ptr(out), L.dt(dtype), L.i64(t.numel()), L.stream())
+    return out
+
+
+def linear(x, weight, bias, act, grad_owner, anchor):
+    """grad_owner() -> (weight.grad view, bias.grad view or None); anchor: the nn.Parameter behind `weight`."""
+    return LinearFn.apply(x, weight, bias, act, grad_owner, anchor)
+
+
+class MulFn(torch.autograd.Function):
+    """element-wise product with a constant mask (dropout)."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        out = torch.empty_like(x)
+        _call("dwc_mul", L.ptr(x.contiguous()), L.ptr(mask), L.ptr(out), L.i64(x.numel()), L.stream())
+        ctx.save_for_backward(mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (mask,) = ctx.saved_tensors
+        dx = torch.empty_like(dout)
+        _call("dwc_mul", L.ptr(dout.contiguous()), L.ptr(mask), L.ptr(dx), L.i64(dx.numel()), L.stream())
+        return dx, None
+
+
+# --------------------------------------------------------------------------------------------
+# GMM + losses
+# --------------------------------------------------------------------------------------------
+
+def gmm_sample(mu, eps, stddev, c_dim):
+    """z[b, j*c_dim+k] = mu[b,j] + stddev*eps[0,k,b,j]  (tools.py:65-70); no gradient."""
+    _require_cuda(mu)
+    b, ncls = mu.shape
+    z = torch.empty(b, ncls * c_dim, dtype=torch.float32, device=mu.device)
+    _call("dwc_gmm_sample", L.ptr(mu.contiguous().float()), L.ptr(eps.contiguous().float()), stddev, L.ptr(z), b, ncls,
+          c_dim, L.stream())
+    return z
+
+
+class GmmKlFn(torch.autograd.Function):
+    """gmm_kl_distance_sp (gmm.py:13-22) on concatenated [B, ncls*cdim] mu / logvar."""
+
+    @staticmethod
+    def forward(ctx, mu, lv, c, sigma, ncls, cdim):
+        _require_cuda(mu)
+        mu, lv, c = mu.contiguous().float(), lv.contiguous().float(), c.contiguous().float()
+        loss = torch.empty(1, dtype=torch.float32, device=mu.device)
+        dmu, dlv = torch.empty_like(mu), torch.empty_like(lv)
+        _call("dwc_gmm_kl", L.ptr(mu), L.ptr(lv), L.ptr(c), sigma, L.ptr(loss), L.ptr(dmu), L.ptr(dlv), mu.shape[0],
+              ncls, cdim, L.stream())
+        ctx.save_for_backward(dmu, dlv)
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        dmu, dlv = ctx.saved_tensors
+        return ScaleFn_apply(dmu, g), ScaleFn_apply(dlv, g), None, None, None, None
+
+
+def ScaleFn_apply(t, g):
+    """t * g for a 0-dim device scalar g, through dwc_mul on an expanded copy-free path."""
+    out = torch.empty_like(t)
+    gg = g.reshape(1).float().expand(t.numel()).contiguous() if t.numel() <= 4096 else None
+    if gg is None:
+        raise RuntimeError("ScaleFn_apply is for small tensors only")
+    _call("dwc_mul", L.ptr(t), L.ptr(gg), L.ptr(out), L.i64(t.numel()), L.stream())
+    return out
+
+
+def gmm_kl(mu_cat, lv_cat, c, sigma, ncls, cdim):
+    return GmmKlFn.apply(mu_cat, lv_cat, c, float(sigma), ncls, cdim)
+
+
+class L1Fn(torch.autograd.Function):
+    """mean |a - b| (solver.py:113-114,127-132), a/b fp32 or compute dtype, any (matching) layout."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        _require_cuda(a)
+        assert a.shape == b.shape and a.stride() == b.stride(), (a.shape, b.shape, a.stride(), b.stride())
+        loss = torch.zeros(1, dtype=torch.float32, device=a.device)
+        _call("dwc_l1_loss_fwd", L.ptr(a), L.dt(a), L.ptr(b), L.dt(b), L.i64(a.numel()), L.ptr(loss), L.stream())
+        ctx.save_for_backward(a, b)
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        gs = g.reshape(1).float().contiguous()
+        _call("dwc_l1_loss_bwd", L.ptr(a), L.dt(a), L.ptr(b), L.dt(b), L.i64(a.numel()), L.ptr(gs), L.ptr(da), L.ptr(db),
+              L.stream())
+        return da, db
+
+
+def _dense(t):
+    """The tensor itself if it is a dense (possibly permuted) block, else a contiguous copy."""
+    return t if t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last) else t.contiguous()
+
+
+def l1_loss(a, b):
+    a, b = _dense(a), _dense(b)
+    if a.stride() != b.stride():
+        a, b = a.contiguous(), b.contiguous()
+    return L1Fn.apply(a, b)
+
+
+class MseConstFn(torch.autograd.Function):
+    """mean (x - target)^2 : LSGAN terms (networks.py:131,158)."""
+
+    @staticmethod
+    def forward(ctx, x, target):
+        _require_cuda(x)
+        x = x.contiguous().float()
+        loss = torch.empty(1, dtype=torch.float32, device=x.device)
+        _call("dwc_mse_const_loss_fwd", L.ptr(x), target, L.i64(x.numel()), L.ptr(loss), L.stream())
+        ctx.target = target
+        ctx.save_for_backward(x)
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        gs = g.reshape(1).float().contiguous()
+        _call("dwc_mse_const_loss_bwd", L.ptr(x), ctx.target, L.i64(x.numel()), L.ptr(gs), L.ptr(dx), L.stream())
+        return dx, None
+
+
+def mse_const(x, target):
+    return MseConstFn.apply(x, float(target))
+
+
+class BceLogitsFn(torch.autograd.Function):
+    """F.binary_cross_entropy_with_logits(x, y, 'mean') (networks.py:83)."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        _require_cuda(x)
+        x, y = x.contiguous().float(), y.contiguous().float()
+        loss = torch.empty(1, dtype=torch.float32, device=x.device)
+        _call("dwc_bce_logits_loss_fwd", L.ptr(x), L.ptr(y), L.i64(x.numel()), L.ptr(loss), L.stream())
+        ctx.save_for_backward(x, y)
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        gs = g.reshape(1).float().contiguous()
+        _call("dwc_bce_logits_loss_bwd", L.ptr(x), L.ptr(y), L.i64(x.numel()), L.ptr(gs), L.ptr(dx), L.stream())
+        return dx, None
+
+
+def bce_logits(x, y):
+    return BceLogitsFn.apply(x, y)

@@ -1,0 +1,329 @@
+"""Solver: the reference's training-step API (solver.py:22-413) on the B200-native networks.
+
+Same constructor, method names, positional signatures and public attributes (loss_*, gen_opt,
+dis_opt, init_ds_w, gen, dis, gen_copy, dis_copy) as the reference, so train.py's loop body
+(train.py:92-111) runs unchanged.  Differences that do not change results:
+  * work the reference computes and throws away is skipped: the generator graph in
+    dis_update (its gradients are zeroed at solver.py:153), discriminator weight gradients in
+    gen_update, the backward of the detached decode (solver.py:181);
+  * D(x_real) is evaluated once and its loss terms counted twice (solver.py:333-334 evaluates it
+    twice on identical input);
+  * both Adam updates and the EMA are fused flat-buffer kernels (flat.py).
+Optional branches that configs/celeba_faces.yaml switches off (VGG loss, gradient penalty, R1,
+nsgan/wgan) are out of scope and raise NotImplementedError when enabled.
+"""
+from __future__ import annotations
+
+import copy
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .flat import FusedAdam
+from .gmm import gmm_earth_mover_distance_sp, gmm_kl_distance_sp
+from .networks import AdaINGen_v2, MsImageDis
+from .tools import dist_sampling_split
+from .utils import get_model_list, get_scheduler, moving_average, weights_init
+from .vocab import Vocab
+
+
+class _frozen:
+    """Temporarily mark a network's parameters as not requiring grad (skips its weight gradients)."""
+
+    def __init__(self, net):
+        self.params = [p for p in net.parameters() if p.requires_grad]
+
+    def __enter__(self):
+        for p in self.params:
+            p.requires_grad_(False)
+
+    def __exit__(self, *a):
+        for p in self.params:
+            p.requires_grad_(True)
+
+
+class Solver(nn.Module):
+    def __init__(self, configs, device=None, pretrained_embed=None):
+        super().__init__()
+        self.device = device if device is not None else torch.device('cpu')
+        self.configs = configs
+        if configs.get('vgg_w', 0) > 0:
+            raise NotImplementedError("the VGG perceptual loss is outside the B200 hot path (set vgg_w: 0)")
+        if configs.get('gp_w', 0) > 0 or configs.get('use_r1', False):
+            raise NotImplementedError("gradient penalty / R1 are outside the B200 hot path (gp_w: 0, use_r1: False)")
+
+        self.vocab = Vocab(dataset=configs['dataset'])
+        self.gen = AdaINGen_v2(configs['input_dim'], self.vocab, configs['gen'], pretrained_embed=pretrained_embed)
+        self.dis = MsImageDis(configs['input_dim'], configs['dis'], self.device)
+        self.instancenorm = nn.InstanceNorm2d(512, affine=False)
+
+        self.num_cls = configs['gen']['num_cls']
+        self.c_dim = configs['c_dim']
+        self.dist_mode = configs['dist_mode']
+        self.use_attention = configs['gen']['use_attention']
+        self.att_status = self.use_attention
+        self.ds_iter = configs['ds_iter']
+        self.display_size = int(configs['display_size'])
+        self.dataset = configs['dataset']
+        self.stddev = configs['stddev']
+        self.sigma = float(self.stddev ** 2)
+        self.d_reg_every = 16
+        self.rnd_step = 3
+        self.init_ds_w = configs['ds_w']
+        self.lr_policy = configs['lr_policy']
+
+        # same init order / RNG stream as the reference (solver.py:73-74)
+        self.apply(weights_init(configs['init']))
+        self.dis.apply(weights_init('gaussian'))
+        self.gen.flat.rebuild()
+        self.dis.flat.rebuild()
+
+        lr, betas = configs['lr'], (configs['beta1'], configs['beta2'])
+        self.dis_opt = FusedAdam(self.dis.flat, lr=lr, betas=betas, weight_decay=configs['weight_decay'])
+        self.gen_opt = FusedAdam(self.gen.flat, lr=lr, betas=betas, weight_decay=configs['weight_decay'])
+        self.dis_scheduler = get_scheduler(self.dis_opt, configs)
+        self.gen_scheduler = get_scheduler(self.gen_opt, configs)
+        self.criterionL1 = torch.nn.L1Loss()
+        self.grad_sync = None        # set by parallel.DataParallelSync
+        self.noise_hook = None       # tests: callable(name) -> eps tensor for dist_sampling_split
+
+    # ------------------------------------------------------------------ plumbing
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        for net, opt_name in ((self.gen, 'gen_opt'), (self.dis, 'dis_opt')):
+            net.ensure_flat()
+        # optimizers keep pointing at the (possibly rebuilt) flat buffers
+        for opt in (getattr(self, 'gen_opt', None), getattr(self, 'dis_opt', None)):
+            if opt is not None:
+                opt.m = opt.v = None
+        p = next(self.gen.parameters(), None)
+        if p is not None:
+            self.device = p.device
+            self.dis.device = p.device
+        return r
+
+    def copy_nets(self):
+        self.gen_copy = copy.deepcopy(self.gen)
+        self.dis_copy = copy.deepcopy(self.dis)
+
+    def update_learning_rate(self):
+        if self.lr_policy == 'cosa':
+            if self.dis_opt.param_groups[0]['lr'] == self.configs['eta_min'] or \
+                    self.gen_opt.param_groups[0]['lr'] == self.configs['eta_min']:
+                self.configs['step_size'] *= self.configs['t_mult']
+                self.dis_scheduler = get_scheduler(self.dis_opt, self.configs)
+                self.gen_scheduler = get_scheduler(self.gen_opt, self.configs)
+        if self.dis_scheduler is not None:
+            self.dis_scheduler.step()
+        if self.gen_scheduler is not None:
+            self.gen_scheduler.step()
+
+    def update_attention_status(self, iters):
+        if self.att_status:
+            self.use_attention = False if iters < 10000 else True
+
+    def recon_criterion(self, x, y):
+        return ops.l1_loss(x, y)
+
+    def criterion_l1(self, a, z):
+        if isinstance(a, (list, tuple)):
+            a = torch.cat(list(a), dim=1)
+        if isinstance(z, (list, tuple)):
+            z = torch.cat(list(z), dim=1)
+        return ops.l1_loss(a, z)
+
+    def style_replace(self, c_src, c_trg, z_src, z_trg):
+        mark = (c_src == c_trg).repeat_interleave(self.c_dim, dim=1)
+        return torch.where(mark, z_src, z_trg)
+
+    def _sample_style(self, c_trg, tag):
+        eps = self.noise_hook(tag) if self.noise_hook is not None else None
+        return dist_sampling_split(c_trg, self.c_dim, self.stddev, self.device, eps=eps)
+
+    def _blend(self, img, att, x_real):
+        return ops.blend(img, att, x_real) if self.use_attention else img
+
+    def _decode(self, content, style):
+        img, att = self.gen.decode(content, style)
+        return img, att
+
+    # ------------------------------------------------------------------ inference
+    def forward(self, x_real, txt_src2trg, txt_lens):
+        """Translate (solver.py:142-149, with Solver.sample's cat-then-decode semantics)."""
+        content, mu, _ = self.gen.encode_fused(x_real)
+        mt, _ = self.gen.encode_txt(mu, txt_src2trg, txt_lens)
+        img, att = self.gen.decode(content, torch.cat(mt, dim=1))
+        return self._blend(img, att, x_real)
+
+    # ------------------------------------------------------------------ G step
+    def gen_update(self, x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg, configs, iters):
+        gen, dis = self.gen, self.dis
+        self.gen_opt.zero_grad()
+        x_real = x_real.float()
+        content_real, mu_real, lv_real = gen.encode_fused(x_real)
+
+        x_real_rec, att = self._decode(content_real, mu_real)
+        x_real_rec = self._blend(x_real_rec, att, x_real)
+        content_real_rec, mu_real_rec, _ = gen.encode_fused(x_real_rec)
+
+        mt, lvt = gen.encode_txt(mu_real, txt_src2trg, txt_lens)
+        mu_txt, lv_txt = torch.cat(mt, dim=1), torch.cat(lvt, dim=1)
+        x_fake, att = self._decode(content_real, mu_txt)
+        x_fake = self._blend(x_fake, att, x_real)
+
+        style1 = self._sample_style(c_trg, 'gen1')
+        x_fake1, att1 = self._decode(content_real, style1)
+        style2 = self._sample_style(c_trg, 'gen2')
+        with torch.no_grad():                                   # solver.py:181 detaches this branch
+            x_fake2, att2 = self._decode(content_real, style2)
+            x_fake2 = self._blend(x_fake2, att2, x_real)
+        x_fake1 = self._blend(x_fake1, att1, x_real)
+        self.loss_ds = ops.l1_loss(x_fake1, x_fake2)
+        content_rand, mu_rand, _ = gen.encode_fused(x_fake1)
+        self.init_ds_w = max(self.init_ds_w - 1 / 1e5, 0.0)
+
+        content_fake_rec, mu_fake_rec, _ = gen.encode_fused(x_fake)
+        if configs['recon_x_cyc_w'] > 0:
+            x_cycle, att_c = self._decode(content_fake_rec, mu_real)
+            x_cycle = self._blend(x_cycle, att_c, x_real)
+
+        self.loss_gen_recon_x = self.recon_criterion(x_real_rec, x_real)
+        self.loss_gen_recon_c_real = self.recon_criterion(content_real_rec, content_real)
+        self.loss_gen_recon_c_fake = self.recon_criterion(content_fake_rec, content_real)
+        self.loss_gen_recon_c_rand = self.recon_criterion(content_rand, content_real)
+        self.loss_gen_recon_s_real = self.criterion_l1(mu_real_rec, mu_real)
+        self.loss_gen_recon_s_fake = self.criterion_l1(mu_fake_rec, mu_txt)
+        self.loss_gen_recon_s_rand = self.criterion_l1(mu_rand, style1)
+        self.loss_gen_cycrecon_x = 0
+        if configs['recon_x_cyc_w'] > 0:
+            self.loss_gen_cycrecon_x = self.recon_criterion(x_cycle, x_real)
+
+        with _frozen(dis):                                      # D weight gradients are never used here
+            self.loss_gen_adv = dis.calc_gen_loss(x_fake, label_trg, configs['gan_w'], configs['cls_w']) + \
+                dis.calc_gen_loss(x_fake1, label_trg, configs['gan_w'], configs['cls_w'])
+
+            self.loss_kl_x, self.loss_kl_trg = 0.0, 0.0
+            if self.dist_mode == 'kls':
+                self.loss_kl_x = gmm_kl_distance_sp(mu_real, lv_real, c_src, self.sigma)
+                self.loss_kl_trg = gmm_kl_distance_sp(mu_txt, lv_txt, c_trg, self.sigma)
+            else:
+                self.loss_kl_x = gmm_earth_mover_distance_sp(mu_real, c_src)
+                self.loss_kl_trg = gmm_earth_mover_distance_sp(mu_txt, c_trg)
+            self.loss_gen_vgg = 0
+
+            self.loss_gen_total = self.loss_gen_adv + \
+                configs['recon_x_w'] * self.loss_gen_recon_x + \
+                configs['recon_c_w'] * self.loss_gen_recon_c_real + \
+                configs['recon_c_w'] * self.loss_gen_recon_c_fake + \
+                configs['recon_c_w'] * self.loss_gen_recon_c_rand + \
+                configs['recon_s_w'] * self.loss_gen_recon_s_real + \
+                configs['recon_s_w'] * self.loss_gen_recon_s_fake + \
+                configs['recon_s_w'] * self.loss_gen_recon_s_rand + \
+                configs['recon_x_cyc_w'] * self.loss_gen_cycrecon_x + \
+                configs['kl_w'] * self.loss_kl_x + \
+                configs['kl_w'] * self.loss_kl_trg - \
+                self.init_ds_w * self.loss_ds
+            self.loss_gen_total.backward()
+        if self.grad_sync is not None:
+            self.grad_sync(self.gen)
+        self.gen_opt.step()
+
+    # ------------------------------------------------------------------ D step
+    def dis_update(self, x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg, configs, iters):
+        gen, dis = self.gen, self.dis
+        self.dis_opt.zero_grad()
+        x_real = x_real.float()
+        with torch.no_grad():                                   # G gradients of this phase are discarded anyway
+            content_real, mu_real, _ = gen.encode_fused(x_real)
+            style1 = self._sample_style(c_trg, 'dis1')
+            mt, _ = gen.encode_txt(mu_real, txt_src2trg, txt_lens)
+            x_fake, att = self._decode(content_real, torch.cat(mt, dim=1))
+            x_fake1, att1 = self._decode(content_real, style1)
+            x_fake = self._blend(x_fake, att, x_real)
+            x_fake1 = self._blend(x_fake1, att1, x_real)
+
+        gw, cw = configs['gan_w'], configs['cls_w']
+        outs_real = dis.forward(x_real)
+        loss = 0.0
+        for fake in (x_fake, x_fake1):
+            outs_fake = dis.forward(fake)
+            for of, orl in zip(outs_fake, outs_real):
+                loss = loss + ops.mse_const(of[0], 0.0) * gw
+        # real-branch terms appear once per calc_dis_loss call, i.e. twice (solver.py:333-334)
+        for orl in outs_real:
+            loss = loss + 2.0 * (ops.mse_const(orl[0], 1.0) * gw + ops.bce_logits(orl[1], label_src) * cw)
+        self.loss_dis = loss
+        self.loss_dis_all = self.loss_dis
+        self.loss_dis_all.backward()
+        if self.grad_sync is not None:
+            self.grad_sync(self.dis)
+        self.dis_opt.step()
+
+    def smooth_moving(self):
+        moving_average(self.gen, self.gen_copy)
+        moving_average(self.dis, self.dis_copy)
+
+    # ------------------------------------------------------------------ sampling / checkpoints
+    @torch.no_grad()
+    def sample(self, x_real, txt_src2trg, txt_lens):
+        """solver.py:249-289, per image as the reference does (the text encoder mixes batch rows)."""
+        self.eval()
+        recs, abs_, sams, atts = [], [], [], []
+        for i in range(x_real.size(0)):
+            xr = x_real[i:i + 1].float()
+            content, mu, _ = self.gen.encode_fused(xr)
+            mt, _ = self.gen.encode_txt(mu, txt_src2trg[i:i + 1], txt_lens[i:i + 1])
+            style_txt = torch.cat(mt, dim=1)
+            x_rec, a_rec = self.gen.decode(content, mu)
+            x_trg, a_trg = self.gen.decode(content, style_txt)
+            sign = lambda s: torch.where(s.view(1, self.num_cls, self.c_dim).mean(2) < 0.0, -1.0, 1.0)
+            mus_real, mus_txt = sign(mu), sign(style_txt)
+            z = self._sample_style(mus_txt, 'sample')
+            z = self.style_replace(mus_real, mus_txt, mu, z)
+            x_sam, a_sam = self.gen.decode(content, z)
+            if self.use_attention:
+                x_trg = ops.blend(x_trg, a_trg, xr)
+                x_rec = ops.blend(x_rec, a_rec, xr)
+                x_sam = ops.blend(x_sam, a_sam, xr)
+                atts.append(torch.cat([a_trg, a_trg, a_trg], dim=1))
+            abs_.append(x_trg)
+            recs.append(x_rec)
+            sams.append(x_sam)
+        outputs = [x_real, torch.cat(recs), torch.cat(abs_), torch.cat(sams)]
+        if self.use_attention:
+            outputs.append((torch.cat(atts) - 0.5) / 0.5)
+        self.train()
+        return outputs
+
+    def resume(self, checkpoint_dir, configs):
+        last = get_model_list(checkpoint_dir, "gen")
+        self.gen.load_state_dict(torch.load(last, map_location='cpu')['a'])
+        iterations = int(last[-15:-7]) if 'avg' in last else int(last[-11:-3])
+        last = get_model_list(checkpoint_dir, "dis")
+        self.dis.load_state_dict(torch.load(last, map_location='cpu')['b'])
+        self.dis_scheduler = get_scheduler(self.dis_opt, configs, iterations)
+        self.gen_scheduler = get_scheduler(self.gen_opt, configs, iterations)
+        print('Resume from iteration %d' % iterations)
+        return iterations
+
+    def init_network(self, gen_path, dis_path):
+        gen_dict = torch.load(gen_path, map_location='cpu')['a']
+        dis_dict = torch.load(dis_path, map_location='cpu')['b']
+        dsd = self.dis.state_dict()
+        self.dis.load_state_dict({k: dis_dict.get(k, v) for k, v in dsd.items()})
+        gsd = self.gen.state_dict()
+        self.gen.load_state_dict({k: (gen_dict[k] if k in gen_dict and 'embed_tokens' not in k else v)
+                                  for k, v in gsd.items()})
+        print("Initial model loaded...")
+
+    def save(self, snapshot_dir, iterations):
+        n = iterations + 1
+        cont = lambda sd: {k: v.contiguous() for k, v in sd.items()}
+        torch.save({'a': cont(self.gen.state_dict())}, os.path.join(snapshot_dir, 'gen_%08d.pt' % n))
+        torch.save({'b': cont(self.dis.state_dict())}, os.path.join(snapshot_dir, 'dis_%08d.pt' % n))
+        torch.save({'a': cont(self.gen_copy.state_dict())}, os.path.join(snapshot_dir, 'gen_%08d_avg.pt' % n))
+        torch.save({'b': cont(self.dis_copy.state_dict())}, os.path.join(snapshot_dir, 'dis_%08d_avg.pt' % n))
+        torch.save({'gen': self.gen_opt.state_dict(), 'dis': self.dis_opt.state_dict()},
+                   os.path.join(snapshot_dir, 'optimizer.pt'))

@@ -1,0 +1,109 @@
+"""GPU parity of each sub-network (forward values and parameter gradients) against the CPU oracle
+(oracle/dwc_oracle.py), fp32 validation mode (tolerance 1e-4 on outputs, SURVEY/BASELINE) and bf16 product mode
+(tolerance 2e-2).  Everything goes through the reference-shaped nn.Module API."""
+import pytest
+import torch
+
+from oracle import dwc_oracle as O
+from tests.util_gpu import build_solver, compare_grads, cpu_state, grads_of, rel, to_cuda
+
+pytestmark = pytest.mark.gpu
+
+MODES = [("fp32", 1e-4, 2e-3), ("bf16", 2e-2, 5e-2)]
+
+
+def leaf(P):
+    return {k: v.clone().requires_grad_(True) for k, v in P.items()}
+
+
+@pytest.mark.parametrize("mode,tol,gtol", MODES)
+def test_encode(mode, tol, gtol):
+    s, _ = build_solver(mode)
+    G = leaf(O.trainable(cpu_state(s.gen)))
+    batch = O.synthetic_batch(2, 128, seed=3)
+    x = batch["x_real"]
+    c_ref, mus, lvs = O.encode(G, x)
+    mu_ref, lv_ref = torch.cat(mus, 1), torch.cat(lvs, 1)
+    wc, wm, wl = torch.randn_like(c_ref), torch.randn_like(mu_ref), torch.randn_like(lv_ref)
+    ((c_ref * wc).sum() / 100 + (mu_ref * wm).sum() + (lv_ref * wl).sum()).backward()
+
+    s.gen_opt.zero_grad()
+    content, mu_l, lv_l = s.gen.encode(x.cuda())
+    mu, lv = torch.cat(mu_l, 1), torch.cat(lv_l, 1)
+    assert content.shape == c_ref.shape and len(mu_l) == 8 and mu_l[0].shape == (2, 8)
+    assert rel(content.float(), c_ref) < tol * 3, rel(content.float(), c_ref)
+    assert rel(mu, mu_ref) < tol * 3 and rel(lv, lv_ref) < tol * 3
+    ((content.float() * wc.cuda()).sum() / 100 + (mu * wm.cuda()).sum() + (lv * wl.cuda()).sum()).backward()
+    worst, wk, glob = compare_grads(grads_of(s.gen), {k: v.grad for k, v in G.items()})
+    assert glob < gtol and worst < 10 * gtol, (worst, wk, glob)
+
+
+@pytest.mark.parametrize("mode,tol,gtol", MODES)
+def test_decode(mode, tol, gtol):
+    s, _ = build_solver(mode)
+    G = leaf(O.trainable(cpu_state(s.gen)))
+    torch.manual_seed(5)
+    content = torch.randn(2, 256, 32, 32).to(torch.bfloat16).float()
+    style = torch.randn(2, 64)
+    c_leaf = content.clone().requires_grad_(True)
+    s_leaf = style.clone().requires_grad_(True)
+    img_ref, att_ref = O.decode(G, c_leaf, s_leaf)
+    wi, wa = torch.randn_like(img_ref), torch.randn_like(att_ref)
+    ((img_ref * wi).sum() + (att_ref * wa).sum()).backward()
+
+    s.gen_opt.zero_grad()
+    cc = content.cuda().to(dtype=torch.float32 if mode == "fp32" else torch.bfloat16)
+    cc = cc.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    sc = style.cuda().requires_grad_(True)
+    img, att = s.gen.decode(cc, sc)
+    assert rel(img, img_ref) < tol * 3 and rel(att, att_ref) < tol * 3, (rel(img, img_ref), rel(att, att_ref))
+    ((img * wi.cuda()).sum() + (att * wa.cuda()).sum()).backward()
+    worst, wk, glob = compare_grads(grads_of(s.gen), {k: v.grad for k, v in G.items()})
+    assert glob < gtol and worst < 10 * gtol, (worst, wk, glob)
+    assert rel(cc.grad.float(), c_leaf.grad) < gtol and rel(sc.grad, s_leaf.grad) < gtol
+
+
+@pytest.mark.parametrize("mode,tol,gtol", MODES)
+def test_discriminator(mode, tol, gtol):
+    s, cfg = build_solver(mode)
+    D = leaf(cpu_state(s.dis))
+    batch = O.synthetic_batch(3, 128, seed=4)
+    x = batch["x_real"].clone().requires_grad_(True)
+    loss_ref = O.dis_loss(D, x, batch["x_real"].flip(0), batch["label_src"]) + O.gen_adv_loss(D, x, batch["label_trg"])
+    loss_ref.backward()
+
+    s.dis_opt.zero_grad()
+    b = to_cuda(batch)
+    xc = b["x_real"].clone().requires_grad_(True)
+    outs = s.dis(xc)
+    assert len(outs) == 2 and outs[0][0].shape == (3, 1, 4, 4) and outs[1][0].shape == (3, 1, 2, 2) and outs[0][1].shape == (3, 8)
+    loss = s.dis.calc_dis_loss(xc, b["x_real"].flip(0), b["label_trg"], b["label_src"]) + \
+        s.dis.calc_gen_loss(xc, b["label_trg"])
+    assert abs(float(loss) - float(loss_ref)) < tol * abs(float(loss_ref)) * 3, (float(loss), float(loss_ref))
+    loss.backward()
+    worst, wk, glob = compare_grads(grads_of(s.dis), {k: v.grad for k, v in D.items()})
+    assert glob < gtol and worst < 10 * gtol, (worst, wk, glob)
+    assert rel(xc.grad, x.grad) < gtol * 2
+
+
+@pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 2e-3)])
+def test_text_encoder(mode, tol, gtol):
+    s, _ = build_solver(mode)
+    G = leaf(O.trainable(cpu_state(s.gen)))
+    batch = O.synthetic_batch(4, 128, seed=6)
+    style = torch.randn(4, 64)
+    st = style.clone().requires_grad_(True)
+    mus, lvs = O.text_encoder(G, st, batch["txt"], batch["txt_lens"])
+    mu_ref, lv_ref = torch.cat(mus, 1), torch.cat(lvs, 1)
+    wm, wl = torch.randn_like(mu_ref), torch.randn_like(lv_ref)
+    ((mu_ref * wm).sum() + (lv_ref * wl).sum()).backward()
+
+    s.gen_opt.zero_grad()
+    sc = style.cuda().requires_grad_(True)
+    mu_l, lv_l = s.gen.encode_txt(sc, batch["txt"].cuda(), batch["txt_lens"].cuda())
+    mu, lv = torch.cat(mu_l, 1), torch.cat(lv_l, 1)
+    assert rel(mu, mu_ref) < tol * 3 and rel(lv, lv_ref) < tol * 3, (rel(mu, mu_ref), rel(lv, lv_ref))
+    ((mu * wm.cuda()).sum() + (lv * wl.cuda()).sum()).backward()
+    worst, wk, glob = compare_grads(grads_of(s.gen), {k: v.grad for k, v in G.items()})
+    assert glob < gtol and worst < 10 * gtol, (worst, wk, glob)
+    assert rel(sc.grad, st.grad) < gtol
