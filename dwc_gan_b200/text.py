@@ -25,7 +25,7 @@ def _lstm_groups(num_layers):
 
 class TxtBodyFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, style, anchor, enc, tokens, lens, mask_in, mask_mid):
+    def forward(ctx, style, anchor, enc, tokens, lens, mask_in, mask_mid, need_grad):
         ops._require_cuda(style)
         owner = enc.__dict__["_owner"]
         f = owner.flat
@@ -35,7 +35,6 @@ class TxtBodyFn(torch.autograd.Function):
         tokens = tokens.contiguous()
         lens = lens.to(torch.int64).contiguous()
         style = style.contiguous().float()
-        need_grad = torch.is_grad_enabled() and (style.requires_grad or anchor.requires_grad)
         pre = owner.param_name_of(enc, "lstm.weight_ih_l0")[:-len("weight_ih_l0")]
         emb_name = owner.param_name_of(enc, "embed_tokens.weight")
 
@@ -140,7 +139,7 @@ class TxtBodyFn(torch.autograd.Function):
         _call("dwc_embed_concat_bwd", L.ptr(tokens), L.ptr(dseq), L.ptr(mask_in), L.ptr(demb), L.ptr(dstyle), B, T, E, S,
               int(enc.embed_tokens.padding_idx), L.stream())
         ctx.saved = None
-        return dstyle, None, None, None, None, None, None
+        return dstyle, None, None, None, None, None, None, None
 
 
 def txt_encode(enc, style, tokens, lens):
@@ -155,4 +154,5 @@ def txt_encode(enc, style, tokens, lens):
         if enc.num_layers > 1 and p > 0:
             mask_mid = (torch.rand(T, B, 2 * enc.hidden_size, device=dev) >= p).float() / (1 - p)
     anchor = enc.lstm.weight_hh_l0
-    return TxtBodyFn.apply(style, anchor, enc, tokens, lens, mask_in, mask_mid)
+    need_grad = torch.is_grad_enabled() and (style.requires_grad or anchor.requires_grad)
+    return TxtBodyFn.apply(style, anchor, enc, tokens, lens, mask_in, mask_mid, need_grad)

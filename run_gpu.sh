@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-python dwc_gan_b200/build.py > gpurun_out/build.log 2>&1 || tail -5 gpurun_out/build.log
-for f in test_modules_gpu test_step_gpu; do
-  timeout -k 10 1200 python -m pytest tests/$f.py -q -m gpu -x --tb=short 2>&1 | tail -60 > gpurun_out/$f.log
-  echo "== $f"; tail -45 gpurun_out/$f.log
-done
+timeout -k 10 1500 python -m pytest tests/test_modules_gpu.py -q -m gpu -n 4 --tb=line 2>&1 | tail -30 > gpurun_out/test_modules_gpu.log
+echo "== modules"; tail -30 gpurun_out/test_modules_gpu.log
+timeout -k 10 1500 python -m pytest tests/test_step_gpu.py -q -m gpu -n 2 --tb=short -rP 2>&1 | grep -v "^frame\|python()\|Warning" | tail -80 > gpurun_out/test_step_gpu.log
+echo "== step"; tail -80 gpurun_out/test_step_gpu.log

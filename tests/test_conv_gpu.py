@@ -46,6 +46,9 @@ CASES = [
     (2, 16, 16, 3, 64, 7, 1, 3),
     (2, 16, 16, 3, 64, 4, 2, 1),
     (1, 32, 32, 256, 256, 3, 1, 1),
+    (3, 8, 8, 512, 512, 4, 2, 1),
+    (3, 16, 16, 256, 512, 4, 2, 1),
+    (2, 16, 16, 64, 4, 7, 1, 3),
 ]
 MODES = [("simt", torch.float32), ("simt", torch.bfloat16), ("tc", torch.bfloat16)]
 

@@ -50,9 +50,12 @@ def grads_of(net):
             for k, p in net.named_parameters()}
 
 
-def compare_grads(mine, ref, skip_tiny=1e-6):
-    """(worst per-tensor rel err, its key, global rel err) ignoring tensors whose reference gradient is round-off."""
+def compare_grads(mine, ref, skip_rel=1e-5):
+    """(worst per-tensor rel err, its key, global rel err).  Tensors whose reference gradient is pure round-off
+    (biases in front of InstanceNorm/AdaIN: exactly zero in exact arithmetic) are left out of the per-tensor figure."""
     worst, wk, num, den = 0.0, None, 0.0, 0.0
+    gmax = max(float(g.double().norm()) for g in ref.values() if g is not None)
+    skip_tiny = skip_rel * gmax
     for k, g in ref.items():
         if g is None:
             continue
