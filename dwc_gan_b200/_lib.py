@@ -52,6 +52,8 @@ class WGrad(C.Structure):
         ("dbias", C.c_void_p),
         ("accumulate", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("remap_axis", C.c_int32), ("remap_div", C.c_int32), ("remap_lo_limit", C.c_int32), ("remap_hi_limit", C.c_int32),
+        ("remap_hi_stride", C.c_int64), ("remap_lo_stride", C.c_int64),
     ]
 
 
@@ -64,9 +66,9 @@ EXPORTS = [
     "dwc_last_error", "dwc_abi_version", "dwc_tc_available", "dwc_gconv", "dwc_wgrad_workspace_bytes", "dwc_wgrad",
     "dwc_nc_stats", "dwc_norm_finalize", "dwc_post_fwd", "dwc_post_bwd_reduce", "dwc_norm_bwd_finalize",
     "dwc_post_bwd_apply", "dwc_upsample_pad_fwd", "dwc_upsample_pad_bwd", "dwc_image_pad_fwd", "dwc_image_pad_bwd",
-    "dwc_heads_fwd", "dwc_heads_bwd", "dwc_blend_fwd", "dwc_blend_bwd", "dwc_relu_gap_fwd", "dwc_relu_gap_bwd",
+    "dwc_heads_fwd", "dwc_heads_bwd", "dwc_image_rows_fwd", "dwc_heads_bwd_rows", "dwc_blend_fwd", "dwc_blend_bwd", "dwc_relu_gap_fwd", "dwc_relu_gap_bwd",
     "dwc_sgemm", "dwc_colsum", "dwc_relu_bwd", "dwc_mul", "dwc_embed_concat_fwd", "dwc_embed_concat_bwd",
-    "dwc_lstm_step_fwd", "dwc_lstm_step_bwd", "dwc_gmm_sample", "dwc_gmm_kl", "dwc_l1_loss_fwd", "dwc_l1_loss_bwd",
+    "dwc_lstm_step_fwd", "dwc_lstm_step_bwd", "dwc_transpose", "dwc_gmm_sample", "dwc_gmm_kl", "dwc_l1_loss_fwd", "dwc_l1_loss_bwd",
     "dwc_mse_const_loss_fwd", "dwc_mse_const_loss_bwd", "dwc_bce_logits_loss_fwd", "dwc_bce_logits_loss_bwd",
     "dwc_adam_step", "dwc_ema_step", "dwc_pack_weights", "dwc_cast", "dwc_fill",
 ]

@@ -766,3 +766,132 @@ extern "C" int dwc_relu_gap_bwd(const float* dout, const dwc_hbuf_t* y, const dw
   DWC_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// row-im2col buffers that put the 3-channel / 4-channel convolutions on the tensor-core kernels
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void image_rows_fwd_kernel(const float* __restrict__ img, int N, int C, int H, int W, int pool, int pad, int sx,
+                                      int ys, int Wo, T* __restrict__ rows) {
+  const int h = H / pool, w = W / pool;               // interior after pooling
+  const int Hp = h + 2 * pad, Wp = w + 2 * pad;
+  const int Yr = Hp / ys;
+  const long long total = (long long)N * ys * Yr * Wo * 8;      // one thread per (pixel window slot j)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(i & 7);
+    long long r = i >> 3;
+    int x = (int)(r % Wo); r /= Wo;
+    int yr = (int)(r % Yr); r /= Yr;
+    int z = (int)(r % ys);
+    int n = (int)(r / ys);
+    const int Y = yr * ys + z, X = x * sx + j;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (X < Wp) {
+      const int iy = reflect_idx(Y - pad, h), ix = reflect_idx(X - pad, w);
+      for (int ch = 0; ch < C && ch < 8; ++ch) {
+        const float* p = img + ((long long)n * C + ch) * H * W;
+        if (pool == 1) v[ch] = p[(long long)iy * W + ix];
+        else {
+          const float* q = p + (long long)(pool * iy) * W + pool * ix;
+          float acc = 0.f;
+          for (int a = 0; a < pool; ++a)
+            for (int b = 0; b < pool; ++b) acc += q[(long long)a * W + b];
+          v[ch] = acc / (float)(pool * pool);
+        }
+      }
+    }
+    Vec8<T>::store(rows + i * 8, v);
+  }
+}
+extern "C" int dwc_image_rows_fwd(const float* img, int n, int c, int h, int w, int pool, int pad, int sx, int ys, int wo,
+                                  void* rows, int dtype, dwc_stream_t stream) {
+  DWC_CHECK(c <= 8 && pool >= 1 && (ys == 1 || ys == 2) && ((h / pool + 2 * pad) % ys) == 0, "dwc_image_rows_fwd: bad geometry");
+  long long total = (long long)n * (h / pool + 2 * pad) * wo * 8;
+  DISPATCH_T(dtype, (image_rows_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
+                        img, n, c, h, w, pool, pad, sx, ys, wo, reinterpret_cast<T*>(rows))));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// dy of the fused heads at interior pixel (n, y, x), 4 channels (0 outside the image)
+__device__ __forceinline__ void heads_dy(const float* __restrict__ dimg, const float* __restrict__ datt,
+                                         const float* __restrict__ img, const float* __restrict__ att, int n, int y, int x,
+                                         int H, int W, float* d) {
+  d[0] = d[1] = d[2] = d[3] = 0.f;
+  if (y < 0 || y >= H || x < 0 || x >= W) return;
+  const long long hw = (long long)H * W, p = (long long)y * W + x;
+  if (dimg) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      long long k = ((long long)n * 3 + c) * hw + p;
+      float t = img[k];
+      d[c] = dimg[k] * (1.f - t * t);
+    }
+  }
+  if (datt) {
+    float a = att[(long long)n * hw + p];
+    d[3] = datt[(long long)n * hw + p] * a * (1.f - a);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    heads_bwd_rows_kernel(const float* __restrict__ dimg, const float* __restrict__ datt, const float* __restrict__ img,
+                          const float* __restrict__ att, int N, int H, int W, int halo, T* __restrict__ rows_d,
+                          T* __restrict__ win, float* __restrict__ part) {
+  const int Hh = H + 2 * halo, Wh = W + 2 * halo, Wu = W + halo;
+  const long long n_rows = (long long)N * Hh * Wh * 8;      // rows_d slots
+  const long long n_win = (long long)N * H * Wu * 8;        // win slots
+  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_rows + n_win; i += (long long)gridDim.x * blockDim.x) {
+    float v[8], d[4];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (i < n_rows) {
+      int j = (int)(i & 7);
+      long long r = i >> 3;
+      int X = (int)(r % Wh); r /= Wh;
+      int Y = (int)(r % Hh);
+      int n = (int)(r / Hh);
+      heads_dy(dimg, datt, img, att, n, Y - halo, X + j - halo, H, W, d);
+      v[0] = d[0]; v[1] = d[1]; v[2] = d[2]; v[3] = d[3];
+      Vec8<T>::store(rows_d + i * 8, v);
+    } else {
+      long long k = i - n_rows;
+      int j = (int)(k & 7);
+      long long r = k >> 3;
+      int u = (int)(r % Wu); r /= Wu;
+      int y = (int)(r % H);
+      int n = (int)(r / H);
+      heads_dy(dimg, datt, img, att, n, y, u - j, H, W, d);
+      v[0] = d[0]; v[1] = d[1]; v[2] = d[2]; v[3] = d[3];
+      Vec8<T>::store(win + k * 8, v);
+      if (j == 0) { bs[0] += d[0]; bs[1] += d[1]; bs[2] += d[2]; bs[3] += d[3]; }   // each pixel once (u = x)
+    }
+  }
+  __shared__ float red[4][256];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) red[c][threadIdx.x] = bs[c];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) red[c][threadIdx.x] += red[c][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) part[(long long)blockIdx.x * 4 + threadIdx.x] = red[threadIdx.x][0];
+}
+extern "C" int dwc_heads_bwd_rows(const float* dimg, const float* datt, const float* img, const float* att, int n, int h,
+                                  int w, int halo, void* rows_d, void* win, int dtype, float* part, int32_t* nblocks,
+                                  dwc_stream_t stream) {
+  long long total = (long long)n * (h + 2 * halo) * (w + 2 * halo) * 8 + (long long)n * h * (w + halo) * 8;
+  int grid = ew_grid(total);
+  if (grid > 1024) grid = 1024;
+  *nblocks = grid;
+  DISPATCH_T(dtype, (heads_bwd_rows_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(
+                        dimg, datt, img, att, n, h, w, halo, reinterpret_cast<T*>(rows_d), reinterpret_cast<T*>(win), part)));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}

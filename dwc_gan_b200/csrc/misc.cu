@@ -231,6 +231,20 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int K
       long long r = i % K;
       int tp = (int)(r / Cout), co = (int)(r % Cout);
       if (row < Cin) v = w[((long long)co * taps + (taps - 1 - tp)) * Cin + row];
+    } else if (mode == 3) {
+      // out[row=co][kh][j*8+ci] = w[co][kh][j][ci]
+      long long K = (long long)KH * 64;
+      int row = (int)(i / K);
+      int r = (int)(i % K);
+      int kh = r >> 6, j = (r >> 3) & 7, ci = r & 7;
+      if (row < Cout && j < KW && ci < Cin) v = w[(((long long)row * KH + kh) * KW + j) * Cin + ci];
+    } else if (mode == 4) {
+      // out[row=ci][kh'][j*8+co] = w[co][KH-1-kh'][KW-1-j][ci]
+      long long K = (long long)KH * 64;
+      int row = (int)(i / K);
+      int r = (int)(i % K);
+      int khp = r >> 6, j = (r >> 3) & 7, co = r & 7;
+      if (row < Cin && j < KW && co < Cout) v = w[(((long long)co * KH + (KH - 1 - khp)) * KW + (KW - 1 - j)) * Cin + row];
     } else {
       // 4 phases: out[phase][row=ci][(i',j')][co] = w[co][2(1-i')+py][2(1-j')+px][ci]   (KH = KW = 4)
       long long K = 4LL * Cout;
@@ -249,11 +263,13 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int K
 }
 extern "C" int dwc_pack_weights(const float* w, int cout, int taps_h, int taps_w, int cin, int mode, void* out,
                                 int out_dtype, int rows_padded, dwc_stream_t stream) {
-  DWC_CHECK(mode >= 0 && mode <= 2, "dwc_pack_weights: bad mode");
+  DWC_CHECK(mode >= 0 && mode <= 4, "dwc_pack_weights: bad mode");
+  DWC_CHECK(mode < 3 || (taps_w <= 8 && (mode == 3 ? cin : cout) <= 8), "dwc_pack_weights: row-im2col modes need kw, c <= 8");
   DWC_CHECK(mode != 2 || (taps_h == 4 && taps_w == 4), "dwc_pack_weights: mode 2 needs a 4x4 kernel");
   long long total;
   if (mode == 0) total = (long long)rows_padded * taps_h * taps_w * cin;
   else if (mode == 1) total = (long long)rows_padded * taps_h * taps_w * cout;
+  else if (mode == 3 || mode == 4) total = (long long)rows_padded * taps_h * 64;
   else total = 4LL * rows_padded * 4 * cout;
   if (out_dtype == DWC_F32)
     pack_weights_kernel<float><<<grid1d(total), 256, 0, as_stream(stream)>>>(w, cout, taps_h, taps_w, cin, mode,

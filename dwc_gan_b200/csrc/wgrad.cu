@@ -122,19 +122,21 @@ constexpr int WG_PIX = 64;                      // pixels per stage (K extent)
 constexpr int WG_BOX_BYTES = WG_PIX * 128;      // one (64 pixel x 64 channel) TMA box = 8 KB
 constexpr int WG_THREADS = 192;
 
-template <int BN> struct WgCfg {
-  static constexpr int M_BYTES = 2 * WG_BOX_BYTES;          // 128 channels
+template <int BN, int MR = 128> struct WgCfg {
+  static constexpr int M_BYTES = (MR / 64) * WG_BOX_BYTES;   // MR channels
   static constexpr int N_BYTES = (BN / 64) * WG_BOX_BYTES;
   static constexpr int STAGE = M_BYTES + N_BYTES;
   static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 5 : 6);
   static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
 };
 
-template <int BN>
+// MR = 128: accumulator rows = 128 channels.  MR = 64: UMMA M = 64, whose 64 rows live in TMEM lanes
+// {0-15, 32-47, 64-79, 96-111} (16 per warp quadrant).
+template <int BN, int MR>
 __global__ void __launch_bounds__(WG_THREADS)
     wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
                     const __grid_constant__ WgradDev p) {
-  using Cfg = WgCfg<BN>;
+  using Cfg = WgCfg<BN, MR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(WG_THREADS)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mblocks = p.cm / 128, nblocks = p.cn / BN;
+  const int mblocks = p.cm / MR, nblocks = p.cn / BN;
   int wid = blockIdx.x;
   const int mb = wid % mblocks; wid /= mblocks;
   const int nb = wid % nblocks; wid /= nblocks;
@@ -182,8 +184,8 @@ __global__ void __launch_bounds__(WG_THREADS)
         mbar_expect_tx(&full_bar[stage], Cfg::STAGE);
         uint8_t* s = smem + stage * Cfg::STAGE;
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          tma_load_5d(s + j * WG_BOX_BYTES, &tmM, &full_bar[stage], mb * 128 + j * 64, x0 + mdx, y0 + mdy, mdz, n0);
+        for (int j = 0; j < MR / 64; ++j)
+          tma_load_5d(s + j * WG_BOX_BYTES, &tmM, &full_bar[stage], mb * MR + j * 64, x0 + mdx, y0 + mdy, mdz, n0);
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
           tma_load_5d(s + Cfg::M_BYTES + j * WG_BOX_BYTES, &tmN, &full_bar[stage], nb * BN + j * 64, x0 + ndx,
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(WG_THREADS)
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);   // both operands MN-major
+      constexpr uint32_t idesc = umma_idesc_bf16(MR, BN, 1, 1);   // both operands MN-major
       int stage = 0;
       uint32_t phase = 0;
       uint32_t first = 1;
@@ -223,7 +225,8 @@ __global__ void __launch_bounds__(WG_THREADS)
     }
   } else {
     const int q = warp & 3;
-    const int m = mb * 128 + q * 32 + lane;
+    const int m = MR == 128 ? mb * 128 + q * 32 + lane : mb * 64 + q * 16 + (lane & 15);
+    const bool row_ok = MR == 128 || lane < 16;
     float* ws = p.ws + (((long long)split * p.ntaps + t) * p.cm + m) * p.cn + nb * BN;
     if (tile_end > tile_begin) {
       mbar_wait(tmem_full, 0);
@@ -233,13 +236,15 @@ __global__ void __launch_bounds__(WG_THREADS)
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
         tmem_ld_wait();
+        if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(ws + cc + j) =
-              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                          __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(ws + cc + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+        }
       }
-    } else {
+    } else if (row_ok) {
       for (int cc = 0; cc < BN; cc += 4) *reinterpret_cast<float4*>(ws + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -251,54 +256,74 @@ __global__ void __launch_bounds__(WG_THREADS)
   }
 }
 
-// dw[m*s_m + t*s_t + n*s_n] (+)= sum_s ws[s][t][m][n]
+// dw[m*s_m + t*s_t + n*s_n] (+)= sum_s ws[s][t][m][n]   (optionally with one index split, see dwc_wgrad_t)
+struct WgRemap {
+  int axis, div, lo_limit, hi_limit;
+  long long hi_stride, lo_stride;
+};
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int ntaps, int cm, int cn, float* dw,
-                                    long long s_m, long long s_t, long long s_n, int accumulate) {
+                                    long long s_m, long long s_t, long long s_n, int accumulate, WgRemap rm) {
   const long long total = (long long)ntaps * cm * cn;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += ws[k * total + i];
     int n = (int)(i % cn);
     long long r = i / cn;
     int m = (int)(r % cm);
     int t = (int)(r / cm);
-    float* o = dw + m * s_m + t * s_t + n * s_n;
+    long long om = m * s_m, on = n * s_n;
+    if (rm.axis == 1) {
+      if (m % rm.div >= rm.lo_limit || m / rm.div >= rm.hi_limit) continue;
+      om = (m / rm.div) * rm.hi_stride + (m % rm.div) * rm.lo_stride;
+    } else if (rm.axis == 2) {
+      if (n % rm.div >= rm.lo_limit || n / rm.div >= rm.hi_limit) continue;
+      on = (n / rm.div) * rm.hi_stride + (n % rm.div) * rm.lo_stride;
+    }
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += ws[k * total + i];
+    float* o = dw + om + t * s_t + on;
     *o = accumulate ? (*o + s) : s;
   }
 }
 
-// bias gradient: column sums of A over all pixels, two deterministic stages
-constexpr int DB_SPLITS = 64;
+// bias gradient: column sums of dY over all pixels, two deterministic stages.
+// grid (ceil(C/32), DB_SPLITS); block 256 = 4 channel-vectors (8 channels each) x 64 pixel lanes; 16-byte loads.
+constexpr int DB_SPLITS = 32;
 template <typename T>
-__global__ void __launch_bounds__(256) dbias_partial_kernel(const __grid_constant__ WgradDev p, const T* __restrict__ A,
-                                                            const long long* dimstr /*unused*/, float* part, int ca) {
-  // grid: (ceil(ca/32), DB_SPLITS); thread = (pixel lane 0..7, channel 0..31)
-  __shared__ float red[8][33];
-  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int pl = threadIdx.x >> 5;
-  const int rows = p.box_x * p.box_y * p.box_n;
-  float s = 0.f;
-  for (int tile = blockIdx.y; tile < p.ntiles; tile += DB_SPLITS) {
-    int x0, y0, n0;
-    wg_tile_origin(p, tile, &x0, &y0, &n0);
-    for (int r = pl; r < rows; r += 8) {
-      int x = x0 + r % p.box_x;
-      int r2 = r / p.box_x;
-      int y = y0 + r2 % p.box_y;
-      int n = n0 + r2 / p.box_y;
-      // dY is always the untapped operand
-      const long long* dim = p.m_tap ? p.n_dim : p.m_dim;
-      const long long* str = p.m_tap ? p.n_str : p.m_str;
-      if (ch < ca && x < dim[1] && y < dim[2] && n < dim[4]) s += to_f<T>(A[n * str[4] + y * str[2] + x * str[1] + ch]);
+__global__ void __launch_bounds__(256) dbias_partial_kernel(const T* __restrict__ A, long long sx, long long sy, long long sn,
+                                                            int W, int H, int N, float* part, int ca) {
+  __shared__ float red[64][33];
+  const int cv = threadIdx.x & 3, pl = threadIdx.x >> 2;
+  const int c0 = blockIdx.x * 32 + cv * 8;
+  const long long total = (long long)N * H * W;
+  const long long per = (total + DB_SPLITS - 1) / DB_SPLITS;
+  const long long p0 = blockIdx.y * per, p1 = min(total, p0 + per);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (c0 < ca) {
+    for (long long p = p0 + pl; p < p1; p += 64) {
+      int x = (int)(p % W);
+      long long r = p / W;
+      int y = (int)(r % H);
+      int n = (int)(r / H);
+      const T* q = A + n * sn + y * sy + x * sx + c0;
+      if (c0 + 8 <= ca) {
+        float v[8];
+        Vec8<T>::load(q, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      } else {
+        for (int e = 0; e < 8 && c0 + e < ca; ++e) acc[e] += to_f<T>(q[e]);
+      }
     }
   }
-  red[pl][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (pl == 0) {
-    float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x];
-    if (ch < ca) part[(long long)blockIdx.y * ca + ch] = tot;
+  for (int e = 0; e < 8; ++e) red[pl][cv * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+    for (int i = 0; i < 64; ++i) t += red[i][threadIdx.x];
+    int c = blockIdx.x * 32 + threadIdx.x;
+    if (c < ca) part[(long long)blockIdx.y * ca + c] = t;
   }
 }
 __global__ void dbias_final_kernel(const float* part, int ca, float* dbias, int accumulate) {
@@ -314,25 +339,28 @@ __global__ void dbias_final_kernel(const float* part, int ca, float* dbias, int 
 // =====================================================================================================
 struct WgPlan {
   bool swap;
-  int cm, cn, bn, splits, tiles_per_split, ntiles, items;
+  int cm, cn, bn, mr, splits, tiles_per_split, ntiles, items;
 };
 
 static int wg_plan(const dwc_wgrad_t* g, WgPlan* pl) {
   pl->ntiles = g->tiles[0] * g->tiles[1] * g->tiles[2];
   if (g->backend == DWC_TC) {
     // accumulator rows need a multiple of 128 channels
-    pl->swap = (g->ca % 128 != 0);
+    DWC_CHECK(g->ca % 64 == 0 && g->cb % 64 == 0, "dwc_wgrad: tcgen05 needs channel counts (%d,%d) %% 64 == 0", g->ca,
+              g->cb);
+    pl->swap = (g->ca % 128 != 0) && (g->cb % 128 == 0);
     pl->cm = pl->swap ? g->cb : g->ca;
     pl->cn = pl->swap ? g->ca : g->cb;
-    DWC_CHECK(pl->cm % 128 == 0 && pl->cn % 64 == 0, "dwc_wgrad: tcgen05 needs channel counts (%d,%d) with one %%128==0, other %%64==0",
-              g->ca, g->cb);
+    pl->mr = pl->cm % 128 == 0 ? 128 : 64;
     pl->bn = pl->cn % 256 == 0 ? 256 : (pl->cn % 128 == 0 ? 128 : 64);
-    pl->items = (pl->cm / 128) * (pl->cn / pl->bn) * g->ntaps;
+    if (pl->mr == 64) pl->bn = 64;
+    pl->items = (pl->cm / pl->mr) * (pl->cn / pl->bn) * g->ntaps;
   } else {
     pl->swap = false;
     pl->cm = g->ca;
     pl->cn = g->cb;
     pl->bn = 64;
+    pl->mr = 64;
     pl->items = cdiv(pl->cm, 64) * cdiv(pl->cn, 64) * g->ntaps;
   }
   int want = cdiv(2 * dwc_num_sms(), pl->items);
@@ -352,9 +380,9 @@ extern "C" int64_t dwc_wgrad_workspace_bytes(const dwc_wgrad_t* g) {
   return ws;
 }
 
-template <int BN>
+template <int BN, int MR>
 static int launch_wg_tc(const dwc_wgrad_t* g, const WgradDev& d, const WgPlan& pl, cudaStream_t st) {
-  using Cfg = WgCfg<BN>;
+  using Cfg = WgCfg<BN, MR>;
   CUtensorMap tmM, tmN;
   const bool sw = pl.swap;
   if (dwc_make_tmap5(&tmM, sw ? g->b : g->a, sw ? g->b_dim : g->a_dim, sw ? g->b_str : g->a_str, g->box[0], g->box[1],
@@ -365,11 +393,11 @@ static int launch_wg_tc(const dwc_wgrad_t* g, const WgradDev& d, const WgPlan& p
     return 1;
   static bool attr_set = false;
   if (!attr_set) {
-    DWC_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    DWC_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
   dim3 grid(pl.items, pl.splits);
-  wgrad_tc_kernel<BN><<<grid, WG_THREADS, Cfg::SMEM, st>>>(tmM, tmN, d);
+  wgrad_tc_kernel<BN, MR><<<grid, WG_THREADS, Cfg::SMEM, st>>>(tmM, tmN, d);
   DWC_LAUNCH_CHECK();
   return 0;
 }
@@ -410,9 +438,10 @@ extern "C" int dwc_wgrad(const dwc_wgrad_t* g, dwc_stream_t stream) {
 
   if (g->backend == DWC_TC) {
     int rc;
-    if (pl.bn == 256) rc = launch_wg_tc<256>(g, d, pl, st);
-    else if (pl.bn == 128) rc = launch_wg_tc<128>(g, d, pl, st);
-    else rc = launch_wg_tc<64>(g, d, pl, st);
+    if (pl.mr == 64) rc = launch_wg_tc<64, 64>(g, d, pl, st);
+    else if (pl.bn == 256) rc = launch_wg_tc<256, 128>(g, d, pl, st);
+    else if (pl.bn == 128) rc = launch_wg_tc<128, 128>(g, d, pl, st);
+    else rc = launch_wg_tc<64, 128>(g, d, pl, st);
     if (rc) return rc;
   } else {
     dim3 grid(pl.items, pl.splits);
@@ -420,18 +449,28 @@ extern "C" int dwc_wgrad(const dwc_wgrad_t* g, dwc_stream_t stream) {
     else wgrad_simt_kernel<bf16><<<grid, 256, 0, st>>>(d);
     DWC_LAUNCH_CHECK();
   }
+  WgRemap rm;
+  rm.axis = g->remap_axis == 0 ? 0 : ((g->remap_axis == 1) != sw ? 1 : 2);   // axis in (m, n) terms after the operand swap
+  rm.div = g->remap_div > 0 ? g->remap_div : 1;
+  rm.lo_limit = g->remap_lo_limit; rm.hi_limit = g->remap_hi_limit;
+  rm.hi_stride = g->remap_hi_stride; rm.lo_stride = g->remap_lo_stride;
   const long long total = (long long)g->ntaps * pl.cm * pl.cn;
   wgrad_reduce_kernel<<<cdiv(total, 256 * 4) > 1184 ? 1184 : cdiv(total, 256 * 4), 256, 0, st>>>(
       g->workspace, pl.splits, g->ntaps, pl.cm, pl.cn, g->dw, sw ? g->s_b : g->s_a, g->s_t, sw ? g->s_a : g->s_b,
-      g->accumulate);
+      g->accumulate, rm);
   DWC_LAUNCH_CHECK();
   if (g->dbias) {
     float* part = g->workspace + (int64_t)pl.splits * g->ntaps * pl.cm * pl.cn;
     dim3 grid(cdiv(g->ca, 32), DB_SPLITS);
+    DWC_CHECK(g->ca % 8 == 0 || g->ca < 8, "dwc_wgrad: dbias needs ca %% 8 == 0");
     if (g->dtype == DWC_F32)
-      dbias_partial_kernel<float><<<grid, 256, 0, st>>>(d, reinterpret_cast<const float*>(g->a), nullptr, part, g->ca);
+      dbias_partial_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(g->a), g->a_str[1], g->a_str[2],
+                                                        g->a_str[4], (int)g->a_dim[1], (int)g->a_dim[2],
+                                                        (int)g->a_dim[4], part, g->ca);
     else
-      dbias_partial_kernel<bf16><<<grid, 256, 0, st>>>(d, reinterpret_cast<const bf16*>(g->a), nullptr, part, g->ca);
+      dbias_partial_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(g->a), g->a_str[1], g->a_str[2],
+                                                       g->a_str[4], (int)g->a_dim[1], (int)g->a_dim[2],
+                                                       (int)g->a_dim[4], part, g->ca);
     DWC_LAUNCH_CHECK();
     dbias_final_kernel<<<cdiv(g->ca, 128), 128, 0, st>>>(part, g->ca, g->dbias, g->accumulate);
     DWC_LAUNCH_CHECK();

@@ -209,20 +209,38 @@ class Conv2dBlock(nn.Module):
             self._packed[key] = hit
         return hit[1], rows_p
 
-    def packed_dgrad(self, dtype):
+    def packed_dgrad(self, dtype, pad_rows=False):
+        """(GEMM operand of the data gradient, its padded row count): rows = input channels (16 when a few-channel
+        image gradient runs on the tensor cores)."""
         f, w, _ = self._raw_weight()
         tot = self.total_cout()
-        key = ("d", dtype)
+        rows_p = 16 if (pad_rows and self.cin <= 16) else self.cin
+        key = ("d", dtype, rows_p)
         hit = self._packed.get(key)
         if hit is None or hit[0] != f.version:
             if self.stride == 1:
-                out = torch.empty(self.cin, self.k * self.k * tot, dtype=dtype, device=w.device)
+                out = torch.empty(rows_p, self.k * self.k * tot, dtype=dtype, device=w.device)
                 mode = 1
             else:
-                out = torch.empty(4, self.cin, 4 * tot, dtype=dtype, device=w.device)
+                out = torch.empty(4, rows_p, 4 * tot, dtype=dtype, device=w.device)
                 mode = 2
             ops._call("dwc_pack_weights", L.ptr(w), tot, self.k, self.k, self.cin, mode, L.ptr(out), L.dt(dtype),
-                      self.cin, L.stream())
+                      rows_p, L.stream())
+            hit = (f.version, out)
+            self._packed[key] = hit
+        return hit[1], rows_p
+
+    def packed_rows(self, dtype, mode):
+        """Weights over a row-im2col operand: mode 3 forward [cout][k*64], mode 4 data gradient [cin][k*64]."""
+        f, w, _ = self._raw_weight()
+        tot = self.total_cout()
+        key = ("r", dtype, mode)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != f.version:
+            rows = tot if mode == 3 else self.cin
+            out = torch.empty(rows, self.k * 64, dtype=dtype, device=w.device)
+            ops._call("dwc_pack_weights", L.ptr(w), tot, self.k, self.k, self.cin, mode, L.ptr(out), L.dt(dtype), rows,
+                      L.stream())
             hit = (f.version, out)
             self._packed[key] = hit
         return hit[1]
@@ -234,6 +252,11 @@ class Conv2dBlock(nn.Module):
         gw = f.raw_grad(wn, tot * self.k * self.k * self.cin)
         gb = f.raw_grad(bn, tot)
         return gw, gb
+
+    def bias_grad_needed(self):
+        """A bias that feeds InstanceNorm / AdaIN cancels in the mean subtraction: its gradient is exactly zero (the
+        reference computes round-off there); the parameter still counts as 'touched' for Adam's bookkeeping."""
+        return self.norm_kind not in (NORM_IN, NORM_ADAIN)
 
     def touch_params(self):
         owner, wn, bn = self._names()
@@ -249,13 +272,22 @@ class Conv2dBlock(nn.Module):
         y = _ConvProxy.conv(xp, self)
         if raw:
             return y
+        return self.finish(y, out_halo, out_layout, res)
+
+    def run_first(self, img, rows_t, pool, out_halo=0, out_layout=0, raw=False) -> HB:
+        """First layer of a network: img NCHW fp32 (3 channels), rows_t = ops.image_rows(img, pool, self)."""
+        y = ops.first_conv(img, rows_t, self, pool)
+        return y if raw else self.finish(y, out_halo, out_layout, None)
+
+    def finish(self, y: HB, out_halo=0, out_layout=0, res: Optional[HB] = None) -> HB:
+        n = y.n
         nw = nb = None
         ln = None
         if self.norm_kind == NORM_ADAIN:
             assert self.norm.weight is not None and self.norm.bias is not None, \
                 "Please assign weight and bias before calling AdaIN!"
-            nw = self.norm.weight.view(xp.n, self.cout)
-            nb = self.norm.bias.view(xp.n, self.cout)
+            nw = self.norm.weight.view(n, self.cout)
+            nb = self.norm.bias.view(n, self.cout)
         elif self.norm_kind == NORM_LN:
             owner = self.__dict__["_owner"]
             f = owner.flat
@@ -269,12 +301,11 @@ class Conv2dBlock(nn.Module):
     def forward(self, x):
         """API-compatible entry: logical NCHW tensor in, logical NCHW tensor (compute dtype) out."""
         self.__dict__["_owner"].ensure_flat()
-        if x.shape[1] % 8 != 0:
-            xp = ops.image_pad(x, 1, self.padding, self.in_layout())
-        else:
-            xp = ops.post(_hb_from_tensor(x), out_halo=self.padding, out_layout=self.in_layout())
         if self.act_name in ("tanh", "sigmoid"):
             raise NotImplementedError("decoder heads run fused through Decoder.forward")
+        if x.shape[1] % 8 != 0:
+            return _hb_to_tensor(self.run_first(x, ops.image_rows(x, 1, self), 1))
+        xp = ops.post(_hb_from_tensor(x), out_halo=self.padding, out_layout=self.in_layout())
         return _hb_to_tensor(self.run(xp))
 
 
@@ -395,10 +426,10 @@ class StyleEncoder(_LinearHolder):
         self.output_dim = dim
         assert activ == "relu"
 
-    def run(self, xp0: HB):
+    def run(self, img, rows_t):
         convs = [m for m in self.model if isinstance(m, Conv2dBlock)]
-        h = xp0
-        for i, cv in enumerate(convs):
+        h = convs[0].run_first(img, rows_t, 1, out_halo=1, out_layout=1)
+        for i, cv in enumerate(convs[1:], start=1):
             last = i == len(convs) - 1
             if last:
                 y = cv.run(h, raw=True)
@@ -424,7 +455,7 @@ class StyleEncoder(_LinearHolder):
 
     def forward(self, x):
         self.__dict__["_owner"].ensure_flat()
-        mu, lv = self.run(ops.image_pad(x, 1, 3, 0))
+        mu, lv = self.run(x, ops.image_rows(x, 1, self.model[0]))
         return list(mu.split(self.c_dim, 1)), list(lv.split(self.c_dim, 1))
 
 
@@ -443,18 +474,21 @@ class ContentEncoder(nn.Module):
         self.model = nn.Sequential(*model)
         self.output_dim = dim
 
-    def run(self, xp0: HB) -> HB:
+    def run(self, img, rows_t) -> HB:
         mods = list(self.model)
-        h = xp0
+        h = None
         for i, m in enumerate(mods[:-1]):
             nxt = mods[i + 1]
             layout = 1 if isinstance(nxt, Conv2dBlock) and nxt.stride == 2 else 0
-            h = m.run(h, out_halo=1, out_layout=layout)
+            if i == 0:
+                h = m.run_first(img, rows_t, 1, out_halo=1, out_layout=layout)
+            else:
+                h = m.run(h, out_halo=1, out_layout=layout)
         return mods[-1].run(h, out_halo=0)
 
     def forward(self, x):
         self.model[0].__dict__["_owner"].ensure_flat()
-        return _hb_to_tensor(self.run(ops.image_pad(x, 1, 3, 0)))
+        return _hb_to_tensor(self.run(x, ops.image_rows(x, 1, self.model[0])))
 
 
 class Decoder(nn.Module):
@@ -484,8 +518,8 @@ class Decoder(nn.Module):
             h = cv.run(h, out_halo=3 if i == len(convs) - 1 else 0)
         if not convs:
             h = ops.post(h, out_halo=3)
-        y = self.image_content.run(h, raw=True)                 # [N, H, W, 4] = content(3) | attention(1)
-        return ops.heads(y, self.image_attention.touch_params)
+        # both heads as one 4-channel conv: [N, H, W, 4] = content(3) | attention(1)
+        return ops.heads_conv(h, self.image_content, self.image_attention.touch_params)
 
     def forward(self, x):
         self.image_content.__dict__["_owner"].ensure_flat()
@@ -579,9 +613,10 @@ class AdaINGen_v2(_FlatOwner):
     def encode_fused(self, images):
         """(content tensor, mu [B, S], logvar [B, S]) with one shared padded copy of the image."""
         self.ensure_flat()
-        xp0 = ops.image_pad(images, 1, 3, 0)
-        mu, lv = self.enc_style.run(xp0)
-        content = _hb_to_tensor(self.enc_content.run(xp0))
+        images = images.contiguous().float()
+        rows = ops.image_rows(images, 1, self.enc_style.model[0])     # shared by both 7x7 first layers
+        mu, lv = self.enc_style.run(images, rows)
+        content = _hb_to_tensor(self.enc_content.run(images, rows))
         return content, mu, lv
 
     def encode(self, images):
@@ -671,10 +706,12 @@ class MsImageDis(_FlatOwner, _LinearHolder):
     def forward(self, x, use_multiscales=True):
         self.ensure_flat()
         outputs = []
+        x = x.contiguous().float()
         for i in range(self.num_scales):
-            h = ops.image_pad(x, 2 ** i, 1, 1)
             convs = list(self.cnns_feat[i])
-            for j, cv in enumerate(convs):
+            pool = 2 ** i
+            h = convs[0].run_first(x, ops.image_rows(x, pool, convs[0]), pool, out_halo=1, out_layout=1)
+            for j, cv in enumerate(convs[1:], start=1):
                 last = j == len(convs) - 1
                 h = cv.run(h, out_halo=0 if last else 1, out_layout=0 if last else 1)
             outputs.append(list(self._head(h, self.cnns_src[i], self.cnns_cls[i])))

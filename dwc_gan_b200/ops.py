@@ -146,15 +146,17 @@ class ConvFn(torch.autograd.Function):
         dxp_t = None
         if ctx.needs_input_grad[0]:
             dxp = HB.empty(n, h, w, c, halo, layout, dy_t.dtype, dy_t.device)
-            wd = layer.packed_dgrad(dy_t.dtype)
             tc = RT.tc_ok(c, cout)
-            for q in P.plan_conv_dgrad(dy, wd, dxp, k, s, L.TC if tc else L.SIMT):
+            wd, rows_p = layer.packed_dgrad(dy_t.dtype)
+            for q in P.plan_conv_dgrad(dy, wd, dxp, k, s, L.TC if tc else L.SIMT, cin_padded=rows_p):
                 RT.launches += 1
                 q.launch()
             dxp_t = dxp.t
         if ctx.needs_input_grad[1]:
             gw, gb = layer.grad_buffers()
-            tc = RT.tc_ok(c, cout) and (c % 128 == 0 or cout % 128 == 0)
+            if not layer.bias_grad_needed():
+                gb = None          # bias in front of InstanceNorm / AdaIN: its gradient is exactly zero
+            tc = RT.tc_ok(c, cout)
             wp = P.plan_conv_wgrad(dy, xp, gw, gb, k, s, L.TC if tc else L.SIMT, accumulate=True)
             RT.launches += 3
             wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device))
@@ -166,6 +168,142 @@ def conv(xp: HB, layer) -> HB:
     ho, wo = P.out_size(xp, k, s)
     t = ConvFn.apply(xp.t, layer.weight_param, layer, xp)
     return HB(t, xp.n, ho, wo, layer.total_cout(), k - 1 if s == 1 else 1, 0)
+
+
+def image_rows(img, pool, layer):
+    """Row-im2col buffer of the (pooled, reflect-padded) image for a few-channel first convolution; no autograd."""
+    _require_cuda(img)
+    img = img.contiguous().float()
+    n, c, h, w = img.shape
+    k, s, p = layer.k, layer.stride, layer.padding
+    hp = h // pool + 2 * p
+    wo = (w // pool + 2 * p - k) // s + 1
+    rows = torch.empty(P.rows_shape(n, hp, wo, s), dtype=RT.dtype, device=img.device)
+    _call("dwc_image_rows_fwd", L.ptr(img), n, c, h, w, pool, p, s, s, wo, L.ptr(rows), L.dt(rows), L.stream())
+    return rows
+
+
+class FirstConvFn(torch.autograd.Function):
+    """First convolution of an encoder / discriminator scale (3 -> 64 channels, 7x7 s1 or 4x4 s2) on the tensor
+    cores: the image is expanded once into 8-pixel x 8-channel windows (image_rows), which turns the layer into a
+    k-tap, 64-channel gconv / wgrad.  Backward to the image (generated images only) is a regular dgrad."""
+
+    @staticmethod
+    def forward(ctx, img, weight, layer, rows_t, pool):
+        n, c, h, w = img.shape
+        k, s, p, cout = layer.k, layer.stride, layer.padding, layer.cout
+        hi, wi = h // pool, w // pool
+        hp = hi + 2 * p
+        ho, wo = (hp - k) // s + 1, (wi + 2 * p - k) // s + 1
+        hy = k - 1 if s == 1 else 1
+        y = HB.empty(n, ho, wo, cout, hy, 0, rows_t.dtype, rows_t.device)
+        be = L.TC if RT.tc_ok(64, cout) else L.SIMT
+        RT.launches += 1
+        P.plan_first_conv_fwd(rows_t, n, hp, wo, ho, k, s, layer.packed_rows(rows_t.dtype, 3), cout, layer.bias_f32(), y,
+                              be).launch()
+        ctx.layer, ctx.meta = layer, (n, c, h, w, pool, hp, ho, wo, hy)
+        ctx.save_for_backward(rows_t)
+        return y.t
+
+    @staticmethod
+    def backward(ctx, dy_t):
+        layer = ctx.layer
+        (rows_t,) = ctx.saved_tensors
+        n, c, h, w, pool, hp, ho, wo, hy = ctx.meta
+        k, s, p, cout = layer.k, layer.stride, layer.padding, layer.cout
+        dy = HB(dy_t.contiguous(), n, ho, wo, cout, hy, 0)
+        dimg = None
+        if ctx.needs_input_grad[0]:
+            layout = 1 if s == 2 else 0
+            dxp = HB.empty(n, h // pool, w // pool, c, p, layout, dy_t.dtype, dy_t.device)
+            tc = RT.tc_ok(cout)
+            wd, rows_p = layer.packed_dgrad(dy_t.dtype, pad_rows=tc)
+            for q in P.plan_conv_dgrad(dy, wd, dxp, k, s, L.TC if tc else L.SIMT, cin_padded=rows_p):
+                RT.launches += 1
+                q.launch()
+            dimg = torch.empty(n, c, h, w, dtype=torch.float32, device=dy_t.device)
+            ds = dxp.struct()
+            _call("dwc_image_pad_bwd", C.byref(ds), pool, L.ptr(dimg), n, c, h, w, 0, L.stream())
+        if ctx.needs_input_grad[1]:
+            gw, gb = layer.grad_buffers()
+            if not layer.bias_grad_needed():
+                gb = None
+            be = L.TC if RT.tc_ok(64, cout) else L.SIMT
+            RT.launches += 3
+            P.plan_first_conv_wgrad(dy, rows_t, n, hp, wo, k, s, c, gw, gb, be).launch(
+                lambda nbytes: RT.workspace(nbytes, dy_t.device))
+        return dimg, None, None, None, None
+
+
+def first_conv(img, rows_t, layer, pool) -> HB:
+    n, c, h, w = img.shape
+    k, s, p = layer.k, layer.stride, layer.padding
+    ho, wo = (h // pool + 2 * p - k) // s + 1, (w // pool + 2 * p - k) // s + 1
+    t = FirstConvFn.apply(img.contiguous().float(), layer.weight_param, layer, rows_t, pool)
+    return HB(t, n, ho, wo, layer.cout, k - 1 if s == 1 else 1, 0)
+
+
+class HeadsConvFn(torch.autograd.Function):
+    """Decoder heads (networks_v2.py:162-169): the two 7x7 convolutions as one 4-channel gconv + tanh / sigmoid.
+    Backward builds 64-wide window buffers of the 4-channel gradient so that dgrad and wgrad run on the tensor cores."""
+
+    @staticmethod
+    def forward(ctx, xp_t, weight, layer, xp: HB, on_att_grad):
+        ctx.set_materialize_grads(False)
+        k, cout = layer.k, layer.total_cout()
+        n, h, w = xp.n, xp.h, xp.w
+        y = HB.empty(n, h, w, cout, 0, 0, xp_t.dtype, xp_t.device)
+        wf, rows_p = layer.packed_fwd(xp_t.dtype)
+        tc = RT.tc_ok(xp.c) and rows_p == 16
+        RT.launches += 1
+        P.plan_conv_fwd(HB(xp_t, n, h, w, xp.c, xp.halo, 0), wf, cout, rows_p, layer.bias_f32(), y, k, 1,
+                        L.TC if tc else L.SIMT).launch()
+        img = torch.empty(n, cout - 1, h, w, dtype=torch.float32, device=xp_t.device)
+        att = torch.empty(n, 1, h, w, dtype=torch.float32, device=xp_t.device)
+        ys = y.struct()
+        _call("dwc_heads_fwd", C.byref(ys), L.ptr(img), L.ptr(att), L.stream())
+        ctx.layer, ctx.meta, ctx.on_att_grad = layer, (n, h, w, xp.c, xp.halo), on_att_grad
+        ctx.save_for_backward(xp_t, img, att)
+        return img, att
+
+    @staticmethod
+    def backward(ctx, dimg, datt):
+        layer = ctx.layer
+        xp_t, img, att = ctx.saved_tensors
+        n, h, w, cin, halo_in = ctx.meta
+        k, cout = layer.k, layer.total_cout()
+        dev, dtype = xp_t.device, xp_t.dtype
+        if datt is not None and ctx.on_att_grad is not None:
+            ctx.on_att_grad()
+        dimg = dimg.contiguous() if dimg is not None else None
+        datt = datt.contiguous() if datt is not None else None
+        halo = k - 1
+        hh, wh, wu = h + 2 * halo, w + 2 * halo, w + halo
+        assert wu == w + 2 * halo_in, "window buffer must span the padded input width"
+        rows_d = torch.empty(n, hh, wh, 64, dtype=dtype, device=dev)
+        win = torch.empty(n, h, wu, 64, dtype=dtype, device=dev)
+        part = torch.empty(1024 * 4, dtype=torch.float32, device=dev)
+        nblk = C.c_int32(0)
+        _call("dwc_heads_bwd_rows", L.ptr(dimg), L.ptr(datt), L.ptr(img), L.ptr(att), n, h, w, halo, L.ptr(rows_d),
+              L.ptr(win), L.dt(dtype), L.ptr(part), C.byref(nblk), L.stream())
+        be = L.TC if RT.tc_ok(64, cin) else L.SIMT
+        dxp_t = None
+        if ctx.needs_input_grad[0]:
+            dxp = HB.empty(n, h, w, cin, halo_in, 0, dtype, dev)
+            RT.launches += 1
+            P.plan_heads_dgrad(rows_d, n, hh, wh, layer.packed_rows(dtype, 4), dxp, k, be).launch()
+            dxp_t = dxp.t
+        if ctx.needs_input_grad[1]:
+            gw, gb = layer.grad_buffers()
+            RT.launches += 2
+            P.plan_heads_wgrad(win, HB(xp_t, n, h, w, cin, halo_in, 0), gw, k, cout, be).launch(
+                lambda nbytes: RT.workspace(nbytes, dev))
+            _call("dwc_colsum", nblk.value, cout, L.ptr(part), cout, 1, L.ptr(gb), 1, L.stream())
+        return dxp_t, None, None, None, None
+
+
+def heads_conv(xp: HB, layer, on_att_grad=None):
+    return HeadsConvFn.apply(xp.t, layer.weight_param, layer, xp, on_att_grad)
 
 
 # --------------------------------------------------------------------------------------------

@@ -164,6 +164,7 @@ class WGradPlan:
     dbias: Optional[torch.Tensor]
     accumulate: bool = True
     backend: int = L.SIMT
+    remap: Optional[Tuple[int, int, int, int, int, int]] = None   # axis, div, lo_limit, hi_limit, hi_stride, lo_stride
 
     def _struct(self, workspace=None):
         g = L.WGrad()
@@ -187,6 +188,9 @@ class WGradPlan:
         g.s_a, g.s_t, g.s_b = self.s_a, self.s_t, self.s_b
         g.dbias = self.dbias.data_ptr() if self.dbias is not None else 0
         g.accumulate = int(self.accumulate)
+        if self.remap is not None:
+            (g.remap_axis, g.remap_div, g.remap_lo_limit, g.remap_hi_limit, g.remap_hi_stride,
+             g.remap_lo_stride) = self.remap
         if workspace is not None:
             g.workspace = workspace.data_ptr()
             g.workspace_bytes = workspace.numel() * workspace.element_size()
@@ -287,3 +291,72 @@ def plan_conv_wgrad(dy: HB, xp: HB, dw, dbias, k, stride, backend, accumulate=Tr
     return WGradPlan(a=dy.t, a_off=dy.interior_offset(), a_dim=a_dim, a_str=a_str, b=xp.t, b_off=0, b_dim=b_dim,
                      b_str=b_str, box=box, tiles=tiles, taps=conv_taps(k, stride), ca=cout, cb=cin, dw=dw,
                      s_a=k * k * cin, s_t=cin, s_b=1, dbias=dbias, accumulate=accumulate, backend=backend)
+
+
+# --------------------------------------------------------------------------------------------
+# few-channel layers on the tensor-core kernels through row-im2col buffers
+# --------------------------------------------------------------------------------------------
+
+def rows_shape(n, hp, wo, ys):
+    """[N, ys, Hp/ys, Wo, 64] row-im2col buffer of a padded image (8-pixel x 8-channel windows)."""
+    return (n, ys, hp // ys, wo, 64)
+
+
+def rows_view(n, hp, wo, ys):
+    yr = hp // ys
+    return (64, wo, yr, ys, n), (1, 64, wo * 64, yr * wo * 64, ys * yr * wo * 64)
+
+
+def first_conv_taps(k, stride):
+    return [(0, kh, 0) for kh in range(k)] if stride == 1 else [(0, kh // 2, kh % 2) for kh in range(k)]
+
+
+def plan_first_conv_fwd(rows_t, n, hp, wo, ho, k, stride, w_packed, cout, bias, y: HB, backend) -> GConvPlan:
+    dims, strs = rows_view(n, hp, wo, stride)
+    box = choose_box(wo, ho, n, 128)
+    tiles = (-(-wo // box[0]), -(-ho // box[1]), -(-n // box[2]))
+    cy = y.c
+    return GConvPlan(a=rows_t, a_off=0, a_dim=dims, a_str=strs, box=box, tiles=tiles, valid=(wo, ho, n),
+                     flat=(0, 0, 0, 0, 0), taps=first_conv_taps(k, stride), w=w_packed, w_off=0, ncols=cout,
+                     ncols_padded=cout, bias=bias, out=y.t, out_off=y.interior_offset(),
+                     o_str=(cy, y.wp * cy, y.hp * y.wp * cy), backend=backend)
+
+
+def plan_first_conv_wgrad(dy: HB, rows_t, n, hp, wo, k, stride, cin, dw, dbias, backend, accumulate=True) -> WGradPlan:
+    """dw: fp32 master gradient [Cout, k, k, cin]; the 64-wide window index (j, ch) is scattered to (kw=j, ci=ch)."""
+    cout = dy.c
+    b_dim, b_str = rows_view(n, hp, wo, stride)
+    a_dim = (cout, dy.w, dy.h, 1, dy.n)
+    a_str = (1, cout, dy.wp * cout, dy.hp * dy.wp * cout, dy.hp * dy.wp * cout)
+    box = choose_box(dy.w, dy.h, dy.n, 64)
+    tiles = (-(-dy.w // box[0]), -(-dy.h // box[1]), -(-dy.n // box[2]))
+    return WGradPlan(a=dy.t, a_off=dy.interior_offset(), a_dim=a_dim, a_str=a_str, b=rows_t, b_off=0, b_dim=b_dim,
+                     b_str=b_str, box=box, tiles=tiles, taps=first_conv_taps(k, stride), ca=cout, cb=64, dw=dw,
+                     s_a=k * k * cin, s_t=k * cin, s_b=1, dbias=dbias, accumulate=accumulate, backend=backend,
+                     remap=(2, 8, cin, k, cin, 1))
+
+
+def plan_heads_dgrad(rows_d, n, hh, wh, w_packed, dxp: HB, k, backend) -> GConvPlan:
+    """rows_d [N, Hh, Wh, 64]: 8-pixel windows of the zero-haloed 4(+4)-channel head gradient."""
+    rows = n * hh * wh
+    cin = dxp.c
+    taps = [(kh * wh, 0, 0) for kh in range(k)]
+    return GConvPlan(a=rows_d, a_off=0, a_dim=(64, rows, 1, 1, 1), a_str=(1, 64, rows * 64, rows * 64, rows * 64),
+                     box=(128, 1, 1), tiles=(-(-rows // 128), 1, 1), valid=(rows, 1, n),
+                     flat=(1, hh * wh, wh, dxp.hp, dxp.wp), taps=taps, w=w_packed, w_off=0, ncols=cin, ncols_padded=cin,
+                     bias=None, out=dxp.t, out_off=0, o_str=(cin, dxp.wp * cin, dxp.hp * dxp.wp * cin), backend=backend)
+
+
+def plan_heads_wgrad(win, xp: HB, dw, k, cout, backend, accumulate=True) -> WGradPlan:
+    """win [N, H, W+halo, 64] with win[.., u, j*8+co] = dy[.., u-j, co]; dw: fp32 master gradient [cout, k, k, cin]."""
+    n, h, wu = xp.n, xp.h, xp.wp
+    cin = xp.c
+    b_dim, b_str = input_view(xp)
+    a_dim = (64, wu, h, 1, n)
+    a_str = (1, 64, wu * 64, h * wu * 64, h * wu * 64)
+    box = choose_box(wu, h, n, 64)
+    tiles = (-(-wu // box[0]), -(-h // box[1]), -(-n // box[2]))
+    return WGradPlan(a=win, a_off=0, a_dim=a_dim, a_str=a_str, b=xp.t, b_off=0, b_dim=b_dim, b_str=b_str, box=box,
+                     tiles=tiles, taps=[(0, kh, 0) for kh in range(k)], ca=64, cb=cin, dw=dw, s_a=0, s_t=k * cin, s_b=1,
+                     dbias=None, accumulate=accumulate, backend=backend,
+                     remap=(1, 8, cout, k, cin, k * k * cin))

@@ -51,6 +51,8 @@ class TxtBodyFn(torch.autograd.Function):
             whh = f.raw(pre + f"weight_hh_l{l}", 2 * 4 * H * H)
             bih = f.raw(pre + f"bias_ih_l{l}", 2 * 4 * H)
             bhh = f.raw(pre + f"bias_hh_l{l}", 2 * 4 * H)
+            whh_t = torch.empty(2, H, 4 * H, dtype=torch.float32, device=dev)
+            _call("dwc_transpose", L.ptr(whh), L.ptr(whh_t), 2, 4 * H, H, L.stream())
             xproj = torch.empty(T, B, 2, 4 * H, dtype=torch.float32, device=dev)
             # xproj = b_ih + b_hh (rank-1 GEMM) then += inp @ Wih^T
             sgemm(T * B, 8 * H, 1, 1.0, ones, 1, 1, bhh, 8 * H, 1, 0.0, xproj, 8 * H, 1, bias=bih)
@@ -62,7 +64,7 @@ class TxtBodyFn(torch.autograd.Function):
             csave = torch.empty(T, B, 2, H, dtype=torch.float32, device=dev) if need_grad else None
             for s in range(T):
                 a, b = s & 1, (s + 1) & 1
-                _call("dwc_lstm_step_fwd", s, T, B, H, L.ptr(xproj), L.ptr(whh), L.ptr(lens), L.ptr(hbuf[a]),
+                _call("dwc_lstm_step_fwd", s, T, B, H, L.ptr(xproj), L.ptr(whh_t), L.ptr(lens), L.ptr(hbuf[a]),
                       L.ptr(cbuf[a]), L.ptr(hbuf[b]), L.ptr(cbuf[b]), L.ptr(out), L.ptr(gates), L.ptr(csave), L.stream())
             hf, cf = hbuf[T & 1], cbuf[T & 1]                          # [2, B, H]
             finals_h.append(hf.permute(1, 0, 2).reshape(B, 2 * H))   # combine_bidir

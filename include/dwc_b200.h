@@ -99,6 +99,12 @@ typedef struct {
   float* dbias;         /* NULL to skip */
   int32_t accumulate;   /* dw/dbias += (else overwritten) */
   float* workspace; int64_t workspace_bytes;
+  /* Optional index split for row-im2col operands (8-pixel x 8-channel windows of a few-channel image): with
+   * remap_axis = 1 (A index) or 2 (B index) the channel index i of that operand is stored at
+   * (i / remap_div) * remap_hi_stride + (i % remap_div) * remap_lo_stride instead of i * s_a (or s_b), and dropped
+   * unless i % remap_div < remap_lo_limit and i / remap_div < remap_hi_limit.  remap_axis = 0: plain strides. */
+  int32_t remap_axis, remap_div, remap_lo_limit, remap_hi_limit;
+  int64_t remap_hi_stride, remap_lo_stride;
 } dwc_wgrad_t;
 
 int64_t dwc_wgrad_workspace_bytes(const dwc_wgrad_t* p);
@@ -159,6 +165,18 @@ int dwc_image_pad_fwd(const float* img, int n, int c, int h, int w, int pool, co
 int dwc_image_pad_bwd(const dwc_hbuf_t* dout, int pool, float* dimg, int n, int c, int h, int w,
                       int accumulate, dwc_stream_t stream);
 
+/* Row-im2col of a few-channel image for the tensor-core path of the first convolutions (3 -> 64, 7x7 s1 and
+ * 4x4 s2): rows[n, z, yr, x, j*8 + ch] = P[n, yr*ys + z, x*sx + j, ch] for j, ch < 8 where P is the (avg-pooled,)
+ * reflect-padded image; ys = 2 stores even/odd padded rows as two planes z.  0 beyond the image. */
+int dwc_image_rows_fwd(const float* img, int n, int c, int h, int w, int pool, int pad, int sx, int ys, int wo,
+                       void* rows, int dtype, dwc_stream_t stream);
+/* Backward of the fused decoder heads for the tensor-core path: from dimg/datt (may be NULL) and the saved
+ * img/att builds  rows_d[n, Y, X, j*8+c] = dyz[n, Y, X+j, c]   (dyz = dy with a zero halo of `halo`, for dgrad),
+ *                 win[n, h, u, j*8+c]   = dy[n, h, u-j, c]     (u over the padded width w+halo, for wgrad)
+ * and per-block partial sums of dy (bias gradient), part[block*4 + c]; returns the number of blocks in *nblocks. */
+int dwc_heads_bwd_rows(const float* dimg, const float* datt, const float* img, const float* att, int n, int h, int w,
+                       int halo, void* rows_d, void* win, int dtype, float* part, int32_t* nblocks, dwc_stream_t stream);
+
 /* Decoder heads: y[..., 0:3] -> tanh -> img NCHW f32 ; y[..., 3] -> sigmoid -> att NCHW f32
  * (networks_v2.py:162-169).  Backward writes dy (zero halo). */
 int dwc_heads_fwd(const dwc_hbuf_t* y, float* img, float* att, dwc_stream_t stream);
@@ -200,10 +218,11 @@ int dwc_embed_concat_fwd(const int64_t* tokens /*[B,T]*/, const float* emb, cons
 int dwc_embed_concat_bwd(const int64_t* tokens, const float* dx, const float* mask, float* demb, float* dstyle,
                          int b, int t, int e, int s, int pad_idx, dwc_stream_t stream);
 /* step index `step`: direction 0 handles time t=step, direction 1 handles t=T-1-step.
- * xproj [T,B,2,4H] (input projection + both biases), whh [2,4H,H], h/c state [2,B,H] (in place),
+ * xproj [T,B,2,4H] (input projection + both biases), whh_t [2,H,4H] (transposed recurrent weights, see
+ * dwc_transpose), h/c state [2,B,H] (ping-pong: h_in/h_out must differ),
  * out [T,B,2H], gates_save [T,B,2,4H] (activated gates i,f,g,o) and c_save [T,B,2,H] (cell state
  * after the step) for the backward pass (may be NULL in inference). */
-int dwc_lstm_step_fwd(int step, int t_total, int b, int h, const float* xproj, const float* whh,
+int dwc_lstm_step_fwd(int step, int t_total, int b, int h, const float* xproj, const float* whh_t,
                       const int64_t* lens, const float* h_in, const float* c_in, float* h_out, float* c_out,
                       float* out, float* gates_save, float* c_save, dwc_stream_t stream);
 /* backward of one step: consumes dh/dc state [2,B,H] (+ dout[t]), the NEXT processed step's gate
@@ -212,6 +231,9 @@ int dwc_lstm_step_bwd(int step, int t_total, int b, int h, const float* whh, con
                       const float* dout /*[T,B,2H] or NULL*/, const float* gates_save, const float* c_save,
                       const float* dh_in, const float* dc_in, float* dh_out, float* dc_out,
                       float* dgates, dwc_stream_t stream);
+
+/* dst[b][c][r] = src[b][r][c] (float32) */
+int dwc_transpose(const float* src, float* dst, int batch, int rows, int cols, dwc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * GMM style space (tools.py:65-70, gmm.py:13-22) and losses.
@@ -250,7 +272,9 @@ int dwc_ema_step(const float* param, float* avg, int64_t count, float beta, dwc_
 /* master float32 weights [Cout][taps][Cin] -> packed compute-dtype GEMM operands.
  * mode 0: forward  wf[co][t][ci]                (cast only, rows padded to ncols_padded)
  * mode 1: stride-1 dgrad  wd[ci][T-1-t][co]     (taps reversed)
- * mode 2: stride-2 k4 dgrad, 4 parity phases  wd[phase][ci][(i,j)][co] */
+ * mode 2: stride-2 k4 dgrad, 4 parity phases  wd[phase][ci][(i,j)][co]
+ * mode 3: forward over a row-im2col input     wr[co][kh][j*8+ci] = w[co][kh][j][ci]  (j < kw, ci < cin, else 0)
+ * mode 4: stride-1 dgrad over row-im2col dY   wr[ci][kh'][j*8+co] = w[co][KH-1-kh'][KW-1-j][ci]  (else 0) */
 int dwc_pack_weights(const float* w, int cout, int taps_h, int taps_w, int cin, int mode, void* out,
                      int out_dtype, int rows_padded, dwc_stream_t stream);
 int dwc_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t count, dwc_stream_t stream);

@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-timeout -k 10 1500 python -m pytest tests/test_modules_gpu.py -q -m gpu -n 4 --tb=line 2>&1 | tail -30 > gpurun_out/test_modules_gpu.log
-echo "== modules"; tail -30 gpurun_out/test_modules_gpu.log
-timeout -k 10 1500 python -m pytest tests/test_step_gpu.py -q -m gpu -n 2 --tb=short -rP 2>&1 | grep -v "^frame\|python()\|Warning" | tail -80 > gpurun_out/test_step_gpu.log
-echo "== step"; tail -80 gpurun_out/test_step_gpu.log
+python dwc_gan_b200/build.py > gpurun_out/build.log 2>&1 || tail -5 gpurun_out/build.log
+timeout -k 10 900 python -m pytest tests/test_conv_gpu.py tests/test_rows_gpu.py tests/test_post_gpu.py -q -m gpu -n 4 --tb=short 2>&1 | tail -40 > gpurun_out/t_units.log; tail -40 gpurun_out/t_units.log
+timeout -k 10 1500 python -m pytest tests/test_modules_gpu.py tests/test_step_gpu.py -q -m gpu -n 4 --tb=short -rP 2>&1 | grep -v "^frame\|python()\|Warning\|warnings.html\|detach()" | tail -60 > gpurun_out/t_net.log; tail -60 gpurun_out/t_net.log

@@ -70,11 +70,22 @@ def emu_wgrad(plan):
     for t, (dx, dy, z) in enumerate(plan.taps):
         B = _gather(b, plan.b_off, plan.b_dim, plan.b_str, x + dx, y + dy, torch.full_like(x, z), n, torch.arange(plan.cb))
         g = A.t() @ B                                        # [ca, cb]
-        idx = (torch.arange(plan.ca)[:, None] * plan.s_a + t * plan.s_t + torch.arange(plan.cb)[None, :] * plan.s_b)
+        ia, ib = torch.arange(plan.ca), torch.arange(plan.cb)
+        oa, ob = ia * plan.s_a, ib * plan.s_b
+        va, vb = torch.ones_like(ia, dtype=torch.bool), torch.ones_like(ib, dtype=torch.bool)
+        if plan.remap is not None:
+            axis, div, lo_lim, hi_lim, hi_s, lo_s = plan.remap
+            if axis == 1:
+                oa, va = (ia // div) * hi_s + (ia % div) * lo_s, ((ia % div) < lo_lim) & ((ia // div) < hi_lim)
+            else:
+                ob, vb = (ib // div) * hi_s + (ib % div) * lo_s, ((ib % div) < lo_lim) & ((ib // div) < hi_lim)
+        idx = (oa[:, None] + t * plan.s_t + ob[None, :])
+        ok = (va[:, None] & vb[None, :]).reshape(-1)
+        idx, gv = idx.reshape(-1)[ok], g.reshape(-1)[ok].to(dw.dtype)
         if plan.accumulate:
-            dw[idx.reshape(-1)] += g.reshape(-1).to(dw.dtype)
+            dw[idx] += gv
         else:
-            dw[idx.reshape(-1)] = g.reshape(-1).to(dw.dtype)
+            dw[idx] = gv
     if plan.dbias is not None:
         s = A.sum(0).to(plan.dbias.dtype)
         if plan.accumulate:
@@ -136,3 +147,48 @@ def make_zero_haloed(y_nchw, halo, dtype=torch.float32):
     t = torch.zeros(n, h + 2 * halo, w + 2 * halo, c, dtype=dtype)
     t[:, halo:halo + h, halo:halo + w, :] = y_nchw.permute(0, 2, 3, 1).to(dtype)
     return HB(t, n, h, w, c, halo, 0)
+
+
+def make_rows(img_nchw, pool, pad, sx, ys, wo, dtype=torch.float32):
+    """torch version of dwc_image_rows_fwd."""
+    import torch.nn.functional as F
+    x = F.avg_pool2d(img_nchw, pool) if pool > 1 else img_nchw
+    xp = F.pad(x, (pad,) * 4, mode="reflect")
+    n, c, hp, wp = xp.shape
+    xpp = F.pad(xp, (0, sx * wo + 8 - wp if sx * wo + 8 > wp else 0, 0, 0))
+    rows = torch.zeros(n, hp, wo, 8, 8, dtype=dtype)
+    for j in range(8):
+        rows[:, :, :, j, :c] = xpp[:, :, :, j:j + sx * wo:sx][:, :, :, :wo].permute(0, 2, 3, 1).to(dtype)
+    rows = rows.reshape(n, hp // ys, ys, wo, 64).permute(0, 2, 1, 3, 4).contiguous()
+    return rows
+
+
+def pack_rows_fwd(w):
+    co, kh, kw, ci = w.shape
+    out = w.new_zeros(co, kh, 8, 8)
+    out[:, :, :kw, :ci] = w
+    return out.reshape(co, kh * 64)
+
+
+def pack_rows_dgrad(w):
+    co, kh, kw, ci = w.shape
+    out = w.new_zeros(ci, kh, 8, 8)
+    out[:, :, :kw, :co] = w.flip(1, 2).permute(3, 1, 2, 0)
+    return out.reshape(ci, kh * 64)
+
+
+def make_heads_rows(dy_nchw, halo, dtype=torch.float32):
+    """torch version of dwc_heads_bwd_rows' two outputs (rows_d, win) from dy [N, 4, H, W]."""
+    import torch.nn.functional as F
+    n, c, h, w = dy_nchw.shape
+    dyz = F.pad(dy_nchw, (halo, halo + 8, halo, halo))                     # extra zeros right for the windows
+    hh, wh = h + 2 * halo, w + 2 * halo
+    rows_d = torch.zeros(n, hh, wh, 8, 8, dtype=dtype)
+    for j in range(8):
+        rows_d[:, :, :, j, :c] = dyz[:, :, :, j:j + wh].permute(0, 2, 3, 1).to(dtype)
+    wu = w + halo
+    dyl = F.pad(dy_nchw, (8, halo, 0, 0))                                  # dy[u - j]: zeros on the left
+    win = torch.zeros(n, h, wu, 8, 8, dtype=dtype)
+    for j in range(8):
+        win[:, :, :, j, :c] = dyl[:, :, :, 8 - j:8 - j + wu].permute(0, 2, 3, 1).to(dtype)
+    return rows_d.reshape(n, hh, wh, 64), win.reshape(n, h, wu, 64)
