@@ -1,5 +1,5 @@
 // Small dense algebra and the text encoder: strided fp32 GEMM (style MLP, mapping network, heads,
-// LSTM input projections and weight gradients), embedding + style concat, fused LSTM time steps.
+// LSTM input projections and weight gradients), embedding + style concat (the LSTM recurrence is in lstm.cu).
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -179,184 +179,6 @@ extern "C" int dwc_embed_concat_bwd(const int64_t* tokens, const float* dx, cons
                                     float* dstyle, int b, int t, int e, int s, int pad_idx, dwc_stream_t stream) {
   embed_concat_bwd_kernel<<<grid1d((long long)b * (e + s)), 256, 0, as_stream(stream)>>>(tokens, dx, mask, demb, dstyle,
                                                                                           b, t, e, s, pad_idx);
-  DWC_LAUNCH_CHECK();
-  return 0;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// LSTM time step, both directions.  grid (ceil(H/32), 2 dirs); block 128 = 4 gates x 32 hidden units.
-// Thread (gate q, unit j) accumulates its gate pre-activation for up to 16 samples at a time:
-//   forward : sum_k h_prev[b,k] * WhhT[k, q*H+j]      (WhhT = transposed recurrent weights: coalesced over j)
-//   backward: sum_i dgates_later[b, q*H+i] * Whh[q*H+i, j]   (row-major Whh: coalesced over j), summed over q
-// then the 128 threads share the point-wise cell update of the 32 units x B samples.
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
-
-constexpr int LSTM_BC = 16;     // samples per register chunk
-
-__global__ void __launch_bounds__(128)
-    lstm_step_fwd_kernel(int step, int T, int B, int H, const float* __restrict__ xproj, const float* __restrict__ whh_t,
-                         const int64_t* __restrict__ lens, const float* __restrict__ h_in, const float* __restrict__ c_in,
-                         float* __restrict__ h_out, float* __restrict__ c_out, float* __restrict__ out,
-                         float* __restrict__ gates_save, float* __restrict__ c_save) {
-  extern __shared__ float sm[];
-  float* hs = sm;                                  // [LSTM_BC][H]
-  float* gs = sm + LSTM_BC * H;                    // [4][32][LSTM_BC + 1]
-  const int dir = blockIdx.y;
-  const int t = dir == 0 ? step : T - 1 - step;
-  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 32 + lane;
-  const bool jv = j < H;
-  const float* wt = whh_t + (long long)dir * H * 4 * H + (long long)q * H + j;   // + k*4H
-  for (int b0 = 0; b0 < B; b0 += LSTM_BC) {
-    const int nb = min(LSTM_BC, B - b0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nb * H; i += blockDim.x) hs[i] = h_in[((long long)dir * B + b0) * H + i];
-    __syncthreads();
-    float acc[LSTM_BC];
-#pragma unroll
-    for (int b = 0; b < LSTM_BC; ++b) acc[b] = 0.f;
-    if (jv) {
-      for (int k = 0; k < H; ++k) {
-        const float w = wt[(long long)k * 4 * H];
-#pragma unroll
-        for (int b = 0; b < LSTM_BC; ++b) acc[b] = fmaf(hs[b * H + k], w, acc[b]);   // rows >= nb hold stale data, unused
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < LSTM_BC; ++b) {
-      float pre = 0.f;
-      if (jv && b < nb) pre = acc[b] + xproj[((((long long)t * B + b0 + b) * 2 + dir) * 4 + q) * H + j];
-      gs[(q * 32 + lane) * (LSTM_BC + 1) + b] = pre;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 32 * nb; e += blockDim.x) {
-      const int l2 = e & 31, b = e >> 5;
-      const int jj = blockIdx.x * 32 + l2;
-      if (jj >= H) continue;
-      const int bb = b0 + b;
-      const float gi = sigm(gs[(0 * 32 + l2) * (LSTM_BC + 1) + b]), gf = sigm(gs[(1 * 32 + l2) * (LSTM_BC + 1) + b]);
-      const float gg = tanhf(gs[(2 * 32 + l2) * (LSTM_BC + 1) + b]), go = sigm(gs[(3 * 32 + l2) * (LSTM_BC + 1) + b]);
-      const long long st = ((long long)dir * B + bb) * H + jj;
-      const float hprev = h_in[st], cprev = c_in[st];
-      const bool active = (long long)t < lens[bb];
-      const float cn = gf * cprev + gi * gg;
-      const float hn = go * tanhf(cn);
-      h_out[st] = active ? hn : hprev;
-      c_out[st] = active ? cn : cprev;
-      if (out) out[((long long)t * B + bb) * 2 * H + dir * H + jj] = active ? hn : 0.f;
-      if (gates_save) {
-        float* g4 = gates_save + (((long long)t * B + bb) * 2 + dir) * 4 * H;
-        g4[jj] = gi; g4[H + jj] = gf; g4[2 * H + jj] = gg; g4[3 * H + jj] = go;
-        c_save[(((long long)t * B + bb) * 2 + dir) * H + jj] = active ? cn : cprev;
-      }
-    }
-  }
-}
-
-extern "C" int dwc_lstm_step_fwd(int step, int t_total, int b, int h, const float* xproj, const float* whh_t,
-                                 const int64_t* lens, const float* h_in, const float* c_in, float* h_out, float* c_out,
-                                 float* out, float* gates_save, float* c_save, dwc_stream_t stream) {
-  size_t smem = ((size_t)LSTM_BC * h + 4 * 32 * (LSTM_BC + 1)) * sizeof(float);
-  DWC_CHECK(smem <= 48 * 1024, "dwc_lstm_step_fwd: hidden size too large");
-  dim3 grid(cdiv(h, 32), 2);
-  lstm_step_fwd_kernel<<<grid, 128, smem, as_stream(stream)>>>(step, t_total, b, h, xproj, whh_t, lens, h_in, c_in,
-                                                               h_out, c_out, out, gates_save, c_save);
-  DWC_LAUNCH_CHECK();
-  return 0;
-}
-
-// Backward of one step.  For direction d at time t (processed in reverse order of the forward):
-//   dh_t = dh_state (+ W_hh^T dgates of the step processed just before, folded in here) + dout[t]
-__global__ void __launch_bounds__(128)
-    lstm_step_bwd_kernel(int step, int T, int B, int H, const float* __restrict__ whh, const int64_t* __restrict__ lens,
-                         const float* __restrict__ dout, const float* __restrict__ gates_save,
-                         const float* __restrict__ c_save, const float* __restrict__ dh_in, const float* __restrict__ dc_in,
-                         float* __restrict__ dh_out, float* __restrict__ dc_out, float* __restrict__ dgates) {
-  extern __shared__ float sm[];
-  float* dgs = sm;                                 // [LSTM_BC][4H] gate gradients of the later step
-  float* part = sm + LSTM_BC * 4 * H;              // [4][32][LSTM_BC + 1]
-  const int dir = blockIdx.y;
-  const int t = dir == 0 ? T - 1 - step : step;
-  const int t_later = dir == 0 ? t + 1 : t - 1;
-  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 32 + lane;
-  const bool jv = j < H;
-  const bool has_later = step > 0;
-  const float* w = whh + (long long)dir * 4 * H * H + (long long)q * H * H + j;   // + i*H
-  for (int b0 = 0; b0 < B; b0 += LSTM_BC) {
-    const int nb = min(LSTM_BC, B - b0);
-    float acc[LSTM_BC];
-#pragma unroll
-    for (int b = 0; b < LSTM_BC; ++b) acc[b] = 0.f;
-    __syncthreads();
-    if (has_later) {
-      for (int i = threadIdx.x; i < nb * 4 * H; i += blockDim.x) {
-        int b = i / (4 * H), g = i - b * 4 * H;
-        dgs[b * 4 * H + g] = dgates[(((long long)t_later * B + b0 + b) * 2 + dir) * 4 * H + g];
-      }
-      __syncthreads();
-      if (jv) {
-        for (int i = 0; i < H; ++i) {
-          const float wv = w[(long long)i * H];
-#pragma unroll
-          for (int b = 0; b < LSTM_BC; ++b) acc[b] = fmaf(dgs[b * 4 * H + q * H + i], wv, acc[b]);
-        }
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < LSTM_BC; ++b) part[(q * 32 + lane) * (LSTM_BC + 1) + b] = acc[b];
-    __syncthreads();
-    for (int e = threadIdx.x; e < 32 * nb; e += blockDim.x) {
-      const int l2 = e & 31, b = e >> 5;
-      const int jj = blockIdx.x * 32 + l2;
-      if (jj >= H) continue;
-      const int bb = b0 + b;
-      const float rec = part[(0 * 32 + l2) * (LSTM_BC + 1) + b] + part[(1 * 32 + l2) * (LSTM_BC + 1) + b] +
-                        part[(2 * 32 + l2) * (LSTM_BC + 1) + b] + part[(3 * 32 + l2) * (LSTM_BC + 1) + b];
-      const long long st = ((long long)dir * B + bb) * H + jj;
-      const bool active = (long long)t < lens[bb];
-      float dh = dh_in[st] + rec;
-      const float dc = dc_in[st];
-      float* dg = dgates + (((long long)t * B + bb) * 2 + dir) * 4 * H;
-      if (active) {
-        if (dout) dh += dout[((long long)t * B + bb) * 2 * H + dir * H + jj];
-        const float* g4 = gates_save + (((long long)t * B + bb) * 2 + dir) * 4 * H;
-        const float gi = g4[jj], gf = g4[H + jj], gg = g4[2 * H + jj], go = g4[3 * H + jj];
-        const float cn = c_save[(((long long)t * B + bb) * 2 + dir) * H + jj];
-        const int t_prev = dir == 0 ? t - 1 : t + 1;
-        float cprev = 0.f;
-        if (t_prev >= 0 && t_prev < T) cprev = c_save[(((long long)t_prev * B + bb) * 2 + dir) * H + jj];
-        const float tc = tanhf(cn);
-        const float dco = dc + dh * go * (1.f - tc * tc);
-        dg[jj] = dco * gg * gi * (1.f - gi);
-        dg[H + jj] = dco * cprev * gf * (1.f - gf);
-        dg[2 * H + jj] = dco * gi * (1.f - gg * gg);
-        dg[3 * H + jj] = dh * tc * go * (1.f - go);
-        dc_out[st] = dco * gf;
-        dh_out[st] = 0.f;           // the recurrent part is added by the next launch from dgates
-      } else {
-        dg[jj] = 0.f; dg[H + jj] = 0.f; dg[2 * H + jj] = 0.f; dg[3 * H + jj] = 0.f;
-        dc_out[st] = dc;
-        dh_out[st] = dh;            // state passes through a padded step unchanged
-      }
-    }
-  }
-}
-
-extern "C" int dwc_lstm_step_bwd(int step, int t_total, int b, int h, const float* whh, const int64_t* lens,
-                                 const float* dout, const float* gates_save, const float* c_save, const float* dh_in,
-                                 const float* dc_in, float* dh_out, float* dc_out, float* dgates, dwc_stream_t stream) {
-  size_t smem = ((size_t)LSTM_BC * 4 * h + 4 * 32 * (LSTM_BC + 1)) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    DWC_CUDA(cudaFuncSetAttribute(lstm_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
-  DWC_CHECK(smem <= 200 * 1024, "dwc_lstm_step_bwd: hidden size too large for shared memory");
-  dim3 grid(cdiv(h, 32), 2);
-  lstm_step_bwd_kernel<<<grid, 128, smem, as_stream(stream)>>>(step, t_total, b, h, whh, lens, dout, gates_save, c_save,
-                                                               dh_in, dc_in, dh_out, dc_out, dgates);
   DWC_LAUNCH_CHECK();
   return 0;
 }

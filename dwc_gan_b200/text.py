@@ -4,7 +4,7 @@ cat/view quirk (networks/networks_v2.py:213-249).
 
 One autograd Function for the whole recurrent body: the input projections and all weight
 gradients are single GEMMs over the packed [T*B] rows (dwc_sgemm); only the recurrence itself is
-sequential (one fused kernel per time step handling both directions).
+sequential: one persistent cooperative kernel per layer and pass (csrc/lstm.cu).
 """
 from __future__ import annotations
 
@@ -51,22 +51,18 @@ class TxtBodyFn(torch.autograd.Function):
             whh = f.raw(pre + f"weight_hh_l{l}", 2 * 4 * H * H)
             bih = f.raw(pre + f"bias_ih_l{l}", 2 * 4 * H)
             bhh = f.raw(pre + f"bias_hh_l{l}", 2 * 4 * H)
-            whh_t = torch.empty(2, H, 4 * H, dtype=torch.float32, device=dev)
-            _call("dwc_transpose", L.ptr(whh), L.ptr(whh_t), 2, 4 * H, H, L.stream())
             xproj = torch.empty(T, B, 2, 4 * H, dtype=torch.float32, device=dev)
             # xproj = b_ih + b_hh (rank-1 GEMM) then += inp @ Wih^T
             sgemm(T * B, 8 * H, 1, 1.0, ones, 1, 1, bhh, 8 * H, 1, 0.0, xproj, 8 * H, 1, bias=bih)
             sgemm(T * B, 8 * H, I, 1.0, inp, I, 1, wih, 1, I, 1.0, xproj, 8 * H, 1)
-            hbuf = [torch.zeros(2, B, H, dtype=torch.float32, device=dev) for _ in range(2)]
-            cbuf = [torch.zeros(2, B, H, dtype=torch.float32, device=dev) for _ in range(2)]
+            hf = torch.empty(2, B, H, dtype=torch.float32, device=dev)
+            cf = torch.empty(2, B, H, dtype=torch.float32, device=dev)
             out = torch.empty(T, B, 2 * H, dtype=torch.float32, device=dev)
             gates = torch.empty(T, B, 2, 4 * H, dtype=torch.float32, device=dev) if need_grad else None
             csave = torch.empty(T, B, 2, H, dtype=torch.float32, device=dev) if need_grad else None
-            for s in range(T):
-                a, b = s & 1, (s + 1) & 1
-                _call("dwc_lstm_step_fwd", s, T, B, H, L.ptr(xproj), L.ptr(whh_t), L.ptr(lens), L.ptr(hbuf[a]),
-                      L.ptr(cbuf[a]), L.ptr(hbuf[b]), L.ptr(cbuf[b]), L.ptr(out), L.ptr(gates), L.ptr(csave), L.stream())
-            hf, cf = hbuf[T & 1], cbuf[T & 1]                          # [2, B, H]
+            ws = torch.empty(int(L.lib().dwc_lstm_workspace_bytes(B, H)), dtype=torch.uint8, device=dev)
+            _call("dwc_lstm_layer_fwd", T, B, H, L.ptr(xproj), L.ptr(whh), L.ptr(lens), L.ptr(out), L.ptr(gates),
+                  L.ptr(csave), L.ptr(hf), L.ptr(cf), L.ptr(ws), L.stream())
             finals_h.append(hf.permute(1, 0, 2).reshape(B, 2 * H))   # combine_bidir
             finals_c.append(cf.permute(1, 0, 2).reshape(B, 2 * H))
             nxt = out
@@ -99,13 +95,12 @@ class TxtBodyFn(torch.autograd.Function):
             I = inp.shape[2]
             wih = f.raw(pre + f"weight_ih_l{l}", 2 * 4 * H * I)
             whh = f.raw(pre + f"weight_hh_l{l}", 2 * 4 * H * H)
-            dh = [dfh[l].reshape(B, 2, H).permute(1, 0, 2).contiguous(), torch.empty(2, B, H, device=dev)]
-            dc = [dfc[l].reshape(B, 2, H).permute(1, 0, 2).contiguous(), torch.empty(2, B, H, device=dev)]
+            dh0 = dfh[l].reshape(B, 2, H).permute(1, 0, 2).contiguous()
+            dc0 = dfc[l].reshape(B, 2, H).permute(1, 0, 2).contiguous()
             dgates = torch.empty(T, B, 2, 4 * H, dtype=torch.float32, device=dev)
-            for s in range(T):
-                a, b = s & 1, (s + 1) & 1
-                _call("dwc_lstm_step_bwd", s, T, B, H, L.ptr(whh), L.ptr(lens), L.ptr(dseq), L.ptr(gates), L.ptr(csave),
-                      L.ptr(dh[a]), L.ptr(dc[a]), L.ptr(dh[b]), L.ptr(dc[b]), L.ptr(dgates), L.stream())
+            ws = torch.empty(int(L.lib().dwc_lstm_workspace_bytes(B, H)), dtype=torch.uint8, device=dev)
+            _call("dwc_lstm_layer_bwd", T, B, H, L.ptr(whh), L.ptr(lens), L.ptr(dseq), L.ptr(gates), L.ptr(csave),
+                  L.ptr(dh0), L.ptr(dc0), L.ptr(dgates), L.ptr(ws), L.stream())
             names = [pre + f"{k}_l{l}{sfx}" for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")
                      for sfx in ("", "_reverse")]
             f.touch(*names)

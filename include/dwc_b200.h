@@ -210,27 +210,30 @@ int dwc_relu_bwd(const float* dout, const float* out, float* din, int64_t count,
 int dwc_mul(const float* a, const float* b, float* out, int64_t count, dwc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Text encoder (networks_v2.py:213-254): embedding + style concat, one LSTM time step for both
- * directions (gate order i,f,g,o; per-sample lengths give pack_padded_sequence semantics).
+ * Text encoder (networks_v2.py:213-254): embedding + style concat, bidirectional LSTM layers.
  * ------------------------------------------------------------------------------------------ */
 int dwc_embed_concat_fwd(const int64_t* tokens /*[B,T]*/, const float* emb, const float* style, const float* mask,
                          float* x /*[T,B,E+S]*/, int b, int t, int e, int s, dwc_stream_t stream);
 int dwc_embed_concat_bwd(const int64_t* tokens, const float* dx, const float* mask, float* demb, float* dstyle,
                          int b, int t, int e, int s, int pad_idx, dwc_stream_t stream);
-/* step index `step`: direction 0 handles time t=step, direction 1 handles t=T-1-step.
- * xproj [T,B,2,4H] (input projection + both biases), whh_t [2,H,4H] (transposed recurrent weights, see
- * dwc_transpose), h/c state [2,B,H] (ping-pong: h_in/h_out must differ),
- * out [T,B,2H], gates_save [T,B,2,4H] (activated gates i,f,g,o) and c_save [T,B,2,H] (cell state
- * after the step) for the backward pass (may be NULL in inference). */
-int dwc_lstm_step_fwd(int step, int t_total, int b, int h, const float* xproj, const float* whh_t,
-                      const int64_t* lens, const float* h_in, const float* c_in, float* h_out, float* c_out,
-                      float* out, float* gates_save, float* c_save, dwc_stream_t stream);
-/* backward of one step: consumes dh/dc state [2,B,H] (+ dout[t]), the NEXT processed step's gate
- * gradients are folded in through whh.  Writes dgates [T,B,2,4H] for the step. */
-int dwc_lstm_step_bwd(int step, int t_total, int b, int h, const float* whh, const int64_t* lens,
-                      const float* dout /*[T,B,2H] or NULL*/, const float* gates_save, const float* c_save,
-                      const float* dh_in, const float* dc_in, float* dh_out, float* dc_out,
-                      float* dgates, dwc_stream_t stream);
+/* Whole-layer bidirectional LSTM recurrence as ONE persistent cooperative kernel (csrc/lstm.cu): both
+ * directions, all time steps up to max(lens); gate order i,f,g,o; per-sample lengths give
+ * pack_padded_sequence semantics (state frozen and output zero at t >= lens[b]).
+ *   xproj [T,B,2,4H]  input projection + both biases;  whh [2,4H,H] recurrent weights (nn.LSTM layout,
+ *   forward then reverse);  out [T,B,2H] (may be NULL);  gates_save [T,B,2,4H] (activated gates) and
+ *   c_save [T,B,2,H] (cell state after the step) for the backward pass (both NULL in inference);
+ *   h_final / c_final [2,B,H];  workspace: dwc_lstm_workspace_bytes(b, h) bytes.
+ * Replaces nn.LSTM forward (networks_v2.py:225-233) after the input-projection GEMM. */
+int64_t dwc_lstm_workspace_bytes(int b, int h);
+int dwc_lstm_layer_fwd(int t_total, int b, int h, const float* xproj, const float* whh, const int64_t* lens,
+                       float* out, float* gates_save, float* c_save, float* h_final, float* c_final,
+                       void* workspace, dwc_stream_t stream);
+/* Backward of the recurrence: dout [T,B,2H] (gradient of `out`, may be NULL), dh_final / dc_final [2,B,H]
+ * (gradients of the final states) -> dgates [T,B,2,4H] (gradient of the gate pre-activations, zero at
+ * padded steps), from which the caller forms the weight / input gradients with GEMMs. */
+int dwc_lstm_layer_bwd(int t_total, int b, int h, const float* whh, const int64_t* lens, const float* dout,
+                       const float* gates_save, const float* c_save, const float* dh_final,
+                       const float* dc_final, float* dgates, void* workspace, dwc_stream_t stream);
 
 /* dst[b][c][r] = src[b][r][c] (float32) */
 int dwc_transpose(const float* src, float* dst, int batch, int rows, int cols, dwc_stream_t stream);
