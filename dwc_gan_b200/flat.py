@@ -160,8 +160,8 @@ class FusedAdam(torch.optim.Optimizer):
         self.steps = {n: 0 for n in self._names}
         self.m = None
         self.v = None
-        self._hyper_host = None
         self._hyper_dev = None
+        self.captured = None
         self.grad_scale = 1.0
 
     def _ensure_state(self):
@@ -191,14 +191,35 @@ class FusedAdam(torch.optim.Optimizer):
             prev_merged = True
         return out
 
+    MAX_RANGES = 64
+
+    def _hyper_row(self, st):
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        return [g["lr"], b1, b2, g["eps"], g["weight_decay"], 1 - b1 ** st, 1 - b2 ** st, self.grad_scale]
+
+    def _launch(self, ranges, hd):
+        f = self.flat
+        lib = L.lib()
+        for i, (s, e, _) in enumerate(ranges):
+            L.check(lib.dwc_adam_step(L.ptr(f.data[s:]), L.ptr(f.grad[s:]), L.ptr(self.m[s:]), L.ptr(self.v[s:]),
+                                      L.i64(e - s), None, L.ptr(hd[i]), L.stream()), "adam")
+
+    def graph_buffers(self):
+        """Persistent hyper-parameter buffers of the CUDA-graph path (allocate before capturing)."""
+        if self._hyper_dev is None or self._hyper_dev.device != self.flat.data.device:
+            self._hyper_dev = torch.zeros(self.MAX_RANGES, 8, dtype=torch.float32, device=self.flat.data.device)
+            self._hyper_ring = [torch.zeros(self.MAX_RANGES, 8, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._hyper_events = [None] * 4
+            self._hyper_slot = 0
+        self._ensure_state()
+        return self._hyper_dev
+
     @torch.no_grad()
     def step(self, closure=None):
         f = self.flat
         if not f.data.is_cuda and not _DRYRUN[0]:
             raise RuntimeError("FusedAdam runs on CUDA only (no CPU fallback)")
-        self._ensure_state()
-        g = self.param_groups[0]
-        b1, b2 = g["betas"]
         ranges = self.active_ranges()
         if not ranges:
             return
@@ -209,20 +230,48 @@ class FusedAdam(torch.optim.Optimizer):
                     self.steps[n] += 1
             f.bump()
             return
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture: the kernels read their hyper-parameters from the persistent device rows that
+            # graph_prepare() refreshes before every replay; step counters advance in graph_finish().
+            if self._hyper_dev is None or len(ranges) > self.MAX_RANGES:
+                raise RuntimeError("FusedAdam: call graph_buffers() before capturing")
+            self.captured = dict(ranges=ranges, touched=[n for n in self._names if n in f.touched],
+                                 rep=[next(n for n in self._names if n in f.touched and s <= f.offsets[n] < e)
+                                      for s, e, _ in ranges])
+            self._launch(ranges, self._hyper_dev)
+            f.bump()
+            return
+        self._ensure_state()
         hyper = torch.empty(len(ranges), 8, dtype=torch.float32, pin_memory=True)
         for i, (_, _, st) in enumerate(ranges):
-            hyper[i] = torch.tensor([g["lr"], b1, b2, g["eps"], g["weight_decay"], 1 - b1 ** st, 1 - b2 ** st,
-                                     self.grad_scale])
+            hyper[i] = torch.tensor(self._hyper_row(st))
         hd = hyper.to(f.data.device, non_blocking=True)
         self._keep = (hyper, hd)
-        lib = L.lib()
-        for i, (s, e, _) in enumerate(ranges):
-            L.check(lib.dwc_adam_step(L.ptr(f.data[s:]), L.ptr(f.grad[s:]), L.ptr(self.m[s:]), L.ptr(self.v[s:]),
-                                      L.i64(e - s), None, L.ptr(hd[i]), L.stream()), "adam")
+        self._launch(ranges, hd)
         for n in self._names:
             if n in f.touched:
                 self.steps[n] += 1
         f.bump()
+
+    def graph_prepare(self, rec):
+        """Before a replay of a graph captured with `rec = self.captured`: upload this step's hyper-parameters."""
+        slot = self._hyper_slot
+        self._hyper_slot = (slot + 1) % len(self._hyper_ring)
+        ev = self._hyper_events[slot]
+        if ev is not None:
+            ev.synchronize()
+        host = self._hyper_ring[slot]
+        for i, n in enumerate(rec["rep"]):
+            host[i] = torch.tensor(self._hyper_row(self.steps[n] + 1))
+        self._hyper_dev.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hyper_events[slot] = ev
+
+    def graph_finish(self, rec):
+        for n in rec["touched"]:
+            self.steps[n] += 1
+        self.flat.bump()
 
     def state_dict(self):
         """torch.optim.Adam-shaped state (what Solver.save writes, solver.py:413)."""

@@ -15,6 +15,7 @@ nsgan/wgan) are out of scope and raise NotImplementedError when enabled.
 from __future__ import annotations
 
 import copy
+import gc
 import os
 
 import torch
@@ -88,6 +89,12 @@ class Solver(nn.Module):
         self.criterionL1 = torch.nn.L1Loss()
         self.grad_sync = None        # set by parallel.DataParallelSync
         self.noise_hook = None       # tests: callable(name) -> eps tensor for dist_sampling_split
+        # CUDA graphs: after `graph_warmup` eager calls per (phase, batch shape, attention status) the whole
+        # phase (forward, backward, gradient all-reduce, Adam) is captured once and replayed afterwards.
+        self.use_cuda_graphs = os.environ.get("DWC_CUDA_GRAPHS", "1") != "0"
+        self.graph_warmup = 2
+        self._graphs = {}
+        self._ds_w_dev = None
 
     # ------------------------------------------------------------------ plumbing
     def _apply(self, fn, *a, **k):
@@ -149,6 +156,68 @@ class Solver(nn.Module):
         img, att = self.gen.decode(content, style)
         return img, att
 
+    # ------------------------------------------------------------------ CUDA-graph plumbing
+    def _run_phase(self, phase, impl, opt, tensors, configs, iters):
+        """Run one update phase: eagerly for the first calls of a given shape, then as a replayed CUDA graph.
+        The graph holds every kernel of the phase (forward, backward, NCCL gradient all-reduce, Adam); per-step
+        host values reach it through device memory only (static input buffers, Adam hyper-parameter rows, the
+        diversity weight), so a replay is numerically the same program as the eager call."""
+        x_real = tensors[0]
+        if not (self.use_cuda_graphs and x_real.is_cuda and self.noise_hook is None):
+            return impl(*tensors, configs, iters)
+        key = (phase, tuple(tuple(t.shape) for t in tensors), tuple(str(t.dtype) for t in tensors),
+               bool(self.use_attention), self.training, ops.RT.dtype, ops.RT.use_tc)
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = dict(calls=0, graph=None)
+        if ent["graph"] is None:
+            ent["calls"] += 1
+            if ent["calls"] <= self.graph_warmup:
+                return impl(*tensors, configs, iters)
+            self._capture(ent, impl, opt, tensors, configs, iters)
+        for st, t in zip(ent["static"], tensors):
+            if st.data_ptr() != t.data_ptr():
+                st.copy_(t, non_blocking=True)
+        opt.graph_prepare(ent["adam"])
+        ent["graph"].replay()
+        opt.graph_finish(ent["adam"])
+        ops.RT.launches += ent["launches"]
+        for k, v in ent["attrs"].items():
+            setattr(self, k, v)
+
+    def _release_autograd(self):
+        """Drop every reference to the previous step's autograd graph (loss attributes, the AdaIN parameters the
+        decoder modules still hold): gradient-accumulator nodes that outlive a step stay bound to the stream they
+        were created on, which a stream capture must not depend on."""
+        for k, v in list(self.__dict__.items()):
+            if 'loss' in k and isinstance(v, torch.Tensor) and v.grad_fn is not None:
+                self.__dict__[k] = v.detach()
+        for net in (self.gen, getattr(self, 'gen_copy', None)):
+            if net is None:
+                continue
+            for m in net.modules():
+                if m.__class__.__name__ == "AdaptiveInstanceNorm2d" and m.weight is not None:
+                    m.weight = m.weight.detach()
+                    m.bias = m.bias.detach()
+        gc.collect()
+
+    def _capture(self, ent, impl, opt, tensors, configs, iters):
+        self._release_autograd()
+        static = [t.clone() for t in tensors]
+        opt.graph_buffers()
+        for net in (self.gen, self.dis):
+            net.ensure_flat().bump()             # every graph packs the weights it uses itself
+        before = {k: v for k, v in self.__dict__.items() if 'loss' in k}
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = ops.RT.launches
+        with torch.cuda.graph(g):
+            impl(*static, configs, iters)
+        ent["launches"], ops.RT.launches = ops.RT.launches - l0, l0     # kernels per replay (nothing ran yet)
+        ent["attrs"] = {k: v for k, v in self.__dict__.items() if 'loss' in k and before.get(k, None) is not v}
+        ent["static"], ent["graph"], ent["adam"] = static, g, opt.captured
+        opt.captured = None
+
     # ------------------------------------------------------------------ inference
     def forward(self, x_real, txt_src2trg, txt_lens):
         """Translate (solver.py:142-149, with Solver.sample's cat-then-decode semantics)."""
@@ -159,6 +228,15 @@ class Solver(nn.Module):
 
     # ------------------------------------------------------------------ G step
     def gen_update(self, x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg, configs, iters):
+        # the reference lowers the diversity weight in the middle of the step, before its only use (solver.py:185)
+        self.init_ds_w = max(self.init_ds_w - 1 / 1e5, 0.0)
+        if self._ds_w_dev is None or self._ds_w_dev.device != x_real.device:
+            self._ds_w_dev = torch.zeros((), dtype=torch.float32, device=x_real.device)
+        self._ds_w_dev.fill_(self.init_ds_w)
+        self._run_phase('gen', self._gen_update_impl, self.gen_opt,
+                        (x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg), configs, iters)
+
+    def _gen_update_impl(self, x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg, configs, iters):
         gen, dis = self.gen, self.dis
         self.gen_opt.zero_grad()
         x_real = x_real.float()
@@ -182,7 +260,6 @@ class Solver(nn.Module):
         x_fake1 = self._blend(x_fake1, att1, x_real)
         self.loss_ds = ops.l1_loss(x_fake1, x_fake2)
         content_rand, mu_rand, _ = gen.encode_fused(x_fake1)
-        self.init_ds_w = max(self.init_ds_w - 1 / 1e5, 0.0)
 
         content_fake_rec, mu_fake_rec, _ = gen.encode_fused(x_fake)
         if configs['recon_x_cyc_w'] > 0:
@@ -224,7 +301,7 @@ class Solver(nn.Module):
                 configs['recon_x_cyc_w'] * self.loss_gen_cycrecon_x + \
                 configs['kl_w'] * self.loss_kl_x + \
                 configs['kl_w'] * self.loss_kl_trg - \
-                self.init_ds_w * self.loss_ds
+                self._ds_w_dev * self.loss_ds
             self.loss_gen_total.backward()
         if self.grad_sync is not None:
             self.grad_sync(self.gen)
@@ -232,6 +309,10 @@ class Solver(nn.Module):
 
     # ------------------------------------------------------------------ D step
     def dis_update(self, x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg, configs, iters):
+        self._run_phase('dis', self._dis_update_impl, self.dis_opt,
+                        (x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg), configs, iters)
+
+    def _dis_update_impl(self, x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg, configs, iters):
         gen, dis = self.gen, self.dis
         self.dis_opt.zero_grad()
         x_real = x_real.float()
