@@ -5,11 +5,14 @@
 // ---------------------------------------------------------------------------------------------------
 // C[m,n] = act(alpha * sum_k A[m,k] B[k,n] + bias[n] + beta*C[m,n]); 64x64 tile, 256 threads x (4x4)
 // ---------------------------------------------------------------------------------------------------
+// blockIdx.z = K split: split z covers k in [z*kper, min(K, (z+1)*kper)) and (when gridDim.z > 1) writes its raw
+// partial sums to a dense [split][M][N] workspace; sgemm_splitk_finish_kernel applies alpha / bias / beta / act.
 template <typename TA>
 __global__ void __launch_bounds__(256)
     sgemm_kernel(int M, int N, int K, float alpha, const TA* __restrict__ A, long long a_sm, long long a_sk,
                  const float* __restrict__ B, long long b_sk, long long b_sn, float beta, float* __restrict__ C,
-                 long long c_sm, long long c_sn, const float* __restrict__ bias, int act) {
+                 long long c_sm, long long c_sn, const float* __restrict__ bias, int act, int kper,
+                 float* __restrict__ ws) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tid = threadIdx.x;
@@ -23,18 +26,19 @@ __global__ void __launch_bounds__(256)
   // loaders: choose the thread->element map so that the unit-stride axis is the fast one
   const bool a_kfast = (a_sk == 1);
   const bool b_nfast = (b_sn == 1);
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  const int kbeg = blockIdx.z * kper, kend = min(K, kbeg + kper);
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int e = tid + j * 256;   // 0..1023
       int mm, kk;
       if (a_kfast) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
       int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < M && gk < K) ? to_f<TA>(A[gm * a_sm + gk * a_sk]) : 0.f;
+      As[kk][mm] = (gm < M && gk < kend) ? to_f<TA>(A[gm * a_sm + gk * a_sk]) : 0.f;
       int nn, k2;
       if (b_nfast) { nn = e & 63; k2 = e >> 6; } else { k2 = e & 15; nn = e >> 4; }
       int gn = n0 + nn, gk2 = k0 + k2;
-      Bs[k2][nn] = (gn < N && gk2 < K) ? B[gk2 * b_sk + gn * b_sn] : 0.f;
+      Bs[k2][nn] = (gn < N && gk2 < kend) ? B[gk2 * b_sk + gn * b_sn] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -49,6 +53,7 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
   }
+  const bool split = gridDim.z > 1;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int m = m0 + ty * 4 + i;
@@ -57,27 +62,77 @@ __global__ void __launch_bounds__(256)
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
       if (n >= N) continue;
-      float* o = C + m * c_sm + n * c_sn;
-      float v = alpha * acc[i][j] + (bias ? bias[n] : 0.f) + (beta != 0.f ? beta * *o : 0.f);
-      if (act == 1) v = v > 0.f ? v : 0.f;
-      *o = v;
+      if (split) {
+        ws[((long long)blockIdx.z * M + m) * N + n] = acc[i][j];
+      } else {
+        float* o = C + m * c_sm + n * c_sn;
+        float v = alpha * acc[i][j] + (bias ? bias[n] : 0.f) + (beta != 0.f ? beta * *o : 0.f);
+        if (act == 1) v = v > 0.f ? v : 0.f;
+        *o = v;
+      }
     }
   }
+}
+
+__global__ void sgemm_splitk_finish_kernel(int M, int N, int splits, float alpha, const float* __restrict__ ws,
+                                           float beta, float* __restrict__ C, long long c_sm, long long c_sn,
+                                           const float* __restrict__ bias, int act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const int m = i / N, n = i - m * N;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += ws[(long long)z * M * N + i];   // fixed order: deterministic
+  float* o = C + m * c_sm + n * c_sn;
+  float v = alpha * s + (bias ? bias[n] : 0.f) + (beta != 0.f ? beta * *o : 0.f);
+  if (act == 1) v = v > 0.f ? v : 0.f;
+  *o = v;
+}
+
+// number of K splits for a problem whose (M, N) tile grid alone cannot fill the GPU
+static int sgemm_splits(int m, int n, int k) {
+  const int ctas = cdiv(m, 64) * cdiv(n, 64);
+  if (ctas >= 64 || k < 512) return 1;
+  int s = cdiv(2 * dwc_num_sms(), ctas);
+  const int smax = cdiv(k, 128);
+  if (s > smax) s = smax;
+  return s < 1 ? 1 : s;
+}
+
+extern "C" int64_t dwc_sgemm_workspace_bytes(int m, int n, int k) {
+  const int s = sgemm_splits(m, n, k);
+  return s > 1 ? (int64_t)s * m * n * sizeof(float) : 0;
+}
+
+extern "C" int dwc_sgemm_ws(int m, int n, int k, float alpha, const void* a, int a_dtype, int64_t a_sm, int64_t a_sk,
+                            const float* b, int64_t b_sk, int64_t b_sn, float beta, float* c, int64_t c_sm, int64_t c_sn,
+                            const float* bias, int act, float* workspace, int64_t workspace_bytes, dwc_stream_t stream) {
+  DWC_CHECK(m > 0 && n > 0 && k > 0, "dwc_sgemm: empty problem (%d,%d,%d)", m, n, k);
+  int splits = workspace ? sgemm_splits(m, n, k) : 1;
+  if (splits > 1 && workspace_bytes < (int64_t)splits * m * n * (int64_t)sizeof(float)) splits = 1;
+  int kper = cdiv(cdiv(k, splits), 16) * 16;
+  splits = cdiv(k, kper);
+  dim3 grid(cdiv(m, 64), cdiv(n, 64), splits);
+  cudaStream_t st = as_stream(stream);
+  if (a_dtype == DWC_F32)
+    sgemm_kernel<float><<<grid, 256, 0, st>>>(m, n, k, alpha, reinterpret_cast<const float*>(a), a_sm, a_sk, b, b_sk,
+                                              b_sn, beta, c, c_sm, c_sn, bias, act, kper, workspace);
+  else
+    sgemm_kernel<bf16><<<grid, 256, 0, st>>>(m, n, k, alpha, reinterpret_cast<const bf16*>(a), a_sm, a_sk, b, b_sk,
+                                             b_sn, beta, c, c_sm, c_sn, bias, act, kper, workspace);
+  DWC_LAUNCH_CHECK();
+  if (splits > 1) {
+    sgemm_splitk_finish_kernel<<<cdiv((long long)m * n, 256), 256, 0, st>>>(m, n, splits, alpha, workspace, beta, c,
+                                                                            c_sm, c_sn, bias, act);
+    DWC_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 extern "C" int dwc_sgemm(int m, int n, int k, float alpha, const void* a, int a_dtype, int64_t a_sm, int64_t a_sk,
                          const float* b, int64_t b_sk, int64_t b_sn, float beta, float* c, int64_t c_sm, int64_t c_sn,
                          const float* bias, int act, dwc_stream_t stream) {
-  DWC_CHECK(m > 0 && n > 0 && k > 0, "dwc_sgemm: empty problem (%d,%d,%d)", m, n, k);
-  dim3 grid(cdiv(m, 64), cdiv(n, 64));
-  if (a_dtype == DWC_F32)
-    sgemm_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(m, n, k, alpha, reinterpret_cast<const float*>(a), a_sm,
-                                                              a_sk, b, b_sk, b_sn, beta, c, c_sm, c_sn, bias, act);
-  else
-    sgemm_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(m, n, k, alpha, reinterpret_cast<const bf16*>(a), a_sm,
-                                                             a_sk, b, b_sk, b_sn, beta, c, c_sm, c_sn, bias, act);
-  DWC_LAUNCH_CHECK();
-  return 0;
+  return dwc_sgemm_ws(m, n, k, alpha, a, a_dtype, a_sm, a_sk, b, b_sk, b_sn, beta, c, c_sm, c_sn, bias, act, nullptr, 0,
+                      stream);
 }
 
 __global__ void colsum_kernel(int M, int N, const float* __restrict__ A, long long a_sm, long long a_sn,

@@ -343,6 +343,59 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Per-sample variant (grid.y = sample, 256 %% (C/8) == 0): every thread keeps ONE 8-channel group for the whole launch,
+// so its scale / shift coefficients are loaded once instead of once per pixel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    post_fwd_ps_kernel(HB y, const float4* __restrict__ coef, int act, HB res, int has_res, HB out) {
+  const int cvs = out.c >> 3;
+  const int cv = threadIdx.x % cvs, pl = threadIdx.x / cvs, PL = 256 / cvs;
+  const int n = blockIdx.y, c0 = cv * 8;
+  const T* yb = reinterpret_cast<const T*>(y.ptr);
+  const T* rb = reinterpret_cast<const T*>(res.ptr);
+  T* ob = reinterpret_cast<T*>(out.ptr);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (coef) {
+      const float4 q = coef[(long long)n * out.c + c0 + e];
+      sc[e] = q.x; sh[e] = q.y;
+    } else { sc[e] = 1.f; sh[e] = 0.f; }
+  }
+  const int npix = out.hp * out.wp;
+  for (int p = blockIdx.x * PL + pl; p < npix; p += gridDim.x * PL) {
+    const int Y = p / out.wp, X = p - Y * out.wp;
+    const int iy = reflect_idx(Y - out.halo, out.h), ix = reflect_idx(X - out.halo, out.w);
+    float v[8];
+    Vec8<T>::load(yb + y.off(n, iy, ix) + c0, v);
+    if (coef) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = act_fwd(sc[e] * v[e] + sh[e], act);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = act_fwd(v[e], act);
+    }
+    if (has_res) {
+      float rr[8];
+      Vec8<T>::load(rb + res.off(n, iy, ix) + c0, rr);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += rr[e];
+    }
+    Vec8<T>::store(ob + out.off_padded(n, Y, X) + c0, v);
+  }
+}
+
+// grid for the per-sample kernels: enough blocks per sample to fill the GPU ~8 CTAs deep
+static inline dim3 ps_grid(int npix, int cvs, int n) {
+  const int PL = 256 / cvs;
+  int bx = (npix + PL - 1) / PL;
+  int cap = (dwc_num_sms() * 8 + n - 1) / n;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  return dim3(bx < 1 ? 1 : bx, n);
+}
+static inline bool ps_ok(int c) { return c % 8 == 0 && (c / 8) <= 256 && 256 % (c / 8) == 0; }
+
 static inline int ew_grid(long long total) {
   long long b = (total + 255) / 256;
   long long cap = (long long)dwc_num_sms() * 16;
@@ -358,8 +411,13 @@ extern "C" int dwc_post_fwd(const dwc_hbuf_t* y, const float* coef, int act, con
             "dwc_post_fwd: plane layout needs even padded extent");
   HB hy(*y), ho(*out), hr = res ? HB(*res) : HB(*y);
   long long total = ho.padded_pixels() * (out->c / 8);
-  DISPATCH_T(y->dtype, (post_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
-                           hy, reinterpret_cast<const float4*>(coef), act, hr, res != nullptr, ho)));
+  if (ps_ok(out->c)) {
+    DISPATCH_T(y->dtype, (post_fwd_ps_kernel<T><<<ps_grid(ho.hp * ho.wp, out->c / 8, out->n), 256, 0, as_stream(stream)>>>(
+                             hy, reinterpret_cast<const float4*>(coef), act, hr, res != nullptr, ho)));
+  } else {
+    DISPATCH_T(y->dtype, (post_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
+                             hy, reinterpret_cast<const float4*>(coef), act, hr, res != nullptr, ho)));
+  }
   DWC_LAUNCH_CHECK();
   return 0;
 }
@@ -423,6 +481,60 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256)
+    post_bwd_apply_ps_kernel(HB dout, HB y, const float4* __restrict__ coef, const float4* __restrict__ bco, int act,
+                             HB dy, HB dres, int has_dres) {
+  const int hmax = max(dy.halo, has_dres ? dres.halo : 0);
+  const int HP = y.h + 2 * hmax, WP = y.w + 2 * hmax;
+  const int cvs = y.c >> 3;
+  const int cv = threadIdx.x % cvs, pl = threadIdx.x / cvs, PL = 256 / cvs;
+  const int n = blockIdx.y, c0 = cv * 8;
+  const T* yb = reinterpret_cast<const T*>(y.ptr);
+  T* dyb = reinterpret_cast<T*>(dy.ptr);
+  T* drb = reinterpret_cast<T*>(dres.ptr);
+  float sc[8], sh[8], ba[8], bb[8], bc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (coef) {
+      const float4 q = coef[(long long)n * y.c + c0 + e];
+      sc[e] = q.x; sh[e] = q.y;
+    } else { sc[e] = 1.f; sh[e] = 0.f; }
+    if (bco) {
+      const float4 q = bco[(long long)n * y.c + c0 + e];
+      ba[e] = q.x; bb[e] = q.y; bc[e] = q.z;
+    } else { ba[e] = 1.f; bb[e] = 0.f; bc[e] = 0.f; }
+  }
+  const int npix = HP * WP;
+  for (int p = blockIdx.x * PL + pl; p < npix; p += gridDim.x * PL) {
+    const int Y = p / WP, X = p - Y * WP;
+    const int iy = Y - hmax, ix = X - hmax;     // interior coordinates (may be outside)
+    const bool interior = iy >= 0 && iy < y.h && ix >= 0 && ix < y.w;
+    float g[8], o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = o[e] = 0.f;
+    if (interior) {
+      fold_read8<T>(dout, n, iy, ix, c0, g);
+      float v[8];
+      Vec8<T>::load(yb + y.off(n, iy, ix) + c0, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float z = coef ? sc[e] * v[e] + sh[e] : v[e];
+        const float dz = g[e] * act_grad(z, act);
+        o[e] = bco ? ba[e] * dz + bb[e] * v[e] + bc[e] : dz;
+      }
+    }
+    {
+      int py = iy + dy.halo, px = ix + dy.halo;
+      if (py >= 0 && py < dy.hp && px >= 0 && px < dy.wp) Vec8<T>::store(dyb + dy.off_padded(n, py, px) + c0, o);
+    }
+    if (has_dres) {
+      int py = iy + dres.halo, px = ix + dres.halo;
+      if (py >= 0 && py < dres.hp && px >= 0 && px < dres.wp) Vec8<T>::store(drb + dres.off_padded(n, py, px) + c0, g);
+    }
+  }
+}
+
 extern "C" int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, const float* bco,
                                   int act, const dwc_hbuf_t* dy, const dwc_hbuf_t* dres, dwc_stream_t stream) {
   DWC_CHECK(y->c % 8 == 0 && y->layout == 0 && dy->layout == 0, "dwc_post_bwd_apply: needs C %% 8 == 0, plain y/dy");
@@ -431,9 +543,17 @@ extern "C" int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, c
   int hmax = dy->halo;
   if (dres && dres->halo > hmax) hmax = dres->halo;
   long long total = (long long)y->n * (y->h + 2 * hmax) * (y->w + 2 * hmax) * (y->c / 8);
-  DISPATCH_T(y->dtype, (post_bwd_apply_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
-                           hd, hy, reinterpret_cast<const float4*>(coef), reinterpret_cast<const float4*>(bco), act,
-                           hdy, hr, dres != nullptr)));
+  if (ps_ok(y->c)) {
+    DISPATCH_T(y->dtype,
+               (post_bwd_apply_ps_kernel<T><<<ps_grid((y->h + 2 * hmax) * (y->w + 2 * hmax), y->c / 8, y->n), 256, 0,
+                                              as_stream(stream)>>>(hd, hy, reinterpret_cast<const float4*>(coef),
+                                                                   reinterpret_cast<const float4*>(bco), act, hdy, hr,
+                                                                   dres != nullptr)));
+  } else {
+    DISPATCH_T(y->dtype, (post_bwd_apply_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
+                             hd, hy, reinterpret_cast<const float4*>(coef), reinterpret_cast<const float4*>(bco), act,
+                             hdy, hr, dres != nullptr)));
+  }
   DWC_LAUNCH_CHECK();
   return 0;
 }

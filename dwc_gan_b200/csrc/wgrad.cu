@@ -363,7 +363,8 @@ static int wg_plan(const dwc_wgrad_t* g, WgPlan* pl) {
     pl->mr = 64;
     pl->items = cdiv(pl->cm, 64) * cdiv(pl->cn, 64) * g->ntaps;
   }
-  int want = cdiv(2 * dwc_num_sms(), pl->items);
+  // one wave of CTAs: fewer K splits mean fewer partial tiles for the (HBM-bound) reduction pass
+  int want = dwc_num_sms() / pl->items;
   if (want < 1) want = 1;
   if (want > pl->ntiles) want = pl->ntiles;
   if (want > 64) want = 64;

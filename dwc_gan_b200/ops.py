@@ -513,8 +513,10 @@ def relu_gap(y: HB):
 # --------------------------------------------------------------------------------------------
 
 def sgemm(m, n, k, alpha, a, a_sm, a_sk, b, b_sk, b_sn, beta, c, c_sm, c_sn, bias=None, act=0):
-    _call("dwc_sgemm", m, n, k, alpha, L.ptr(a), L.dt(a), a_sm, a_sk, L.ptr(b), b_sk, b_sn, beta, L.ptr(c), c_sm, c_sn,
-          L.ptr(bias), act, L.stream())
+    need = int(L.lib().dwc_sgemm_workspace_bytes(m, n, k))
+    ws = RT.workspace(need, c.device) if need else None
+    _call("dwc_sgemm_ws", m, n, k, alpha, L.ptr(a), L.dt(a), a_sm, a_sk, L.ptr(b), b_sk, b_sn, beta, L.ptr(c), c_sm,
+          c_sn, L.ptr(bias), act, L.ptr(ws), need, L.stream())
 
 
 class LinearFn(torch.autograd.Function):

@@ -202,6 +202,13 @@ int dwc_relu_gap_bwd(const float* dout, const dwc_hbuf_t* y, const dwc_hbuf_t* d
 int dwc_sgemm(int m, int n, int k, float alpha, const void* a, int a_dtype, int64_t a_sm, int64_t a_sk,
               const float* b, int64_t b_sk, int64_t b_sn, float beta, float* c, int64_t c_sm, int64_t c_sn,
               const float* bias, int act, dwc_stream_t stream);
+/* Same with a caller-provided float workspace of dwc_sgemm_workspace_bytes(m, n, k) bytes: problems with few
+ * output tiles and a long K (head layers at small batch) are then split along K over many CTAs and summed in a
+ * fixed order (deterministic). */
+int64_t dwc_sgemm_workspace_bytes(int m, int n, int k);
+int dwc_sgemm_ws(int m, int n, int k, float alpha, const void* a, int a_dtype, int64_t a_sm, int64_t a_sk,
+                 const float* b, int64_t b_sk, int64_t b_sn, float beta, float* c, int64_t c_sm, int64_t c_sn,
+                 const float* bias, int act, float* workspace, int64_t workspace_bytes, dwc_stream_t stream);
 /* out[n] (+)= sum_m A[m,n]  (bias gradients) */
 int dwc_colsum(int m, int n, const float* a, int64_t a_sm, int64_t a_sn, float* out, int accumulate,
                dwc_stream_t stream);

@@ -1,0 +1,174 @@
+"""Per-layer microbenchmark (BASELINE.json configs[4]): every conv geometry of SURVEY 8(a)-2 x {fprop, dgrad,
+wgrad} on the tcgen05 kernels, and the norm / post passes, each against its own roofline bound
+min(tensor peak, arithmetic intensity x HBM bandwidth).  Timed with CUDA events on the launching stream over a
+rotation of buffers larger than the 126 MB L2.
+
+  python tools/microbench.py [--batch 16] [--out profiles/xxx.md]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from dwc_gan_b200 import _lib as L  # noqa: E402
+from dwc_gan_b200 import plan as P  # noqa: E402
+from dwc_gan_b200.plan import HB  # noqa: E402
+
+# id, cin, cout, k, stride, pad, input H=W (128x128 network), how many times the layer runs forward per G+D step
+GEOMS = [
+    ("G2", 64, 128, 4, 2, 1, 128), ("G3", 128, 256, 4, 2, 1, 64), ("G4", 256, 256, 4, 2, 1, 32),
+    ("G5", 256, 256, 4, 2, 1, 16), ("G6", 256, 256, 4, 2, 1, 8), ("G7", 256, 256, 3, 1, 1, 32),
+    ("G8", 256, 128, 5, 1, 2, 64), ("G9", 128, 64, 5, 1, 2, 128),
+    ("D2", 64, 128, 4, 2, 1, 64), ("D3", 128, 256, 4, 2, 1, 32), ("D4", 256, 512, 4, 2, 1, 16),
+    ("D5", 512, 512, 4, 2, 1, 8), ("D2s", 64, 128, 4, 2, 1, 32), ("D3s", 128, 256, 4, 2, 1, 16),
+    ("D4s", 256, 512, 4, 2, 1, 8), ("D5s", 512, 512, 4, 2, 1, 4),
+]
+
+_ws = {}
+
+
+def workspace(nbytes):
+    t = _ws.get("t")
+    if t is None or t.numel() * 4 < nbytes:
+        t = torch.empty((nbytes + 3) // 4 + 1024, dtype=torch.float32, device="cuda")
+        _ws["t"] = t
+    return t
+
+
+def timeit(fns, reps=3):
+    for f in fns[:2]:
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for f in fns:
+            f()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / (reps * len(fns))
+
+
+def pack(w_krsc, mode, rows, cout, k, cin):
+    if mode == 0:
+        out = torch.empty(rows, k * k * cin, dtype=torch.bfloat16, device="cuda")
+    elif mode == 1:
+        out = torch.empty(rows, k * k * cout, dtype=torch.bfloat16, device="cuda")
+    else:
+        out = torch.empty(4, rows, 4 * cout, dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib().dwc_pack_weights(L.ptr(w_krsc), cout, k, k, cin, mode, L.ptr(out), L.BF16, rows, L.stream()), "pack")
+    return out
+
+
+def bench_geom(g, n, peaks):
+    name, cin, cout, k, s, p, hw = g
+    ho = (hw + 2 * p - k) // s + 1
+    layout = 0 if s == 1 else 1
+    hy = k - 1 if s == 1 else 1
+    bt = torch.bfloat16
+    in_bytes = n * (hw + 2 * p) ** 2 * cin * 2
+    out_bytes = n * (ho + 2 * hy) ** 2 * cout * 2
+    nbuf = max(2, min(24, int(300e6 // max(1, in_bytes + out_bytes)) + 1))
+    xs = [HB(torch.randn(HB.shape_of(n, hw, hw, cin, p, layout), device="cuda").to(bt), n, hw, hw, cin, p, layout)
+          for _ in range(nbuf)]
+    ys = [HB(torch.randn(HB.shape_of(n, ho, ho, cout, hy, 0), device="cuda").to(bt), n, ho, ho, cout, hy, 0)
+          for _ in range(nbuf)]
+    w = (torch.randn(cout, k, k, cin, device="cuda") * 0.02)
+    bias = torch.zeros(cout, device="cuda")
+    wf = pack(w, 0, cout, cout, k, cin)
+    wd = pack(w, 1 if s == 1 else 2, cin, cout, k, cin)
+    dw = torch.zeros(cout, k, k, cin, device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    flops = 2.0 * n * ho * ho * cout * k * k * cin
+    res = {}
+    fw = [P.plan_conv_fwd(xs[i], wf, cout, cout, bias, ys[i], k, s, L.TC) for i in range(nbuf)]
+    res["fprop"] = timeit([pl.launch for pl in fw])
+    dg = [P.plan_conv_dgrad(ys[i], wd, xs[i], k, s, L.TC) for i in range(nbuf)]
+    res["dgrad"] = timeit([(lambda ps=ps: [q.launch() for q in ps]) for ps in dg])
+    wg = [P.plan_conv_wgrad(ys[i], xs[i], dw, db, k, s, L.TC) for i in range(nbuf)]
+    res["wgrad"] = timeit([(lambda pl=pl: pl.launch(workspace)) for pl in wg])
+    w_bytes = cout * k * k * cin * 2
+    ai = flops / (in_bytes + out_bytes + w_bytes)
+    bound = min(peaks["tflops"] * 1e12, ai * peaks["hbm"] * 1e9)
+    rows = []
+    for op in ("fprop", "dgrad", "wgrad"):
+        t = res[op]
+        rows.append(dict(layer=name, op=op, n=n, cin=cin, cout=cout, k=k, stride=s, hw_in=hw, us=round(t * 1e6, 1),
+                         tflops=round(flops / t / 1e12, 1), bound_tflops=round(bound / 1e12, 1),
+                         frac_of_bound=round(flops / t / bound, 3), frac_of_tensor_peak=round(flops / t / 1e12 / peaks["tflops"], 3)))
+    return rows
+
+
+def bench_post(n, c, hw, kind, peaks):
+    """norm site: stats + finalize + fused normalise/act/pad pass (forward) and reduce + finalize + apply (backward)."""
+    import ctypes as C
+    from dwc_gan_b200 import ops
+    bt = torch.bfloat16
+    nbuf = max(2, min(24, int(300e6 // (n * hw * hw * c * 4)) + 1))
+    ys = [HB(torch.randn(n, hw, hw, c, device="cuda").to(bt), n, hw, hw, c, 0, 0) for _ in range(nbuf)]
+    E = n * hw * hw * c
+    nw = torch.rand(n, c, device="cuda") if kind == ops.NORM_ADAIN else torch.rand(c, device="cuda")
+    nb = torch.rand(n, c, device="cuda") if kind == ops.NORM_ADAIN else torch.rand(c, device="cuda")
+
+    gbuf = (torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda"))
+
+    class _LN:
+        def grad_buffers(self):
+            return gbuf
+    outs = []
+
+    def fwd(y):
+        yt = y.t.detach().requires_grad_(True)
+        o = ops.PostFn.apply(yt, nw, nb, None, None, y, kind, ops.ACT_RELU, None, 1, 0, _LN(), 1e-5)
+        return yt, o
+    tf = timeit([(lambda y=y: fwd(y)) for y in ys])
+    pairs = [fwd(y) for y in ys]
+    gs = [torch.randn_like(o) for _, o in pairs]
+    # zero halo of the incoming gradient is a convention of the conv dgrad producer; content is irrelevant for timing
+    tb = timeit([(lambda pr=pr, g=g: torch.autograd.grad(pr[1], pr[0], g, retain_graph=True)) for pr, g in zip(pairs, gs)],
+                reps=2)
+    rows = []
+    for op, t, byts in (("norm_fwd", tf, 2 * E * 2), ("norm_bwd", tb, 3 * E * 2)):
+        rows.append(dict(layer="%s %dx%dx%d" % ({1: "IN", 2: "AdaIN", 3: "LN"}[kind], c, hw, hw), op=op, n=n, us=round(t * 1e6, 1),
+                         gbs=round(byts / t / 1e9, 1), frac_of_hbm=round(byts / t / 1e9 / peaks["hbm"], 3)))
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    d = json.load(open(pk)) if os.path.exists(pk) else {}
+    peaks = dict(tflops=d.get("bf16_tflops", 1590.0), hbm=d.get("hbm_gbs", 6650.0))
+    from dwc_gan_b200 import ops
+    ops.RT.set_mode("bf16")
+    lines = ["# conv microbench, batch %d, bf16 tcgen05 kernels (peaks: %.0f TFLOP/s, %.0f GB/s %s)" % (
+        args.batch, peaks["tflops"], peaks["hbm"], "measured" if d else "fallback"),
+        "| layer | op | Cin->Cout k/s @in | us | TFLOP/s | bound TFLOP/s | frac of bound | frac of tensor peak |", "|---|---|---|---|---|---|---|---|"]
+    for g in GEOMS:
+        if args.only and g[0] not in args.only.split(","):
+            continue
+        for r in bench_geom(g, args.batch, peaks):
+            lines.append("| %s | %s | %d->%d k%d/s%d @%d | %.1f | %.1f | %.1f | %.3f | %.3f |" % (
+                r["layer"], r["op"], r["cin"], r["cout"], r["k"], r["stride"], r["hw_in"], r["us"], r["tflops"],
+                r["bound_tflops"], r["frac_of_bound"], r["frac_of_tensor_peak"]))
+            print(lines[-1], flush=True)
+    lines += ["", "| norm site | op | us | GB/s (algorithmic) | frac of HBM peak |", "|---|---|---|---|---|"]
+    if not args.only:
+        for (c, hw, kind) in ((64, 128, 1), (128, 64, 1), (256, 32, 1), (256, 32, 2), (128, 64, 3), (64, 128, 3)):
+            for r in bench_post(args.batch, c, hw, kind, peaks):
+                lines.append("| %s | %s | %.1f | %.1f | %.3f |" % (r["layer"], r["op"], r["us"], r["gbs"], r["frac_of_hbm"]))
+                print(lines[-1], flush=True)
+    if args.out:
+        with open(args.out, "w") as f:
+            f.write("\n".join(lines) + "\n")
+
+
+if __name__ == "__main__":
+    main()

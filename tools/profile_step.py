@@ -8,11 +8,11 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 dev = torch.device("cuda", 0)
 s, cfg = bench.build_solver(dev, "bf16")
 b = {k: v.to(dev) for k, v in bench.make_host_batch(B, 128, 0).items()}
-for it in range(2):
+for it in range(5):
     bench.one_step(s, cfg, b, it)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
-bench.one_step(s, cfg, b, 2)
+bench.one_step(s, cfg, b, 5)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("profiled one step, batch", B)
