@@ -240,28 +240,28 @@ class Solver(nn.Module):
         gen, dis = self.gen, self.dis
         self.gen_opt.zero_grad()
         x_real = x_real.float()
+        B = x_real.shape[0]
         content_real, mu_real, lv_real = gen.encode_fused(x_real)
-
-        x_real_rec, att = self._decode(content_real, mu_real)
-        x_real_rec = self._blend(x_real_rec, att, x_real)
-        content_real_rec, mu_real_rec, _ = gen.encode_fused(x_real_rec)
-
         mt, lvt = gen.encode_txt(mu_real, txt_src2trg, txt_lens)
         mu_txt, lv_txt = torch.cat(mt, dim=1), torch.cat(lvt, dim=1)
-        x_fake, att = self._decode(content_real, mu_txt)
-        x_fake = self._blend(x_fake, att, x_real)
-
         style1 = self._sample_style(c_trg, 'gen1')
-        x_fake1, att1 = self._decode(content_real, style1)
         style2 = self._sample_style(c_trg, 'gen2')
+
+        # The three decodes that carry gradient (reconstruction, text-driven, sampled: solver.py:157-177) run as ONE
+        # 3B batch: no operator of the decoder couples samples (AdaIN / LayerNorm are per sample), so the result is
+        # the same as three calls while every kernel sees three times the rows.
+        imgs, atts = self._decode(torch.cat([content_real] * 3, dim=0), torch.cat([mu_real, mu_txt, style1], dim=0))
+        x3 = self._blend(imgs, atts, x_real.repeat(3, 1, 1, 1) if self.use_attention else None)
+        x_real_rec, x_fake, x_fake1 = x3.view(3, B, *x3.shape[1:]).unbind(0)
         with torch.no_grad():                                   # solver.py:181 detaches this branch
             x_fake2, att2 = self._decode(content_real, style2)
             x_fake2 = self._blend(x_fake2, att2, x_real)
-        x_fake1 = self._blend(x_fake1, att1, x_real)
         self.loss_ds = ops.l1_loss(x_fake1, x_fake2)
-        content_rand, mu_rand, _ = gen.encode_fused(x_fake1)
 
-        content_fake_rec, mu_fake_rec, _ = gen.encode_fused(x_fake)
+        # re-encode the three generated batches together (solver.py:162,182,186)
+        contents, mus, _ = gen.encode_fused(x3)
+        content_real_rec, content_fake_rec, content_rand = contents.view(3, B, *contents.shape[1:]).unbind(0)
+        mu_real_rec, mu_fake_rec, mu_rand = mus.view(3, B, mus.shape[1]).unbind(0)
         if configs['recon_x_cyc_w'] > 0:
             x_cycle, att_c = self._decode(content_fake_rec, mu_real)
             x_cycle = self._blend(x_cycle, att_c, x_real)
@@ -278,8 +278,13 @@ class Solver(nn.Module):
             self.loss_gen_cycrecon_x = self.recon_criterion(x_cycle, x_real)
 
         with _frozen(dis):                                      # D weight gradients are never used here
-            self.loss_gen_adv = dis.calc_gen_loss(x_fake, label_trg, configs['gan_w'], configs['cls_w']) + \
-                dis.calc_gen_loss(x_fake1, label_trg, configs['gan_w'], configs['cls_w'])
+            # D(x_fake) and D(x_fake1) (two calc_gen_loss calls, solver.py:206-207) as one 2B pass over x3[B:]
+            adv = 0
+            for src, cls in dis.forward(x3[B:]):
+                for i in range(2):
+                    adv = adv + ops.mse_const(src[i * B:(i + 1) * B], 1.0) * configs['gan_w']
+                    adv = adv + ops.bce_logits(cls[i * B:(i + 1) * B], label_trg) * configs['cls_w']
+            self.loss_gen_adv = adv
 
             self.loss_kl_x, self.loss_kl_trg = 0.0, 0.0
             if self.dist_mode == 'kls':
@@ -316,25 +321,22 @@ class Solver(nn.Module):
         gen, dis = self.gen, self.dis
         self.dis_opt.zero_grad()
         x_real = x_real.float()
+        B = x_real.shape[0]
         with torch.no_grad():                                   # G gradients of this phase are discarded anyway
             content_real, mu_real, _ = gen.encode_fused(x_real)
             style1 = self._sample_style(c_trg, 'dis1')
             mt, _ = gen.encode_txt(mu_real, txt_src2trg, txt_lens)
-            x_fake, att = self._decode(content_real, torch.cat(mt, dim=1))
-            x_fake1, att1 = self._decode(content_real, style1)
-            x_fake = self._blend(x_fake, att, x_real)
-            x_fake1 = self._blend(x_fake1, att1, x_real)
+            # both decodes (solver.py:327-328) as one 2B batch
+            imgs, atts = self._decode(torch.cat([content_real] * 2, dim=0), torch.cat([torch.cat(mt, dim=1), style1], dim=0))
+            fakes = self._blend(imgs, atts, x_real.repeat(2, 1, 1, 1) if self.use_attention else None)
 
         gw, cw = configs['gan_w'], configs['cls_w']
-        outs_real = dis.forward(x_real)
+        # D(x_real), D(x_fake), D(x_fake1) as one 3B pass; rows [0,B) real, [B,2B) x_fake, [2B,3B) x_fake1
         loss = 0.0
-        for fake in (x_fake, x_fake1):
-            outs_fake = dis.forward(fake)
-            for of, orl in zip(outs_fake, outs_real):
-                loss = loss + ops.mse_const(of[0], 0.0) * gw
-        # real-branch terms appear once per calc_dis_loss call, i.e. twice (solver.py:333-334)
-        for orl in outs_real:
-            loss = loss + 2.0 * (ops.mse_const(orl[0], 1.0) * gw + ops.bce_logits(orl[1], label_src) * cw)
+        for src, cls in dis.forward(torch.cat([x_real, fakes], dim=0)):
+            loss = loss + ops.mse_const(src[B:2 * B], 0.0) * gw + ops.mse_const(src[2 * B:], 0.0) * gw
+            # real-branch terms appear once per calc_dis_loss call, i.e. twice (solver.py:333-334)
+            loss = loss + 2.0 * (ops.mse_const(src[:B], 1.0) * gw + ops.bce_logits(cls[:B], label_src) * cw)
         self.loss_dis = loss
         self.loss_dis_all = self.loss_dis
         self.loss_dis_all.backward()

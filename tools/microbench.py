@@ -39,14 +39,21 @@ def workspace(nbytes):
 
 
 def timeit(fns, reps=3):
+    """Seconds per call: the calls are captured once into a CUDA graph and the replay is timed, so that the figure is
+    device time (the product path replays graphs too) and not Python / ctypes launch overhead."""
     for f in fns[:2]:
         f()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for f in fns:
+            f()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        for f in fns:
-            f()
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e-3 / (reps * len(fns))
