@@ -33,6 +33,10 @@ class Runtime:
         self.use_tc = True
         self._ws = {}
         self.launches = 0
+        self.side_streams = {}
+        self.side_keep = []
+        self.side_main = None
+        self.use_side_stream = True
 
     def set_mode(self, mode: str):
         if mode == "bf16":
@@ -58,6 +62,36 @@ class Runtime:
 
 
 RT = Runtime()
+
+
+def side_launch(fn, keep):
+    """Run `fn` (weight-gradient kernels: off the critical path of backward) on the device's side stream, ordered
+    after everything already enqueued on the current stream.  `keep` are the tensors the kernels read: they are held
+    until side_join() so that their memory is not reused while the side stream still needs it."""
+    if not RT.use_side_stream:
+        return fn()
+    dev = torch.cuda.current_device()
+    side = RT.side_streams.get(dev)
+    if side is None:
+        side = RT.side_streams[dev] = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        fn()
+    if not RT.side_keep:
+        # first side launch of this backward pass: join the streams when the pass ends, so that whoever called
+        # .backward() sees complete parameter gradients on its own stream
+        RT.side_main = main
+        torch.autograd.Variable._execution_engine.queue_callback(side_join)
+    RT.side_keep.append(keep)
+
+
+def side_join():
+    """Make the current stream wait for the side stream (before the gradients are consumed)."""
+    if RT.side_keep:
+        main = RT.side_main
+        main.wait_stream(RT.side_streams[main.device.index])
+    RT.side_keep.clear()
 
 
 def _require_cuda(t):
@@ -159,7 +193,7 @@ class ConvFn(torch.autograd.Function):
             tc = RT.tc_ok(c, cout)
             wp = P.plan_conv_wgrad(dy, xp, gw, gb, k, s, L.TC if tc else L.SIMT, accumulate=True)
             RT.launches += 3
-            wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device))
+            side_launch(lambda: wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device)), (dy.t, xp_t))
         return dxp_t, None, None, None
 
 
@@ -230,8 +264,8 @@ class FirstConvFn(torch.autograd.Function):
                 gb = None
             be = L.TC if RT.tc_ok(64, cout) else L.SIMT
             RT.launches += 3
-            P.plan_first_conv_wgrad(dy, rows_t, n, hp, wo, k, s, c, gw, gb, be).launch(
-                lambda nbytes: RT.workspace(nbytes, dy_t.device))
+            wp = P.plan_first_conv_wgrad(dy, rows_t, n, hp, wo, k, s, c, gw, gb, be)
+            side_launch(lambda: wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device)), (dy.t, rows_t))
         return dimg, None, None, None, None
 
 

@@ -308,6 +308,7 @@ class Solver(nn.Module):
                 configs['kl_w'] * self.loss_kl_trg - \
                 self._ds_w_dev * self.loss_ds
             self.loss_gen_total.backward()
+        ops.side_join()
         if self.grad_sync is not None:
             self.grad_sync(self.gen)
         self.gen_opt.step()
@@ -340,6 +341,7 @@ class Solver(nn.Module):
         self.loss_dis = loss
         self.loss_dis_all = self.loss_dis
         self.loss_dis_all.backward()
+        ops.side_join()
         if self.grad_sync is not None:
             self.grad_sync(self.dis)
         self.dis_opt.step()
