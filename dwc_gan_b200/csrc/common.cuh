@@ -86,11 +86,13 @@ struct HB {
   char* ptr;
   int n, h, w, c, halo, layout, dtype;
   int hp, wp;          // padded extents
+  int refl;            // halo width whose reflections a gradient gather still has to fold (0 once dwc_fold_halo ran)
   __host__ __device__ HB() {}
   __host__ HB(const dwc_hbuf_t& b)
       : ptr((char*)b.ptr), n(b.n), h(b.h), w(b.w), c(b.c), halo(b.halo), layout(b.layout), dtype(b.dtype) {
     hp = h + 2 * halo;
     wp = w + 2 * halo;
+    refl = halo;
   }
   // element offset of padded coordinate (n, Y, X) channel 0 ; Y in [0,hp), X in [0,wp)
   __device__ __forceinline__ int64_t off_padded(int in, int Y, int X) const {

@@ -33,11 +33,11 @@ __device__ __forceinline__ void fold_read8(const HB& d, int n, int y, int x, int
   int ys[3], xs[3], ny = 0, nx = 0;
   ys[ny++] = y;
   xs[nx++] = x;
-  if (d.halo > 0) {
-    if (y >= 1 && y <= d.halo) ys[ny++] = -y;
-    if (y >= d.h - 1 - d.halo && y <= d.h - 2) ys[ny++] = 2 * (d.h - 1) - y;
-    if (x >= 1 && x <= d.halo) xs[nx++] = -x;
-    if (x >= d.w - 1 - d.halo && x <= d.w - 2) xs[nx++] = 2 * (d.w - 1) - x;
+  if (d.refl > 0) {
+    if (y >= 1 && y <= d.refl) ys[ny++] = -y;
+    if (y >= d.h - 1 - d.refl && y <= d.h - 2) ys[ny++] = 2 * (d.h - 1) - y;
+    if (x >= 1 && x <= d.refl) xs[nx++] = -x;
+    if (x >= d.w - 1 - d.refl && x <= d.w - 2) xs[nx++] = 2 * (d.w - 1) - x;
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) f[e] = 0.f;
@@ -57,11 +57,11 @@ __device__ __forceinline__ float fold_read1(const HB& d, int n, int y, int x, in
   int ys[3], xs[3], ny = 0, nx = 0;
   ys[ny++] = y;
   xs[nx++] = x;
-  if (d.halo > 0) {
-    if (y >= 1 && y <= d.halo) ys[ny++] = -y;
-    if (y >= d.h - 1 - d.halo && y <= d.h - 2) ys[ny++] = 2 * (d.h - 1) - y;
-    if (x >= 1 && x <= d.halo) xs[nx++] = -x;
-    if (x >= d.w - 1 - d.halo && x <= d.w - 2) xs[nx++] = 2 * (d.w - 1) - x;
+  if (d.refl > 0) {
+    if (y >= 1 && y <= d.refl) ys[ny++] = -y;
+    if (y >= d.h - 1 - d.refl && y <= d.h - 2) ys[ny++] = 2 * (d.h - 1) - y;
+    if (x >= 1 && x <= d.refl) xs[nx++] = -x;
+    if (x >= d.w - 1 - d.refl && x <= d.w - 2) xs[nx++] = 2 * (d.w - 1) - x;
   }
   float s = 0.f;
   for (int i = 0; i < ny; ++i)
@@ -125,29 +125,6 @@ __global__ void __launch_bounds__(256)
     int c = blockIdx.x * 32 + threadIdx.x;
     if (c < y.c) out[((long long)n * splits + split) * y.c + c] = make_float2(t0, t1);
   }
-}
-
-extern "C" int dwc_nc_stats(const dwc_hbuf_t* y, int splits, float* stats, dwc_stream_t stream) {
-  DWC_CHECK(y->c % 8 == 0 && y->layout == 0, "dwc_nc_stats: needs C %% 8 == 0 and plain layout");
-  HB hy(*y);
-  dim3 grid(cdiv(y->c, 32), splits, y->n);
-  DISPATCH_T(y->dtype, (nc_reduce_kernel<T, 0><<<grid, 256, 0, as_stream(stream)>>>(hy, hy, nullptr, 0, splits,
-                                                                                       reinterpret_cast<float2*>(stats))));
-  DWC_LAUNCH_CHECK();
-  return 0;
-}
-
-extern "C" int dwc_post_bwd_reduce(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, int act, int splits,
-                                   float* red, dwc_stream_t stream) {
-  DWC_CHECK(y->c % 8 == 0 && y->layout == 0, "dwc_post_bwd_reduce: needs C %% 8 == 0 and plain y");
-  DWC_CHECK(dout->n == y->n && dout->h == y->h && dout->w == y->w && dout->c == y->c && dout->dtype == y->dtype,
-            "dwc_post_bwd_reduce: geometry mismatch");
-  HB hy(*y), hd(*dout);
-  dim3 grid(cdiv(y->c, 32), splits, y->n);
-  DISPATCH_T(y->dtype, (nc_reduce_kernel<T, 1><<<grid, 256, 0, as_stream(stream)>>>(
-                           hy, hd, reinterpret_cast<const float4*>(coef), act, splits, reinterpret_cast<float2*>(red))));
-  DWC_LAUNCH_CHECK();
-  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -248,58 +225,67 @@ __global__ void __launch_bounds__(256)
       bco[(long long)n * C + c] = make_float4((float)a, (float)b, (float)cc, 0.f);
     }
   } else if (kind == 3) {
-    // per-sample coefficients
+    // per-sample coefficients: one block per sample
     const double M = (double)C * hw;
-    for (int n = 0; n < N; ++n) {
-      double g1 = 0, g2 = 0;
-      const double mean = coef[(long long)n * C].z;
-      for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double S1 = 0, S2 = 0;
-        for (int k = 0; k < splits; ++k) {
-          float2 v = red[((long long)n * splits + k) * C + c];
-          S1 += v.x; S2 += v.y;
-        }
-        double g = weight[c];
-        g1 += g * S1;
-        g2 += g * (S2 - mean * S1);
-      }
-      g1 = block_sum_d(g1, sm);
-      g2 = block_sum_d(g2, sm);
-      const double inv = coef[(long long)n * C].w;
-      const double sd = 1.0 / inv - (double)eps;
-      const double K = sd > 0 ? g2 * inv * inv / ((M - 1.0) * sd) : 0.0;
-      const double b = -K;
-      const double cc = -g1 * inv / M + K * mean;
-      for (int c = threadIdx.x; c < C; c += blockDim.x)
-        bco[(long long)n * C + c] = make_float4((float)(weight[c] * inv), (float)b, (float)cc, 0.f);
-    }
-    // parameter gradients (accumulated)
+    const int n = blockIdx.x;
+    double g1 = 0, g2 = 0;
+    const double mean = coef[(long long)n * C].z;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      double dg = 0, db = 0;
-      for (int n = 0; n < N; ++n) {
-        double S1 = 0, S2 = 0;
-        for (int k = 0; k < splits; ++k) {
-          float2 v = red[((long long)n * splits + k) * C + c];
-          S1 += v.x; S2 += v.y;
-        }
-        float4 q = coef[(long long)n * C + c];
-        dg += (double)q.w * (S2 - (double)q.z * S1);
-        db += S1;
+      double S1 = 0, S2 = 0;
+      for (int k = 0; k < splits; ++k) {
+        float2 v = red[((long long)n * splits + k) * C + c];
+        S1 += v.x; S2 += v.y;
       }
-      dweight[c] += (float)dg;
-      dbias[c] += (float)db;
+      double g = weight[c];
+      g1 += g * S1;
+      g2 += g * (S2 - mean * S1);
     }
+    g1 = block_sum_d(g1, sm);
+    g2 = block_sum_d(g2, sm);
+    const double inv = coef[(long long)n * C].w;
+    const double sd = 1.0 / inv - (double)eps;
+    const double K = sd > 0 ? g2 * inv * inv / ((M - 1.0) * sd) : 0.0;
+    const double b = -K;
+    const double cc = -g1 * inv / M + K * mean;
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      bco[(long long)n * C + c] = make_float4((float)(weight[c] * inv), (float)b, (float)cc, 0.f);
   }
+}
+
+// LayerNorm parameter gradients (accumulated): one thread per channel, fixed summation order over samples / splits
+__global__ void ln_param_grad_kernel(const float2* __restrict__ red, int splits, const float4* __restrict__ coef, int N,
+                                     int C, float* __restrict__ dweight, float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double dg = 0, db = 0;
+  for (int n = 0; n < N; ++n) {
+    double S1 = 0, S2 = 0;
+    for (int k = 0; k < splits; ++k) {
+      float2 v = red[((long long)n * splits + k) * C + c];
+      S1 += v.x; S2 += v.y;
+    }
+    float4 q = coef[(long long)n * C + c];
+    dg += (double)q.w * (S2 - (double)q.z * S1);
+    db += S1;
+  }
+  dweight[c] += (float)dg;
+  dbias[c] += (float)db;
 }
 
 extern "C" int dwc_norm_bwd_finalize(int kind, const float* red, int splits, const float* coef, int n, int c, int hw,
                                      float eps, const float* weight, float* dweight, float* dbias, float* bco,
                                      dwc_stream_t stream) {
   DWC_CHECK(kind >= 1 && kind <= 3, "dwc_norm_bwd_finalize: bad kind");
-  norm_bwd_finalize_kernel<<<kind == 3 ? 1 : n, 256, 0, as_stream(stream)>>>(
+  norm_bwd_finalize_kernel<<<n, 256, 0, as_stream(stream)>>>(
       kind, reinterpret_cast<const float2*>(red), splits, reinterpret_cast<const float4*>(coef), n, c, hw, eps, weight,
       dweight, dbias, reinterpret_cast<float4*>(bco));
   DWC_LAUNCH_CHECK();
+  if (kind == 3) {
+    ln_param_grad_kernel<<<cdiv(c, 64), 64, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(red), splits,
+                                                                   reinterpret_cast<const float4*>(coef), n, c, dweight,
+                                                                   dbias);
+    DWC_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -385,6 +371,243 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// bf16 fast paths of the HBM-bound passes.  One thread owns one 8-channel group of a sample for the whole launch
+// (coefficients in registers) and works on PF pixels at a time: all 16-byte loads of the batch are issued before the
+// first use, which is what keeps enough bytes in flight to approach the HBM roofline (a single load per loop
+// iteration leaves the memory system latency-bound at ~1.5 TB/s).
+// ---------------------------------------------------------------------------------------------------
+constexpr int PF = 4;
+
+__device__ __forceinline__ uint4 ld16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bool has_reflection(int i, int size, int halo) {
+  return halo > 0 && ((i >= 1 && i <= halo) || (i >= size - 1 - halo && i <= size - 2));
+}
+
+__global__ void __launch_bounds__(256)
+    post_fwd_fast_kernel(HB y, const float4* __restrict__ coef, int act, HB res, int has_res, HB out) {
+  const int cvs = out.c >> 3;
+  const int cv = threadIdx.x % cvs, pl = threadIdx.x / cvs, PL = 256 / cvs;
+  const int n = blockIdx.y, c0 = cv * 8;
+  const bf16* yb = reinterpret_cast<const bf16*>(y.ptr);
+  const bf16* rb = reinterpret_cast<const bf16*>(res.ptr);
+  bf16* ob = reinterpret_cast<bf16*>(out.ptr);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (coef) {
+      const float4 q = coef[(long long)n * out.c + c0 + e];
+      sc[e] = q.x; sh[e] = q.y;
+    } else { sc[e] = 1.f; sh[e] = 0.f; }
+  }
+  const int npix = out.hp * out.wp;
+  const int stride = gridDim.x * PL;
+  for (int p0 = blockIdx.x * PL + pl; p0 < npix; p0 += PF * stride) {
+    uint4 vy[PF], vr[PF];
+    long long oo[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int p = p0 + u * stride;
+      oo[u] = -1;
+      if (p < npix) {
+        const int Y = p / out.wp, X = p - Y * out.wp;
+        const int iy = reflect_idx(Y - out.halo, out.h), ix = reflect_idx(X - out.halo, out.w);
+        vy[u] = ld16(yb + y.off(n, iy, ix) + c0);
+        if (has_res) vr[u] = ld16(rb + res.off(n, iy, ix) + c0);
+        oo[u] = out.off_padded(n, Y, X) + c0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      if (oo[u] < 0) continue;
+      float v[8];
+      unpack8(vy[u], v);
+      if (coef) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = act_fwd(sc[e] * v[e] + sh[e], act);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = act_fwd(v[e], act);
+      }
+      if (has_res) {
+        float rr[8];
+        unpack8(vr[u], rr);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += rr[e];
+      }
+      Vec8<bf16>::store(ob + oo[u], v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    post_bwd_apply_fast_kernel(HB dout, HB y, const float4* __restrict__ coef, const float4* __restrict__ bco, int act,
+                               HB dy, HB dres, int has_dres) {
+  const int hmax = max(dy.halo, has_dres ? dres.halo : 0);
+  const int HP = y.h + 2 * hmax, WP = y.w + 2 * hmax;
+  const int cvs = y.c >> 3;
+  const int cv = threadIdx.x % cvs, pl = threadIdx.x / cvs, PL = 256 / cvs;
+  const int n = blockIdx.y, c0 = cv * 8;
+  const bf16* yb = reinterpret_cast<const bf16*>(y.ptr);
+  const bf16* db = reinterpret_cast<const bf16*>(dout.ptr);
+  bf16* dyb = reinterpret_cast<bf16*>(dy.ptr);
+  bf16* drb = reinterpret_cast<bf16*>(dres.ptr);
+  float sc[8], sh[8], ba[8], bb[8], bc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (coef) {
+      const float4 q = coef[(long long)n * y.c + c0 + e];
+      sc[e] = q.x; sh[e] = q.y;
+    } else { sc[e] = 1.f; sh[e] = 0.f; }
+    if (bco) {
+      const float4 q = bco[(long long)n * y.c + c0 + e];
+      ba[e] = q.x; bb[e] = q.y; bc[e] = q.z;
+    } else { ba[e] = 1.f; bb[e] = 0.f; bc[e] = 0.f; }
+  }
+  const int npix = HP * WP;
+  const int stride = gridDim.x * PL;
+  for (int p0 = blockIdx.x * PL + pl; p0 < npix; p0 += PF * stride) {
+    uint4 vy[PF], vd[PF];
+    int iys[PF], ixs[PF], kind[PF];          // kind: 0 skip, 1 outside the interior, 2 interior, 3 interior + reflections
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int p = p0 + u * stride;
+      kind[u] = 0;
+      if (p < npix) {
+        const int Y = p / WP, X = p - Y * WP;
+        const int iy = Y - hmax, ix = X - hmax;
+        iys[u] = iy; ixs[u] = ix;
+        kind[u] = 1;
+        if (iy >= 0 && iy < y.h && ix >= 0 && ix < y.w) {
+          vy[u] = ld16(yb + y.off(n, iy, ix) + c0);
+          if (has_reflection(iy, dout.h, dout.refl) || has_reflection(ix, dout.w, dout.refl)) {
+            kind[u] = 3;
+          } else {
+            kind[u] = 2;
+            vd[u] = ld16(db + dout.off(n, iy, ix) + c0);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      if (kind[u] == 0) continue;
+      const int iy = iys[u], ix = ixs[u];
+      float g[8], o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = o[e] = 0.f;
+      if (kind[u] >= 2) {
+        if (kind[u] == 3) fold_read8<bf16>(dout, n, iy, ix, c0, g);
+        else unpack8(vd[u], g);
+        float v[8];
+        unpack8(vy[u], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float z = coef ? sc[e] * v[e] + sh[e] : v[e];
+          const float dz = g[e] * act_grad(z, act);
+          o[e] = bco ? ba[e] * dz + bb[e] * v[e] + bc[e] : dz;
+        }
+      }
+      {
+        const int py = iy + dy.halo, px = ix + dy.halo;
+        if (py >= 0 && py < dy.hp && px >= 0 && px < dy.wp) Vec8<bf16>::store(dyb + dy.off_padded(n, py, px) + c0, o);
+      }
+      if (has_dres) {
+        const int py = iy + dres.halo, px = ix + dres.halo;
+        if (py >= 0 && py < dres.hp && px >= 0 && px < dres.wp)
+          Vec8<bf16>::store(drb + dres.off_padded(n, py, px) + c0, g);
+      }
+    }
+  }
+}
+
+// per-(n,c) sums, bf16.  grid (C/32, splits, N); block 256 = 4 channel-vectors x 64 pixel lanes, PF pixels per batch.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    nc_reduce_fast_kernel(HB y, HB dout, const float4* __restrict__ coef, int act, int splits, float2* __restrict__ out) {
+  __shared__ float s0[64][33], s1[64][33];
+  const int cv = threadIdx.x & 3, pl = threadIdx.x >> 2;
+  const int c0 = blockIdx.x * 32 + cv * 8;
+  const int split = blockIdx.y, n = blockIdx.z;
+  const int hw = y.h * y.w;
+  const int per = (hw + splits - 1) / splits;
+  const int p_begin = split * per, p_end = min(hw, p_begin + per);
+  const bf16* yb = reinterpret_cast<const bf16*>(y.ptr);
+  const bf16* db = reinterpret_cast<const bf16*>(dout.ptr);
+  float a0[8], a1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a0[e] = a1[e] = 0.f;
+  float sc[8], sh[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (coef && c0 < y.c) {
+        float4 q = coef[(long long)n * y.c + c0 + e];
+        sc[e] = q.x; sh[e] = q.y;
+      } else { sc[e] = 1.f; sh[e] = 0.f; }
+    }
+  }
+  if (c0 < y.c) {
+    for (int pb = p_begin + pl; pb < p_end; pb += 64 * PF) {
+      uint4 vy[PF], vd[PF];
+      int kind[PF], pys[PF], pxs[PF];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int p = pb + u * 64;
+        kind[u] = 0;
+        if (p < p_end) {
+          const int py = p / y.w, px = p - py * y.w;
+          pys[u] = py; pxs[u] = px;
+          vy[u] = ld16(yb + y.off(n, py, px) + c0);
+          kind[u] = 2;
+          if (MODE == 1) {
+            if (has_reflection(py, dout.h, dout.refl) || has_reflection(px, dout.w, dout.refl)) kind[u] = 3;
+            else vd[u] = ld16(db + dout.off(n, py, px) + c0);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        if (kind[u] == 0) continue;
+        float v[8];
+        unpack8(vy[u], v);
+        if (MODE == 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { a0[e] += v[e]; a1[e] += v[e] * v[e]; }
+        } else {
+          float g[8];
+          if (kind[u] == 3) fold_read8<bf16>(dout, n, pys[u], pxs[u], c0, g);
+          else unpack8(vd[u], g);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float dz = g[e] * act_grad(sc[e] * v[e] + sh[e], act);
+            a0[e] += dz; a1[e] += dz * v[e];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s0[pl][cv * 8 + e] = a0[e]; s1[pl][cv * 8 + e] = a1[e]; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int i = 0; i < 64; ++i) { t0 += s0[i][threadIdx.x]; t1 += s1[i][threadIdx.x]; }
+    int c = blockIdx.x * 32 + threadIdx.x;
+    if (c < y.c) out[((long long)n * splits + split) * y.c + c] = make_float2(t0, t1);
+  }
+}
+
+
 // grid for the per-sample kernels: enough blocks per sample to fill the GPU ~8 CTAs deep
 static inline dim3 ps_grid(int npix, int cvs, int n) {
   const int PL = 256 / cvs;
@@ -412,8 +635,12 @@ extern "C" int dwc_post_fwd(const dwc_hbuf_t* y, const float* coef, int act, con
   HB hy(*y), ho(*out), hr = res ? HB(*res) : HB(*y);
   long long total = ho.padded_pixels() * (out->c / 8);
   if (ps_ok(out->c)) {
-    DISPATCH_T(y->dtype, (post_fwd_ps_kernel<T><<<ps_grid(ho.hp * ho.wp, out->c / 8, out->n), 256, 0, as_stream(stream)>>>(
-                             hy, reinterpret_cast<const float4*>(coef), act, hr, res != nullptr, ho)));
+    if (y->dtype == DWC_BF16)
+      post_fwd_fast_kernel<<<ps_grid(ho.hp * ho.wp, out->c / 8, out->n), 256, 0, as_stream(stream)>>>(
+          hy, reinterpret_cast<const float4*>(coef), act, hr, res != nullptr, ho);
+    else
+      post_fwd_ps_kernel<float><<<ps_grid(ho.hp * ho.wp, out->c / 8, out->n), 256, 0, as_stream(stream)>>>(
+          hy, reinterpret_cast<const float4*>(coef), act, hr, res != nullptr, ho);
   } else {
     DISPATCH_T(y->dtype, (post_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
                              hy, reinterpret_cast<const float4*>(coef), act, hr, res != nullptr, ho)));
@@ -536,24 +763,76 @@ __global__ void __launch_bounds__(256)
 }
 
 extern "C" int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, const float* bco,
-                                  int act, const dwc_hbuf_t* dy, const dwc_hbuf_t* dres, dwc_stream_t stream) {
+                                  int act, const dwc_hbuf_t* dy, const dwc_hbuf_t* dres, int prefolded,
+                                  dwc_stream_t stream) {
   DWC_CHECK(y->c % 8 == 0 && y->layout == 0 && dy->layout == 0, "dwc_post_bwd_apply: needs C %% 8 == 0, plain y/dy");
   DWC_CHECK(dout->n == y->n && dout->h == y->h && dout->w == y->w && dout->c == y->c, "dwc_post_bwd_apply: geometry mismatch");
   HB hd(*dout), hy(*y), hdy(*dy), hr = dres ? HB(*dres) : HB(*dy);
+  if (prefolded) hd.refl = 0;
   int hmax = dy->halo;
   if (dres && dres->halo > hmax) hmax = dres->halo;
   long long total = (long long)y->n * (y->h + 2 * hmax) * (y->w + 2 * hmax) * (y->c / 8);
   if (ps_ok(y->c)) {
-    DISPATCH_T(y->dtype,
-               (post_bwd_apply_ps_kernel<T><<<ps_grid((y->h + 2 * hmax) * (y->w + 2 * hmax), y->c / 8, y->n), 256, 0,
-                                              as_stream(stream)>>>(hd, hy, reinterpret_cast<const float4*>(coef),
+    const dim3 g = ps_grid((y->h + 2 * hmax) * (y->w + 2 * hmax), y->c / 8, y->n);
+    if (y->dtype == DWC_BF16)
+      post_bwd_apply_fast_kernel<<<g, 256, 0, as_stream(stream)>>>(hd, hy, reinterpret_cast<const float4*>(coef),
                                                                    reinterpret_cast<const float4*>(bco), act, hdy, hr,
-                                                                   dres != nullptr)));
+                                                                   dres != nullptr);
+    else
+      post_bwd_apply_ps_kernel<float><<<g, 256, 0, as_stream(stream)>>>(hd, hy, reinterpret_cast<const float4*>(coef),
+                                                                        reinterpret_cast<const float4*>(bco), act, hdy,
+                                                                        hr, dres != nullptr);
   } else {
     DISPATCH_T(y->dtype, (post_bwd_apply_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
                              hd, hy, reinterpret_cast<const float4*>(coef), reinterpret_cast<const float4*>(bco), act,
                              hdy, hr, dres != nullptr)));
   }
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// In-place fold of a reflect halo's gradient into the interior: interior pixels whose mirror images lie in the halo
+// (a band of `halo` rows / columns next to each edge) take the sum of their reflections.  Only those band pixels are
+// visited; afterwards the backward passes stream the interior without any gather (refl = 0).
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) fold_halo_kernel(HB d) {
+  const int cvs = d.c >> 3;
+  const int nb = 2 * d.halo;                       // band rows (and band columns)
+  const int row_part = nb * d.w, col_part = (d.h - nb) * nb;
+  const long long total = (long long)d.n * (row_part + col_part) * cvs;
+  T* base = reinterpret_cast<T*>(d.ptr);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvs);
+    long long r = i / cvs;
+    const int j = (int)(r % (row_part + col_part));
+    const int n = (int)(r / (row_part + col_part));
+    int y, x;
+    if (j < row_part) {
+      const int rr = j / d.w;
+      x = j - rr * d.w;
+      y = rr < d.halo ? 1 + rr : (d.h - 1 - d.halo) + (rr - d.halo);
+    } else {
+      const int jj = j - row_part;
+      const int k = jj / nb, cc = jj - k * nb;
+      y = k == 0 ? 0 : (k == d.h - nb - 1 ? d.h - 1 : d.halo + k);
+      x = cc < d.halo ? 1 + cc : (d.w - 1 - d.halo) + (cc - d.halo);
+    }
+    float g[8];
+    fold_read8<T>(d, n, y, x, cv * 8, g);
+    Vec8<T>::store(base + d.off(n, y, x) + cv * 8, g);
+  }
+}
+
+extern "C" int dwc_fold_halo(const dwc_hbuf_t* d, dwc_stream_t stream) {
+  DWC_CHECK(d->c % 8 == 0, "dwc_fold_halo: needs C %% 8 == 0");
+  DWC_CHECK(d->halo > 0 && d->h >= 2 * d->halo + 2 && d->w >= 2 * d->halo + 2,
+            "dwc_fold_halo: image %dx%d too small for halo %d", d->h, d->w, d->halo);
+  HB hd(*d);
+  const int nb = 2 * d->halo;
+  long long total = (long long)d->n * (nb * d->w + (d->h - nb) * nb) * (d->c / 8);
+  DISPATCH_T(d->dtype, (fold_halo_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(hd)));
   DWC_LAUNCH_CHECK();
   return 0;
 }
@@ -651,10 +930,11 @@ extern "C" int dwc_upsample_pad_fwd(const dwc_hbuf_t* x, const dwc_hbuf_t* out, 
   DWC_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int dwc_upsample_pad_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* dx, dwc_stream_t stream) {
+extern "C" int dwc_upsample_pad_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* dx, int prefolded, dwc_stream_t stream) {
   DWC_CHECK(dx->c % 8 == 0 && dout->h == 2 * dx->h && dout->w == 2 * dx->w && dout->c == dx->c && dout->n == dx->n,
             "dwc_upsample_pad_bwd: geometry mismatch");
   HB hd(*dout), hx(*dx);
+  if (prefolded) hd.refl = 0;
   long long total = hx.padded_pixels() * (dx->c / 8);
   DISPATCH_T(dx->dtype, (upsample_pad_bwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(hd, hx)));
   DWC_LAUNCH_CHECK();
@@ -1015,3 +1295,39 @@ extern "C" int dwc_heads_bwd_rows(const float* dimg, const float* datt, const fl
   DWC_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// per-(n,c) reduction entry points
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dwc_nc_stats(const dwc_hbuf_t* y, int splits, float* stats, dwc_stream_t stream) {
+  DWC_CHECK(y->c % 8 == 0 && y->layout == 0, "dwc_nc_stats: needs C %% 8 == 0 and plain layout");
+  HB hy(*y);
+  dim3 grid(cdiv(y->c, 32), splits, y->n);
+  if (y->dtype == DWC_BF16)
+    nc_reduce_fast_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(hy, hy, nullptr, 0, splits,
+                                                                  reinterpret_cast<float2*>(stats));
+  else
+    nc_reduce_kernel<float, 0><<<grid, 256, 0, as_stream(stream)>>>(hy, hy, nullptr, 0, splits,
+                                                                    reinterpret_cast<float2*>(stats));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dwc_post_bwd_reduce(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, int act, int splits,
+                                   float* red, int prefolded, dwc_stream_t stream) {
+  DWC_CHECK(y->c % 8 == 0 && y->layout == 0, "dwc_post_bwd_reduce: needs C %% 8 == 0 and plain y");
+  DWC_CHECK(dout->n == y->n && dout->h == y->h && dout->w == y->w && dout->c == y->c && dout->dtype == y->dtype,
+            "dwc_post_bwd_reduce: geometry mismatch");
+  HB hy(*y), hd(*dout);
+  if (prefolded) hd.refl = 0;
+  dim3 grid(cdiv(y->c, 32), splits, y->n);
+  if (y->dtype == DWC_BF16)
+    nc_reduce_fast_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(hy, hd, reinterpret_cast<const float4*>(coef), act,
+                                                                  splits, reinterpret_cast<float2*>(red));
+  else
+    nc_reduce_kernel<float, 1><<<grid, 256, 0, as_stream(stream)>>>(hy, hd, reinterpret_cast<const float4*>(coef), act,
+                                                                    splits, reinterpret_cast<float2*>(red));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+

@@ -5,57 +5,7 @@
 //                        fp32 accumulator lives in TMEM, the epilogue reads it back with tcgen05.ld.
 //  * gconv_simt_kernel : CUDA-core version of the same abstract operation (fp32 validation mode, the
 //                        3-channel image layers and the 4-channel head gradients).
-#include "common.cuh"
-
-struct GConvDev {
-  const void* a;
-  const void* w;
-  const float* bias;
-  void* out;
-  long long a_dim[5];
-  long long a_str[5];
-  long long o_str[3];
-  int box_x, box_y, box_n;
-  int tiles_x, tiles_y, tiles_n;
-  int valid_x, valid_y, valid_n;
-  int flat, flat_img, flat_pitch, flat_h, flat_w;
-  int ntaps, C, K, ncols, ncols_padded;
-  int out_dtype, accumulate;
-  int taps[DWC_MAX_TAPS][3];
-};
-
-struct RowCoord {
-  int x, y, n;
-};
-
-__device__ __forceinline__ RowCoord tile_row(const GConvDev& p, int tile, int r) {
-  int tx = tile % p.tiles_x;
-  int t2 = tile / p.tiles_x;
-  int ty = t2 % p.tiles_y;
-  int tn = t2 / p.tiles_y;
-  RowCoord rc;
-  rc.x = tx * p.box_x + r % p.box_x;
-  int r2 = r / p.box_x;
-  rc.y = ty * p.box_y + r2 % p.box_y;
-  rc.n = tn * p.box_n + r2 / p.box_y;
-  return rc;
-}
-
-// where (and whether) a row is stored
-__device__ __forceinline__ bool out_offset(const GConvDev& p, const RowCoord& rc, long long* off) {
-  if (p.flat) {
-    int n = rc.x / p.flat_img;
-    int rem = rc.x - n * p.flat_img;
-    int yy = rem / p.flat_pitch;
-    int xx = rem - yy * p.flat_pitch;
-    if (n >= p.valid_n || yy >= p.flat_h || xx >= p.flat_w) return false;
-    *off = (long long)n * p.o_str[2] + (long long)yy * p.o_str[1] + (long long)xx * p.o_str[0];
-    return true;
-  }
-  if (rc.x >= p.valid_x || rc.y >= p.valid_y || rc.n >= p.valid_n) return false;
-  *off = (long long)rc.n * p.o_str[2] + (long long)rc.y * p.o_str[1] + (long long)rc.x * p.o_str[0];
-  return true;
-}
+#include "gconv.cuh"
 
 // =====================================================================================================
 // SIMT kernel: 128 x 64 tile, 256 threads, each thread 8 rows x 4 columns, fp32 accumulate
@@ -342,6 +292,7 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
   DWC_CHECK(g != nullptr, "dwc_gconv: null params");
   DWC_CHECK(g->ntaps > 0 && g->ntaps <= DWC_MAX_TAPS, "dwc_gconv: ntaps %d out of range", g->ntaps);
   DWC_CHECK(g->box[0] * g->box[1] * g->box[2] == 128, "dwc_gconv: box must cover 128 rows");
+  const bool halo = g->backend == DWC_TC_HALO || g->backend == DWC_TC_HALO1;
   DWC_CHECK(g->a_str[0] == 1, "dwc_gconv: channel stride must be 1");
   GConvDev d;
   memset(&d, 0, sizeof(d));
@@ -361,9 +312,15 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
   const long long ntiles = (long long)d.tiles_x * d.tiles_y * d.tiles_n;
   DWC_CHECK(ntiles > 0 && ntiles < 2147483647LL, "dwc_gconv: bad tile count");
 
-  if (g->backend == DWC_TC) {
+  if (g->backend == DWC_TC || halo) {
     DWC_CHECK(g->dtype == DWC_BF16, "dwc_gconv: tcgen05 backend needs bf16 operands");
     DWC_CHECK(d.C % TC_BK == 0, "dwc_gconv: tcgen05 backend needs C %% 64 == 0 (C=%d)", d.C);
+    if (halo) {
+      int ks = 1;
+      while (ks * ks < g->ntaps) ++ks;
+      DWC_CHECK(ks * ks == g->ntaps, "dwc_gconv(halo): ntaps %d is not a square window", g->ntaps);
+      return dwc_launch_gconv_halo(g, d, ks, st);
+    }
     const int np = g->ncols_padded;
     if (np % 256 == 0) return launch_tc<256>(g, d, st);
     if (np % 128 == 0) return launch_tc<128>(g, d, st);

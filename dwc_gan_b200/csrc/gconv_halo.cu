@@ -1,0 +1,316 @@
+// gconv_halo: stride-1 k x k convolution (forward over the reflect-haloed input, data gradient over the zero-haloed
+// output gradient) as a tcgen05 implicit GEMM that stages each INPUT pixel once per channel slab.
+//
+//  tile      : 8 (x) x 16 (y) output pixels of one image = the 128 rows of the UMMA accumulator;
+//  A operand : per 64-channel slab ONE TMA box of 16 x (15+k) input pixels lands in shared memory as
+//              [row][16 px][64 ch] (2 KB per image row, 128-byte swizzle).  The A tile of filter tap (dy, dx) is the
+//              same buffer viewed through a UMMA descriptor whose start address is advanced by (dy*16 + dx) pixels
+//              with an 8-row-group stride (SBO) of one image row: k*k taps re-read shared memory, not L2
+//              (the tap-by-tap kernel in gconv.cu re-fetches the 128-pixel tile from L2 for every tap);
+//  B operand : [BN][64] weight tile per (tap, slab) through an mbarrier ring; in a 2-CTA cluster each CTA fetches
+//              half of the tile and TMA-multicasts it to both, halving the weight traffic per SM;
+//  roles     : warp 0 weight producer, warp 1 MMA issuer, warp 2 lane 0 input producer, warps 2-5 epilogue
+//              (tcgen05.ld -> +bias -> bf16/fp32 store).
+#include "gconv.cuh"
+
+namespace {
+
+constexpr int HT_THREADS = 192;
+constexpr int HT_BK = 64;
+constexpr int HT_NA = 2;          // input-tile stages
+
+template <int BN> struct HaloCfg {
+  static constexpr int B_BYTES = BN * HT_BK * 2;
+  static constexpr int B_BYTES_AL = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int NB = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
+      "{%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// K-major SW128 descriptor with an explicit 8-row-group stride.  The start address may be any multiple of 128 bytes
+// inside the TMA-written buffer: the hardware applies the 128B swizzle to the absolute shared-memory address bits
+// (measured on B200: a pixel-shifted start with matrix-base-offset 0 reads exactly the rows TMA wrote; setting the
+// base-offset field to the row phase does NOT - tests/diag_halo.py), so a shifted window needs no re-staging.
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(16 >> 4) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN, int CL>
+__global__ void __launch_bounds__(HT_THREADS)
+    gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ GConvDev p, const int ksize) {
+  using Cfg = HaloCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_stage = (15 + ksize) * 2048;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + HT_NA * a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + Cfg::NB * Cfg::B_BYTES_AL);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + HT_NA;
+  uint64_t* b_full = bars + 2 * HT_NA;
+  uint64_t* b_empty = b_full + Cfg::NB;
+  uint64_t* tmem_full = b_empty + Cfg::NB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int col0 = blockIdx.y * BN;
+  const int cblocks = p.C / HT_BK;
+  const int ntaps = ksize * ksize;
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+
+  int tx = tile % p.tiles_x;
+  int t2 = tile / p.tiles_x;
+  const int x0 = tx * 8, y0 = (t2 % p.tiles_y) * 16, n0 = t2 / p.tiles_y;   // n0 >= N for the padding CTA of a cluster
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < HT_NA; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < Cfg::NB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], CL);      // every CTA of the cluster must have consumed the slot
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();          // peer barriers are initialised before any multicast can reach them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= weight producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int cb = 0; cb < cblocks; ++cb) {
+        for (int t = 0; t < ntaps; ++t) {
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          mbar_expect_tx(&b_full[stage], Cfg::B_BYTES);
+          uint8_t* dst = sB + stage * Cfg::B_BYTES_AL;
+          if (CL == 1) {
+            tma_load_2d(dst, &tmB, &b_full[stage], t * p.C + cb * HT_BK, col0);
+          } else {
+            tma_load_2d_mc(dst + rank * (Cfg::B_BYTES / CL), &tmB, &b_full[stage], t * p.C + cb * HT_BK,
+                           col0 + rank * (BN / CL), (uint16_t)((1u << CL) - 1));
+          }
+          if (++stage == Cfg::NB) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN < 16 ? 16 : BN, 0, 0);
+      int bs = 0, as = 0;
+      uint32_t bphase = 0, aphase = 0;
+      uint32_t any = 0;
+      for (int cb = 0; cb < cblocks; ++cb) {
+        mbar_wait(&a_full[as], aphase);
+        const uint32_t a_base = smem_u32(sA + as * a_stage);
+        for (int t = 0; t < ntaps; ++t) {
+          mbar_wait(&b_full[bs], bphase);
+          tc_fence_after();
+          const int dy = t / ksize, dx = t - dy * ksize;
+          const uint32_t a_addr = a_base + (uint32_t)(dy * 16 + dx) * 128u;
+          const uint32_t b_addr = smem_u32(sB + bs * Cfg::B_BYTES_AL);
+#pragma unroll
+          for (int k = 0; k < HT_BK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128_sbo(a_addr + k * 32, 2048);
+            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_base, da, db, idesc, any);
+            any = 1;
+          }
+          if (CL == 1) umma_commit(&b_empty[bs]);
+          else umma_commit_mc(&b_empty[bs], (uint16_t)((1u << CL) - 1));
+          if (++bs == Cfg::NB) {
+            bs = 0;
+            bphase ^= 1;
+          }
+        }
+        umma_commit(&a_empty[as]);
+        if (++as == HT_NA) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    if (warp == 2 && lane == 0) {
+      // ================= input-tile producer =================
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int cb = 0; cb < cblocks; ++cb) {
+        mbar_wait(&a_empty[as], aphase ^ 1);
+        mbar_expect_tx(&a_full[as], (uint32_t)a_stage);
+        tma_load_5d(sA + as * a_stage, &tmA, &a_full[as], cb * HT_BK, x0, y0, 0, n0);
+        if (++as == HT_NA) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+    // ================= epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    RowCoord rc;
+    rc.x = x0 + (r & 7);
+    rc.y = y0 + (r >> 3);
+    rc.n = n0;
+    long long off = 0;
+    const bool valid = out_offset(p, rc, &off);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    constexpr int CHUNK = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+    for (int cc = 0; cc < BN; cc += CHUNK) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
+      if (CHUNK == 32) tmem_ld32(taddr, v);
+      else tmem_ld16(taddr, v);
+      tmem_ld_wait();
+      if (valid) {
+        const int cbase = col0 + cc;
+        if (p.out_dtype == DWC_BF16) {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + off + cbase;
+          if (cbase + CHUNK <= p.ncols && (p.ncols & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; j += 8) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + (p.bias ? __ldg(p.bias + cbase + j + e) : 0.f);
+              if (p.accumulate) {
+                float old[8];
+                Vec8<bf16>::load(o + j, old);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += old[e];
+              }
+              Vec8<bf16>::store(o + j, f);
+            }
+          } else {
+            for (int j = 0; j < CHUNK; ++j) {
+              if (cbase + j < p.ncols) {
+                float f = __uint_as_float(v[j]) + (p.bias ? p.bias[cbase + j] : 0.f);
+                if (p.accumulate) f += __bfloat162float(o[j]);
+                o[j] = __float2bfloat16_rn(f);
+              }
+            }
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + off + cbase;
+          for (int j = 0; j < CHUNK; ++j) {
+            if (cbase + j < p.ncols) {
+              float f = __uint_as_float(v[j]) + (p.bias ? p.bias[cbase + j] : 0.f);
+              if (p.accumulate) f += o[j];
+              o[j] = f;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer may still signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int CL>
+int launch_halo(const dwc_gconv_t* g, const GConvDev& d, int ksize, cudaStream_t st) {
+  using Cfg = HaloCfg<BN>;
+  CUtensorMap tmA, tmB;
+  if (dwc_make_tmap5(&tmA, g->a, g->a_dim, g->a_str, 16, 15 + ksize, 1, 1)) return 1;
+  if (dwc_make_tmap2(&tmB, g->w, g->ncols_padded, d.K, d.K, BN / CL, HT_BK)) return 1;
+  const int a_stage = (15 + ksize) * 2048;
+  const int smem = HT_NA * a_stage + Cfg::NB * Cfg::B_BYTES_AL + 1024 + 256;
+  DWC_CHECK(smem <= 227 * 1024, "dwc_gconv(halo): shared memory %d exceeds the SM", smem);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    DWC_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (CL > 1) DWC_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<BN, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr_smem = smem;
+  }
+  const int ntiles = d.tiles_x * d.tiles_y * d.tiles_n;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((ntiles + CL - 1) / CL * CL, cdiv(g->ncols_padded, BN), 1);
+  cfg.blockDim = dim3(HT_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DWC_CUDA(cudaLaunchKernelEx(&cfg, gconv_halo_kernel<BN, CL>, tmA, tmB, d, ksize));
+  return 0;
+}
+
+template <int BN>
+int launch_halo_cl(const dwc_gconv_t* g, const GConvDev& d, int ksize, int cl, cudaStream_t st) {
+  return cl == 2 ? launch_halo<BN, 2>(g, d, ksize, st) : launch_halo<BN, 1>(g, d, ksize, st);
+}
+
+}  // namespace
+
+int dwc_launch_gconv_halo(const dwc_gconv_t* g, const GConvDev& d, int ksize, cudaStream_t st) {
+  DWC_CHECK(ksize >= 1 && ksize <= 9, "dwc_gconv(halo): window %d out of range", ksize);
+  DWC_CHECK(g->box[0] == 8 && g->box[1] == 16 && g->box[2] == 1, "dwc_gconv(halo): tile must be 8 x 16 x 1");
+  DWC_CHECK(!g->flat, "dwc_gconv(halo): flat addressing is not supported");
+  for (int t = 0; t < g->ntaps; ++t)
+    DWC_CHECK(g->taps[t * 3] == t % ksize && g->taps[t * 3 + 1] == t / ksize && g->taps[t * 3 + 2] == 0,
+              "dwc_gconv(halo): taps must be the full k x k window in (ky, kx) order");
+  // cluster size: backend code DWC_TC_HALO + 1 selects the single-CTA variant (diagnostics)
+  const int cl = g->backend == DWC_TC_HALO ? 2 : 1;
+  const int np = g->ncols_padded;
+  if (np % 256 == 0) return launch_halo_cl<256>(g, d, ksize, cl, st);
+  if (np % 128 == 0) return launch_halo_cl<128>(g, d, ksize, cl, st);
+  if (np % 64 == 0) return launch_halo_cl<64>(g, d, ksize, cl, st);
+  if (np == 16) return launch_halo_cl<16>(g, d, ksize, cl, st);
+  DWC_CHECK(false, "dwc_gconv(halo): unsupported padded column count %d", np);
+}

@@ -286,15 +286,15 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
 
 // bias gradient: column sums of dY over all pixels, two deterministic stages.
 // grid (ceil(C/32), DB_SPLITS); block 256 = 4 channel-vectors (8 channels each) x 64 pixel lanes; 16-byte loads.
-constexpr int DB_SPLITS = 32;
+constexpr int DB_SPLITS = 256;        // maximum; the launch picks enough splits to fill the GPU
 template <typename T>
 __global__ void __launch_bounds__(256) dbias_partial_kernel(const T* __restrict__ A, long long sx, long long sy, long long sn,
-                                                            int W, int H, int N, float* part, int ca) {
+                                                            int W, int H, int N, float* part, int ca, int nsplit) {
   __shared__ float red[64][33];
   const int cv = threadIdx.x & 3, pl = threadIdx.x >> 2;
   const int c0 = blockIdx.x * 32 + cv * 8;
   const long long total = (long long)N * H * W;
-  const long long per = (total + DB_SPLITS - 1) / DB_SPLITS;
+  const long long per = (total + nsplit - 1) / nsplit;
   const long long p0 = blockIdx.y * per, p1 = min(total, p0 + per);
   float acc[8];
 #pragma unroll
@@ -326,11 +326,11 @@ __global__ void __launch_bounds__(256) dbias_partial_kernel(const T* __restrict_
     if (c < ca) part[(long long)blockIdx.y * ca + c] = t;
   }
 }
-__global__ void dbias_final_kernel(const float* part, int ca, float* dbias, int accumulate) {
+__global__ void dbias_final_kernel(const float* part, int ca, float* dbias, int accumulate, int nsplit) {
   int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= ca) return;
   float s = 0.f;
-  for (int k = 0; k < DB_SPLITS; ++k) s += part[(long long)k * ca + ch];
+  for (int k = 0; k < nsplit; ++k) s += part[(long long)k * ca + ch];
   dbias[ch] = accumulate ? dbias[ch] + s : s;
 }
 
@@ -462,18 +462,23 @@ extern "C" int dwc_wgrad(const dwc_wgrad_t* g, dwc_stream_t stream) {
   DWC_LAUNCH_CHECK();
   if (g->dbias) {
     float* part = g->workspace + (int64_t)pl.splits * g->ntaps * pl.cm * pl.cn;
-    dim3 grid(cdiv(g->ca, 32), DB_SPLITS);
+    const long long npix = (long long)g->a_dim[1] * g->a_dim[2] * g->a_dim[4];
+    int nsplit = cdiv(4 * dwc_num_sms(), cdiv(g->ca, 32));
+    if (nsplit > DB_SPLITS) nsplit = DB_SPLITS;
+    if (nsplit > cdiv(npix, 64)) nsplit = cdiv(npix, 64);
+    if (nsplit < 1) nsplit = 1;
+    dim3 grid(cdiv(g->ca, 32), nsplit);
     DWC_CHECK(g->ca % 8 == 0 || g->ca < 8, "dwc_wgrad: dbias needs ca %% 8 == 0");
     if (g->dtype == DWC_F32)
       dbias_partial_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(g->a), g->a_str[1], g->a_str[2],
                                                         g->a_str[4], (int)g->a_dim[1], (int)g->a_dim[2],
-                                                        (int)g->a_dim[4], part, g->ca);
+                                                        (int)g->a_dim[4], part, g->ca, nsplit);
     else
       dbias_partial_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(g->a), g->a_str[1], g->a_str[2],
                                                        g->a_str[4], (int)g->a_dim[1], (int)g->a_dim[2],
-                                                       (int)g->a_dim[4], part, g->ca);
+                                                       (int)g->a_dim[4], part, g->ca, nsplit);
     DWC_LAUNCH_CHECK();
-    dbias_final_kernel<<<cdiv(g->ca, 128), 128, 0, st>>>(part, g->ca, g->dbias, g->accumulate);
+    dbias_final_kernel<<<cdiv(g->ca, 128), 128, 0, st>>>(part, g->ca, g->dbias, g->accumulate, nsplit);
     DWC_LAUNCH_CHECK();
   }
   return 0;

@@ -343,6 +343,16 @@ def heads_conv(xp: HB, layer, on_att_grad=None):
 # --------------------------------------------------------------------------------------------
 # norm + activation + residual + reflect pad
 # --------------------------------------------------------------------------------------------
+def _prefold(d: HB) -> int:
+    """Fold the gradient of a reflect halo into the interior, in place (dwc_fold_halo); returns the `prefolded` flag
+    for the backward passes.  Tiny images keep the gathering path."""
+    if d.halo > 0 and d.h >= 2 * d.halo + 2 and d.w >= 2 * d.halo + 2 and d.c % 8 == 0:
+        ds = d.struct()
+        _call("dwc_fold_halo", C.byref(ds), L.stream())
+        return 1
+    return 0
+
+
 NORM_NONE, NORM_IN, NORM_ADAIN, NORM_LN = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 
@@ -390,11 +400,12 @@ class PostFn(torch.autograd.Function):
         dout = HB(dout_t.contiguous(), n, h, w, c, out_halo, out_layout)
         yh = HB(y_t, n, h, w, c, yhalo, 0)
         ds, ys = dout.struct(), yh.struct()
+        pre = _prefold(dout)
         bco = None
         dnw = dnb = None
         if kind != NORM_NONE:
             red = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
-            _call("dwc_post_bwd_reduce", C.byref(ds), C.byref(ys), L.ptr(coef), act, splits, L.ptr(red), L.stream())
+            _call("dwc_post_bwd_reduce", C.byref(ds), C.byref(ys), L.ptr(coef), act, splits, L.ptr(red), pre, L.stream())
             bco = torch.empty(n * c * 4, dtype=torch.float32, device=dev)
             if kind == NORM_ADAIN:
                 dnw = torch.empty(n, c, dtype=torch.float32, device=dev)
@@ -414,7 +425,7 @@ class PostFn(torch.autograd.Function):
             assert dres.layout == 0
             drs = dres.struct()
         _call("dwc_post_bwd_apply", C.byref(ds), C.byref(ys), L.ptr(coef), L.ptr(bco), act, C.byref(dys),
-              C.byref(drs) if drs is not None else None, L.stream())
+              C.byref(drs) if drs is not None else None, pre, L.stream())
         return (dy.t, dnw, dnb, dres.t if dres is not None else None, None, None, None, None, None, None, None, None,
                 None)
 
@@ -444,7 +455,8 @@ class UpsamplePadFn(torch.autograd.Function):
         dout = HB(dout_t.contiguous(), n, 2 * h, 2 * w, c, out_halo, 0)
         dx = HB.empty(n, h, w, c, halo, layout, dout_t.dtype, dout_t.device)
         ds, xs = dout.struct(), dx.struct()
-        _call("dwc_upsample_pad_bwd", C.byref(ds), C.byref(xs), L.stream())
+        pre = _prefold(dout)
+        _call("dwc_upsample_pad_bwd", C.byref(ds), C.byref(xs), pre, L.stream())
         return dx.t, None, None
 
 

@@ -11,6 +11,7 @@ The plans are plain Python objects so that tests can execute them with a CPU emu
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Tuple
 
@@ -234,12 +235,23 @@ def out_size(xp: HB, k: int, stride: int):
     return (xp.hp - k) // stride + 1, (xp.wp - k) // stride + 1
 
 
+HALO_MODE = int(os.environ.get("DWC_HALO", "0"))      # 0: tap-by-tap kernel, 1: halo tile, 2: halo tile + multicast
+
+
+def halo_backend(backend, k, stride, c):
+    """Stride-1 k x k windows on the tensor cores use the halo-tile kernel (csrc/gconv_halo.cu)."""
+    if backend == L.TC and stride == 1 and k in (3, 5, 7) and c % 64 == 0 and HALO_MODE:
+        return L.TC_HALO if HALO_MODE == 2 else L.TC_HALO1
+    return backend
+
+
 def plan_conv_fwd(xp: HB, w_packed, ncols, ncols_padded, bias, y: HB, k, stride, backend) -> GConvPlan:
     ho, wo = out_size(xp, k, stride)
     assert (y.h, y.w, y.n) == (ho, wo, xp.n) and y.layout == 0, ((y.h, y.w), (ho, wo))
     assert (stride == 1 and xp.layout == 0) or (stride == 2 and xp.layout == 1 and k == 4)
     dims, strs = input_view(xp)
-    box = choose_box(wo, ho, xp.n, 128)
+    backend = halo_backend(backend, k, stride, xp.c)
+    box = (8, 16, 1) if backend in (L.TC_HALO, L.TC_HALO1) else choose_box(wo, ho, xp.n, 128)
     tiles = (-(-wo // box[0]), -(-ho // box[1]), -(-xp.n // box[2]))
     cy = y.c
     return GConvPlan(a=xp.t, a_off=0, a_dim=dims, a_str=strs, box=box, tiles=tiles, valid=(wo, ho, xp.n),
@@ -258,7 +270,18 @@ def plan_conv_dgrad(dy: HB, w_packed, dxp: HB, k, stride, backend, cin_padded=No
     a_dim = (cout, rows, 1, 1, 1)
     a_str = (1, cout, rows * cout, rows * cout, rows * cout)
     plans = []
-    if stride == 1:
+    hb = halo_backend(backend, k, stride, cout)
+    if stride == 1 and hb != backend:
+        # full correlation of the zero-haloed gradient with the flipped filter = a valid k x k window over dy's buffer
+        assert dy.halo == k - 1 and dxp.layout == 0 and (dxp.hp, dxp.wp) == (dy.hp - k + 1, dy.wp - k + 1)
+        dims = (cout, dy.wp, dy.hp, 1, dy.n)
+        strs = (1, cout, dy.wp * cout, dy.hp * dy.wp * cout, dy.hp * dy.wp * cout)
+        plans.append(GConvPlan(a=dy.t, a_off=0, a_dim=dims, a_str=strs, box=(8, 16, 1),
+                               tiles=(-(-dxp.wp // 8), -(-dxp.hp // 16), dy.n), valid=(dxp.wp, dxp.hp, dy.n),
+                               flat=(0, 0, 0, 0, 0), taps=conv_taps(k, 1), w=w_packed, w_off=0, ncols=cin,
+                               ncols_padded=cin_padded, bias=None, out=dxp.t, out_off=0,
+                               o_str=(cin, dxp.wp * cin, dxp.hp * dxp.wp * cin), backend=hb))
+    elif stride == 1:
         assert dy.halo == k - 1 and dxp.layout == 0
         taps = [(kh * dy.wp + kw, 0, 0) for kh in range(k) for kw in range(k)]
         plans.append(GConvPlan(a=dy.t, a_off=0, a_dim=a_dim, a_str=a_str, box=(128, 1, 1), tiles=tiles,

@@ -37,6 +37,8 @@ int dwc_tc_available(void);
 #define DWC_BF16 1
 #define DWC_SIMT 0
 #define DWC_TC 1
+#define DWC_TC_HALO 2   /* gconv only: stride-1 k x k window, 8x16-pixel tiles, input staged once per slab, 2-CTA weight multicast */
+#define DWC_TC_HALO1 3  /* same, single-CTA (no cluster) variant */
 #define DWC_MAX_TAPS 64
 
 /* ------------------------------------------------------------------------------------------
@@ -142,7 +144,7 @@ int dwc_post_fwd(const dwc_hbuf_t* y, const float* coef, int act, const dwc_hbuf
 
 /* Backward, pass 1: red[(n*splits+s)*C+c] = {sum dz, sum dz*y} with dz = fold(dout) * act'(scale*y+shift). */
 int dwc_post_bwd_reduce(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, int act, int splits,
-                        float* red, dwc_stream_t stream);
+                        float* red, int prefolded, dwc_stream_t stream);
 /* Backward, pass 1b: per-(n,c) coefficients bco = {a, b, c, 0} so that dy = a*dz + b*y + c,
  * plus parameter gradients: AdaIN dweight/dbias [N,C] (overwritten), LayerNorm dgamma/dbeta [C]
  * (accumulated). */
@@ -152,11 +154,15 @@ int dwc_norm_bwd_finalize(int kind, const float* red, int splits, const float* c
 /* Backward, pass 2: dy = a*dz + b*y + c written with a ZERO halo; dres (optional, same geometry
  * as the forward `res`) = fold(dout) in the interior and zero in the halo. */
 int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, const float* bco,
-                       int act, const dwc_hbuf_t* dy, const dwc_hbuf_t* dres, dwc_stream_t stream);
+                       int act, const dwc_hbuf_t* dy, const dwc_hbuf_t* dres, int prefolded, dwc_stream_t stream);
 
 /* nn.Upsample(2, bilinear, align_corners=False) + reflect pad (networks_v2.py:154, networks.py:531). */
 int dwc_upsample_pad_fwd(const dwc_hbuf_t* x, const dwc_hbuf_t* out, dwc_stream_t stream);
-int dwc_upsample_pad_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* dx, dwc_stream_t stream);
+int dwc_upsample_pad_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* dx, int prefolded, dwc_stream_t stream);
+/* In-place backward of a reflect halo: every interior pixel whose mirror images lie in the halo receives their sum
+ * (the halo itself is left as is).  After it the three backward passes above take prefolded = 1 and stream the
+ * interior without gathering reflections.  Needs h, w >= 2*halo + 2. */
+int dwc_fold_halo(const dwc_hbuf_t* d, dwc_stream_t stream);
 
 /* NCHW float32 image -> haloed NHWC buffer, optional 2x2 average pooling first
  * (F.interpolate(0.5, bilinear) == avg_pool2d, networks.py:113) and reflect padding. */

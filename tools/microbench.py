@@ -109,37 +109,68 @@ def bench_geom(g, n, peaks):
     return rows
 
 
-def bench_post(n, c, hw, kind, peaks):
-    """norm site: stats + finalize + fused normalise/act/pad pass (forward) and reduce + finalize + apply (backward)."""
+def bench_post(n, c, hw, kind, peaks, halo_out=1, halo_dy=2):
+    """norm site through the C ABI: forward = stats + finalize + fused normalise/act/reflect-pad pass; backward =
+    reduce + finalize + apply.  Each kernel is timed on its own (graph replay over rotating buffers)."""
     import ctypes as C
     from dwc_gan_b200 import ops
+    lib = L.lib()
     bt = torch.bfloat16
-    nbuf = max(2, min(24, int(300e6 // (n * hw * hw * c * 4)) + 1))
-    ys = [HB(torch.randn(n, hw, hw, c, device="cuda").to(bt), n, hw, hw, c, 0, 0) for _ in range(nbuf)]
+    st = L.stream
+    nbuf = max(2, min(16, int(400e6 // (n * hw * hw * c * 8)) + 1))
     E = n * hw * hw * c
+    splits = ops._stats_splits(hw * hw)
+    ys = [HB(torch.randn(n, hw, hw, c, device="cuda").to(bt), n, hw, hw, c, 0, 0) for _ in range(nbuf)]
+    outs = [HB.empty(n, hw, hw, c, halo_out, 0, bt, "cuda") for _ in range(nbuf)]
+    douts = [HB(torch.randn(HB.shape_of(n, hw, hw, c, halo_out, 0), device="cuda").to(bt), n, hw, hw, c, halo_out, 0)
+             for _ in range(nbuf)]
+    dys = [HB.empty(n, hw, hw, c, halo_dy, 0, bt, "cuda") for _ in range(nbuf)]
+    stats = torch.empty(n * splits * c * 2, device="cuda")
+    red = torch.empty(n * splits * c * 2, device="cuda")
+    coef = torch.empty(n * c * 4, device="cuda")
+    bco = torch.empty(n * c * 4, device="cuda")
     nw = torch.rand(n, c, device="cuda") if kind == ops.NORM_ADAIN else torch.rand(c, device="cuda")
     nb = torch.rand(n, c, device="cuda") if kind == ops.NORM_ADAIN else torch.rand(c, device="cuda")
+    gw, gb = torch.zeros(n * c, device="cuda"), torch.zeros(n * c, device="cuda")
+    S = lambda hb: C.byref(hb.struct())
 
-    gbuf = (torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda"))
+    def f_stats(i):
+        L.check(lib.dwc_nc_stats(S(ys[i]), splits, L.ptr(stats), st()))
 
-    class _LN:
-        def grad_buffers(self):
-            return gbuf
-    outs = []
+    def f_fin(i):
+        L.check(lib.dwc_norm_finalize(kind, L.ptr(stats), splits, n, c, hw * hw, L.f32(1e-5), L.ptr(nw), L.ptr(nb),
+                                      L.ptr(coef), st()))
 
-    def fwd(y):
-        yt = y.t.detach().requires_grad_(True)
-        o = ops.PostFn.apply(yt, nw, nb, None, None, y, kind, ops.ACT_RELU, None, 1, 0, _LN(), 1e-5)
-        return yt, o
-    tf = timeit([(lambda y=y: fwd(y)) for y in ys])
-    pairs = [fwd(y) for y in ys]
-    gs = [torch.randn_like(o) for _, o in pairs]
-    # zero halo of the incoming gradient is a convention of the conv dgrad producer; content is irrelevant for timing
-    tb = timeit([(lambda pr=pr, g=g: torch.autograd.grad(pr[1], pr[0], g, retain_graph=True)) for pr, g in zip(pairs, gs)],
-                reps=2)
+    def f_post(i):
+        L.check(lib.dwc_post_fwd(S(ys[i]), L.ptr(coef), 1, None, S(outs[i]), st()))
+
+    def b_fold(i):
+        L.check(lib.dwc_fold_halo(S(douts[i]), st()))
+
+    def b_red(i):
+        L.check(lib.dwc_post_bwd_reduce(S(douts[i]), S(ys[i]), L.ptr(coef), 1, splits, L.ptr(red), 1, st()))
+
+    def b_fin(i):
+        L.check(lib.dwc_norm_bwd_finalize(kind, L.ptr(red), splits, L.ptr(coef), n, c, hw * hw, L.f32(1e-5), L.ptr(nw),
+                                          L.ptr(gw), L.ptr(gb), L.ptr(bco), st()))
+
+    def b_app(i):
+        L.check(lib.dwc_post_bwd_apply(S(douts[i]), S(ys[i]), L.ptr(coef), L.ptr(bco), 1, S(dys[i]), None, 1, st()))
+    f_stats(0); f_fin(0); b_red(0); b_fin(0)
     rows = []
-    for op, t, byts in (("norm_fwd", tf, 2 * E * 2), ("norm_bwd", tb, 3 * E * 2)):
-        rows.append(dict(layer="%s %dx%dx%d" % ({1: "IN", 2: "AdaIN", 3: "LN"}[kind], c, hw, hw), op=op, n=n, us=round(t * 1e6, 1),
+    name = "%s %dx%dx%d" % ({1: "IN", 2: "AdaIN", 3: "LN"}[kind], c, hw, hw)
+    tot = {"fwd": 0.0, "bwd": 0.0}
+    for op, fn, byts, grp in (("stats", f_stats, E * 2, "fwd"), ("finalize", f_fin, 0, "fwd"),
+                              ("post_fwd", f_post, 2 * E * 2, "fwd"), ("bwd_fold_halo", b_fold, 0, "bwd"),
+                              ("bwd_reduce", b_red, 2 * E * 2, "bwd"),
+                              ("bwd_finalize", b_fin, 0, "bwd"), ("bwd_apply", b_app, 3 * E * 2, "bwd")):
+        t = timeit([(lambda i=i: fn(i)) for i in range(nbuf)])
+        tot[grp] += t
+        rows.append(dict(layer=name, op=op, n=n, us=round(t * 1e6, 1), gbs=round(byts / t / 1e9, 1),
+                         frac_of_hbm=round(byts / t / 1e9 / peaks["hbm"], 3)))
+    for grp, byts in (("fwd", 2 * E * 2), ("bwd", 3 * E * 2)):
+        t = tot[grp]
+        rows.append(dict(layer=name, op="SITE " + grp + " (algorithmic bytes)", n=n, us=round(t * 1e6, 1),
                          gbs=round(byts / t / 1e9, 1), frac_of_hbm=round(byts / t / 1e9 / peaks["hbm"], 3)))
     return rows
 
@@ -167,7 +198,7 @@ def main():
                 r["bound_tflops"], r["frac_of_bound"], r["frac_of_tensor_peak"]))
             print(lines[-1], flush=True)
     lines += ["", "| norm site | op | us | GB/s (algorithmic) | frac of HBM peak |", "|---|---|---|---|---|"]
-    if not args.only:
+    if not args.only or args.only == "NONE":
         for (c, hw, kind) in ((64, 128, 1), (128, 64, 1), (256, 32, 1), (256, 32, 2), (128, 64, 3), (64, 128, 3)):
             for r in bench_post(args.batch, c, hw, kind, peaks):
                 lines.append("| %s | %s | %.1f | %.1f | %.3f |" % (r["layer"], r["op"], r["us"], r["gbs"], r["frac_of_hbm"]))

@@ -1,0 +1,57 @@
+"""Kernel timeline of one replayed training step through torch.profiler (CUPTI): in-situ kernel durations (warm
+caches, real overlap between the main and the side stream), idle gaps, per-kernel totals.
+  python tools/timeline_step.py [batch] > profiles/xxx.txt"""
+import os, sys, json, collections
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from torch.profiler import profile, ProfilerActivity
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+dev = torch.device("cuda", 0)
+s, cfg = bench.build_solver(dev, "bf16")
+b = {k: v.to(dev) for k, v in bench.make_host_batch(B, 128, 0).items()}
+for it in range(6):
+    bench.one_step(s, cfg, b, it)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    bench.one_step(s, cfg, b, 6)
+    torch.cuda.synchronize()
+path = "/tmp/trace.json"
+prof.export_chrome_trace(path)
+ev = json.load(open(path))["traceEvents"]
+ks = [e for e in ev if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e]
+ks.sort(key=lambda e: e["ts"])
+t0, t1 = ks[0]["ts"], max(e["ts"] + e["dur"] for e in ks)
+print("step span %.2f ms, %d GPU activities" % ((t1 - t0) / 1e3, len(ks)))
+streams = collections.defaultdict(list)
+for e in ks:
+    streams[e["args"].get("stream")].append(e)
+for sid, lst in streams.items():
+    busy = sum(e["dur"] for e in lst)
+    print("stream %s: %d activities, busy %.2f ms" % (sid, len(lst), busy / 1e3))
+# union busy time
+iv = sorted((e["ts"], e["ts"] + e["dur"]) for e in ks)
+busy, cur_s, cur_e = 0.0, iv[0][0], iv[0][1]
+for a, c in iv[1:]:
+    if a > cur_e:
+        busy += cur_e - cur_s
+        cur_s, cur_e = a, c
+    else:
+        cur_e = max(cur_e, c)
+busy += cur_e - cur_s
+print("GPU busy (union) %.2f ms, idle %.2f ms" % (busy / 1e3, (t1 - t0 - busy) / 1e3))
+# gaps on the main stream
+main = max(streams.values(), key=len)
+gaps = [main[i + 1]["ts"] - (main[i]["ts"] + main[i]["dur"]) for i in range(len(main) - 1)]
+gaps = [g for g in gaps if g > 0]
+print("main stream: mean gap %.2f us, total gaps %.2f ms" % (sum(gaps) / max(1, len(gaps)), sum(gaps) / 1e3))
+agg = collections.defaultdict(lambda: [0, 0.0])
+for e in ks:
+    nm = e["name"][:70]
+    agg[nm][0] += 1
+    agg[nm][1] += e["dur"]
+tot = sum(v[1] for v in agg.values())
+print("sum of activity durations %.2f ms" % (tot / 1e3))
+for nm, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+    print("%6.2f%% %9.1f us %5d x %8.1f us  %s" % (100 * d / tot, d, c, d / c, nm))
