@@ -291,8 +291,8 @@ static int launch_tc(const dwc_gconv_t* g, const GConvDev& d, cudaStream_t st) {
 extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
   DWC_CHECK(g != nullptr, "dwc_gconv: null params");
   DWC_CHECK(g->ntaps > 0 && g->ntaps <= DWC_MAX_TAPS, "dwc_gconv: ntaps %d out of range", g->ntaps);
-  DWC_CHECK(g->box[0] * g->box[1] * g->box[2] == 128, "dwc_gconv: box must cover 128 rows");
   const bool halo = g->backend == DWC_TC_HALO || g->backend == DWC_TC_HALO1;
+  DWC_CHECK(halo || g->box[0] * g->box[1] * g->box[2] == 128, "dwc_gconv: box must cover 128 rows");
   DWC_CHECK(g->a_str[0] == 1, "dwc_gconv: channel stride must be 1");
   GConvDev d;
   memset(&d, 0, sizeof(d));

@@ -1,14 +1,14 @@
 // gconv_halo: stride-1 k x k convolution (forward over the reflect-haloed input, data gradient over the zero-haloed
 // output gradient) as a tcgen05 implicit GEMM that stages each INPUT pixel once per channel slab.
 //
-//  tile      : 8 (x) x 16 (y) output pixels of one image = the 128 rows of the UMMA accumulator;
-//  A operand : per 64-channel slab ONE TMA box of 16 x (15+k) input pixels lands in shared memory as
-//              [row][16 px][64 ch] (2 KB per image row, 128-byte swizzle).  The A tile of filter tap (dy, dx) is the
-//              same buffer viewed through a UMMA descriptor whose start address is advanced by (dy*16 + dx) pixels
+//  tile      : 8*MT (x) x 16 (y) output pixels of one image = MT accumulators of 128 rows x BN columns in TMEM;
+//  A operand : per 64-channel slab ONE TMA box of (8*MT+8) x (15+k) input pixels lands in shared memory as
+//              [row][8*MT+8 px][64 ch] (128-byte swizzle).  The A tile of filter tap (dy, dx) and M-tile m is the same
+//              buffer viewed through a UMMA descriptor whose start address is advanced by (dy*pitch + dx + 8m) pixels,
 //              with an 8-row-group stride (SBO) of one image row: k*k taps re-read shared memory, not L2
 //              (the tap-by-tap kernel in gconv.cu re-fetches the 128-pixel tile from L2 for every tap);
-//  B operand : [BN][64] weight tile per (tap, slab) through an mbarrier ring; in a 2-CTA cluster each CTA fetches
-//              half of the tile and TMA-multicasts it to both, halving the weight traffic per SM;
+//  B operand : [BN][64] weight tile per (tap, slab) through an mbarrier ring, used by all MT accumulators: with
+//              MT = 2 the weight bytes per MMA cycle halve, so the ring covers the TMA latency;
 //  roles     : warp 0 weight producer, warp 1 MMA issuer, warp 2 lane 0 input producer, warps 2-5 epilogue
 //              (tcgen05.ld -> +bias -> bf16/fp32 store).
 #include "gconv.cuh"
@@ -19,36 +19,16 @@ constexpr int HT_THREADS = 192;
 constexpr int HT_BK = 64;
 constexpr int HT_NA = 2;          // input-tile stages
 
-template <int BN> struct HaloCfg {
+template <int BN, int MT> struct HaloCfg {
   static constexpr int B_BYTES = BN * HT_BK * 2;
   static constexpr int B_BYTES_AL = (B_BYTES + 1023) / 1024 * 1024;
-  static constexpr int NB = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int NB = BN >= 256 ? 3 : (BN >= 128 ? 6 : 8);
+  static constexpr int ACC_COLS = BN < 32 ? 32 : BN;          // TMEM columns per accumulator
+  static constexpr int TMEM_COLS = ACC_COLS * MT < 32 ? 32 : ACC_COLS * MT;
+  static constexpr int PITCH = 8 * MT + 8;                     // pixels per staged image row
+  static constexpr int ROW_BYTES = PITCH * 128;
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
-      "{%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(mask)
-      : "memory");
-}
 // K-major SW128 descriptor with an explicit 8-row-group stride.  The start address may be any multiple of 128 bytes
 // inside the TMA-written buffer: the hardware applies the 128B swizzle to the absolute shared-memory address bits
 // (measured on B200: a pixel-shifted start with matrix-base-offset 0 reads exactly the rows TMA wrote; setting the
@@ -63,14 +43,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t saddr, uint32_t
   return d;
 }
 
-template <int BN, int CL>
+template <int BN, int MT>
 __global__ void __launch_bounds__(HT_THREADS)
     gconv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ GConvDev p, const int ksize) {
-  using Cfg = HaloCfg<BN>;
+  using Cfg = HaloCfg<BN, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_stage = (15 + ksize) * 2048;
+  const int a_stage = (15 + ksize) * Cfg::ROW_BYTES;
   uint8_t* sA = smem;
   uint8_t* sB = smem + HT_NA * a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + Cfg::NB * Cfg::B_BYTES_AL);
@@ -86,11 +66,10 @@ __global__ void __launch_bounds__(HT_THREADS)
   const int col0 = blockIdx.y * BN;
   const int cblocks = p.C / HT_BK;
   const int ntaps = ksize * ksize;
-  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
 
   int tx = tile % p.tiles_x;
   int t2 = tile / p.tiles_x;
-  const int x0 = tx * 8, y0 = (t2 % p.tiles_y) * 16, n0 = t2 / p.tiles_y;   // n0 >= N for the padding CTA of a cluster
+  const int x0 = tx * 8 * MT, y0 = (t2 % p.tiles_y) * 16, n0 = t2 / p.tiles_y;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -101,7 +80,7 @@ __global__ void __launch_bounds__(HT_THREADS)
     }
     for (int s = 0; s < Cfg::NB; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], CL);      // every CTA of the cluster must have consumed the slot
+      mbar_init(&b_empty[s], 1);
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -109,7 +88,6 @@ __global__ void __launch_bounds__(HT_THREADS)
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();          // peer barriers are initialised before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -123,12 +101,7 @@ __global__ void __launch_bounds__(HT_THREADS)
           mbar_wait(&b_empty[stage], phase ^ 1);
           mbar_expect_tx(&b_full[stage], Cfg::B_BYTES);
           uint8_t* dst = sB + stage * Cfg::B_BYTES_AL;
-          if (CL == 1) {
-            tma_load_2d(dst, &tmB, &b_full[stage], t * p.C + cb * HT_BK, col0);
-          } else {
-            tma_load_2d_mc(dst + rank * (Cfg::B_BYTES / CL), &tmB, &b_full[stage], t * p.C + cb * HT_BK,
-                           col0 + rank * (BN / CL), (uint16_t)((1u << CL) - 1));
-          }
+          tma_load_2d(dst, &tmB, &b_full[stage], t * p.C + cb * HT_BK, col0);
           if (++stage == Cfg::NB) {
             stage = 0;
             phase ^= 1;
@@ -150,17 +123,19 @@ __global__ void __launch_bounds__(HT_THREADS)
           mbar_wait(&b_full[bs], bphase);
           tc_fence_after();
           const int dy = t / ksize, dx = t - dy * ksize;
-          const uint32_t a_addr = a_base + (uint32_t)(dy * 16 + dx) * 128u;
+          const uint32_t a_addr = a_base + (uint32_t)(dy * Cfg::PITCH + dx) * 128u;
           const uint32_t b_addr = smem_u32(sB + bs * Cfg::B_BYTES_AL);
 #pragma unroll
-          for (int k = 0; k < HT_BK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128_sbo(a_addr + k * 32, 2048);
-            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(tmem_base, da, db, idesc, any);
-            any = 1;
+          for (int m = 0; m < MT; ++m) {
+#pragma unroll
+            for (int k = 0; k < HT_BK / 16; ++k) {
+              const uint64_t da = umma_desc_sw128_sbo(a_addr + m * 1024 + k * 32, Cfg::ROW_BYTES);
+              const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+              umma_bf16(tmem_base + m * Cfg::ACC_COLS, da, db, idesc, any | (uint32_t)(k != 0));
+            }
           }
-          if (CL == 1) umma_commit(&b_empty[bs]);
-          else umma_commit_mc(&b_empty[bs], (uint16_t)((1u << CL) - 1));
+          any = 1;
+          umma_commit(&b_empty[bs]);
           if (++bs == Cfg::NB) {
             bs = 0;
             bphase ^= 1;
@@ -193,19 +168,20 @@ __global__ void __launch_bounds__(HT_THREADS)
     // ================= epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =================
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    RowCoord rc;
-    rc.x = x0 + (r & 7);
-    rc.y = y0 + (r >> 3);
-    rc.n = n0;
-    long long off = 0;
-    const bool valid = out_offset(p, rc, &off);
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     constexpr int CHUNK = BN >= 32 ? 32 : 16;
 #pragma unroll 1
-    for (int cc = 0; cc < BN; cc += CHUNK) {
+    for (int mc = 0; mc < MT * BN; mc += CHUNK) {
+      const int m = mc / BN, cc = mc - m * BN;
+      RowCoord rc;
+      rc.x = x0 + m * 8 + (r & 7);
+      rc.y = y0 + (r >> 3);
+      rc.n = n0;
+      long long off = 0;
+      const bool valid = out_offset(p, rc, &off);
       uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * Cfg::ACC_COLS + cc);
       if (CHUNK == 32) tmem_ld32(taddr, v);
       else tmem_ld16(taddr, v);
       tmem_ld_wait();
@@ -251,66 +227,55 @@ __global__ void __launch_bounds__(HT_THREADS)
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
-template <int BN, int CL>
+template <int BN, int MT>
 int launch_halo(const dwc_gconv_t* g, const GConvDev& d, int ksize, cudaStream_t st) {
-  using Cfg = HaloCfg<BN>;
+  using Cfg = HaloCfg<BN, MT>;
   CUtensorMap tmA, tmB;
-  if (dwc_make_tmap5(&tmA, g->a, g->a_dim, g->a_str, 16, 15 + ksize, 1, 1)) return 1;
-  if (dwc_make_tmap2(&tmB, g->w, g->ncols_padded, d.K, d.K, BN / CL, HT_BK)) return 1;
-  const int a_stage = (15 + ksize) * 2048;
+  if (dwc_make_tmap5(&tmA, g->a, g->a_dim, g->a_str, Cfg::PITCH, 15 + ksize, 1, 1)) return 1;
+  if (dwc_make_tmap2(&tmB, g->w, g->ncols_padded, d.K, d.K, BN, HT_BK)) return 1;
+  const int a_stage = (15 + ksize) * Cfg::ROW_BYTES;
   const int smem = HT_NA * a_stage + Cfg::NB * Cfg::B_BYTES_AL + 1024 + 256;
   DWC_CHECK(smem <= 227 * 1024, "dwc_gconv(halo): shared memory %d exceeds the SM", smem);
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    DWC_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (CL > 1) DWC_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<BN, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    DWC_CUDA(cudaFuncSetAttribute(gconv_halo_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  const int ntiles = d.tiles_x * d.tiles_y * d.tiles_n;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((ntiles + CL - 1) / CL * CL, cdiv(g->ncols_padded, BN), 1);
-  cfg.blockDim = dim3(HT_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  DWC_CUDA(cudaLaunchKernelEx(&cfg, gconv_halo_kernel<BN, CL>, tmA, tmB, d, ksize));
+  dim3 grid(d.tiles_x * d.tiles_y * d.tiles_n, cdiv(g->ncols_padded, BN));
+  gconv_halo_kernel<BN, MT><<<grid, HT_THREADS, smem, st>>>(tmA, tmB, d, ksize);
+  DWC_LAUNCH_CHECK();
   return 0;
-}
-
-template <int BN>
-int launch_halo_cl(const dwc_gconv_t* g, const GConvDev& d, int ksize, int cl, cudaStream_t st) {
-  return cl == 2 ? launch_halo<BN, 2>(g, d, ksize, st) : launch_halo<BN, 1>(g, d, ksize, st);
 }
 
 }  // namespace
 
 int dwc_launch_gconv_halo(const dwc_gconv_t* g, const GConvDev& d, int ksize, cudaStream_t st) {
   DWC_CHECK(ksize >= 1 && ksize <= 9, "dwc_gconv(halo): window %d out of range", ksize);
-  DWC_CHECK(g->box[0] == 8 && g->box[1] == 16 && g->box[2] == 1, "dwc_gconv(halo): tile must be 8 x 16 x 1");
+  const int mt = g->box[0] / 8;
+  DWC_CHECK((mt == 1 || mt == 2) && g->box[0] == 8 * mt && g->box[1] == 16 && g->box[2] == 1,
+            "dwc_gconv(halo): tile must be 8 x 16 x 1 or 16 x 16 x 1");
   DWC_CHECK(!g->flat, "dwc_gconv(halo): flat addressing is not supported");
   for (int t = 0; t < g->ntaps; ++t)
     DWC_CHECK(g->taps[t * 3] == t % ksize && g->taps[t * 3 + 1] == t / ksize && g->taps[t * 3 + 2] == 0,
               "dwc_gconv(halo): taps must be the full k x k window in (ky, kx) order");
-  // cluster size: backend code DWC_TC_HALO + 1 selects the single-CTA variant (diagnostics)
-  const int cl = g->backend == DWC_TC_HALO ? 2 : 1;
   const int np = g->ncols_padded;
-  if (np % 256 == 0) return launch_halo_cl<256>(g, d, ksize, cl, st);
-  if (np % 128 == 0) return launch_halo_cl<128>(g, d, ksize, cl, st);
-  if (np % 64 == 0) return launch_halo_cl<64>(g, d, ksize, cl, st);
-  if (np == 16) return launch_halo_cl<16>(g, d, ksize, cl, st);
+  if (mt == 2) {
+    // two accumulators per CTA: 128-column blocks keep the weight stage at 16 KB (more stages in flight)
+    if (np % 256 == 0) return launch_halo<256, 2>(g, d, ksize, st);
+    if (np % 128 == 0) return launch_halo<128, 2>(g, d, ksize, st);
+    if (np % 64 == 0) return launch_halo<64, 2>(g, d, ksize, st);
+    if (np == 16) return launch_halo<16, 2>(g, d, ksize, st);
+  } else {
+    if (np % 256 == 0) return launch_halo<256, 1>(g, d, ksize, st);
+    if (np % 128 == 0) return launch_halo<128, 1>(g, d, ksize, st);
+    if (np % 64 == 0) return launch_halo<64, 1>(g, d, ksize, st);
+    if (np == 16) return launch_halo<16, 1>(g, d, ksize, st);
+  }
   DWC_CHECK(false, "dwc_gconv(halo): unsupported padded column count %d", np);
 }

@@ -235,14 +235,18 @@ def out_size(xp: HB, k: int, stride: int):
     return (xp.hp - k) // stride + 1, (xp.wp - k) // stride + 1
 
 
-HALO_MODE = int(os.environ.get("DWC_HALO", "0"))      # 0: tap-by-tap kernel, 1: halo tile, 2: halo tile + multicast
+HALO_MODE = int(os.environ.get("DWC_HALO", "0"))      # 0: tap-by-tap kernel, 1: halo tile 8x16, 2: halo tile 16x16 (2 accumulators)
 
 
 def halo_backend(backend, k, stride, c):
     """Stride-1 k x k windows on the tensor cores use the halo-tile kernel (csrc/gconv_halo.cu)."""
     if backend == L.TC and stride == 1 and k in (3, 5, 7) and c % 64 == 0 and HALO_MODE:
-        return L.TC_HALO if HALO_MODE == 2 else L.TC_HALO1
+        return L.TC_HALO
     return backend
+
+
+def halo_box():
+    return (16, 16, 1) if HALO_MODE == 2 else (8, 16, 1)
 
 
 def plan_conv_fwd(xp: HB, w_packed, ncols, ncols_padded, bias, y: HB, k, stride, backend) -> GConvPlan:
@@ -251,7 +255,7 @@ def plan_conv_fwd(xp: HB, w_packed, ncols, ncols_padded, bias, y: HB, k, stride,
     assert (stride == 1 and xp.layout == 0) or (stride == 2 and xp.layout == 1 and k == 4)
     dims, strs = input_view(xp)
     backend = halo_backend(backend, k, stride, xp.c)
-    box = (8, 16, 1) if backend in (L.TC_HALO, L.TC_HALO1) else choose_box(wo, ho, xp.n, 128)
+    box = halo_box() if backend == L.TC_HALO else choose_box(wo, ho, xp.n, 128)
     tiles = (-(-wo // box[0]), -(-ho // box[1]), -(-xp.n // box[2]))
     cy = y.c
     return GConvPlan(a=xp.t, a_off=0, a_dim=dims, a_str=strs, box=box, tiles=tiles, valid=(wo, ho, xp.n),
@@ -276,8 +280,9 @@ def plan_conv_dgrad(dy: HB, w_packed, dxp: HB, k, stride, backend, cin_padded=No
         assert dy.halo == k - 1 and dxp.layout == 0 and (dxp.hp, dxp.wp) == (dy.hp - k + 1, dy.wp - k + 1)
         dims = (cout, dy.wp, dy.hp, 1, dy.n)
         strs = (1, cout, dy.wp * cout, dy.hp * dy.wp * cout, dy.hp * dy.wp * cout)
-        plans.append(GConvPlan(a=dy.t, a_off=0, a_dim=dims, a_str=strs, box=(8, 16, 1),
-                               tiles=(-(-dxp.wp // 8), -(-dxp.hp // 16), dy.n), valid=(dxp.wp, dxp.hp, dy.n),
+        hbx = halo_box()
+        plans.append(GConvPlan(a=dy.t, a_off=0, a_dim=dims, a_str=strs, box=hbx,
+                               tiles=(-(-dxp.wp // hbx[0]), -(-dxp.hp // 16), dy.n), valid=(dxp.wp, dxp.hp, dy.n),
                                flat=(0, 0, 0, 0, 0), taps=conv_taps(k, 1), w=w_packed, w_off=0, ncols=cin,
                                ncols_padded=cin_padded, bias=None, out=dxp.t, out_off=0,
                                o_str=(cin, dxp.wp * cin, dxp.hp * dxp.wp * cin), backend=hb))

@@ -37,8 +37,9 @@ int dwc_tc_available(void);
 #define DWC_BF16 1
 #define DWC_SIMT 0
 #define DWC_TC 1
-#define DWC_TC_HALO 2   /* gconv only: stride-1 k x k window, 8x16-pixel tiles, input staged once per slab, 2-CTA weight multicast */
-#define DWC_TC_HALO1 3  /* same, single-CTA (no cluster) variant */
+#define DWC_TC_HALO 2   /* gconv only: stride-1 k x k window, input staged once per 64-channel slab (gconv_halo.cu);
+                         * box = (16,16,1): two 128-row accumulators per CTA, (8,16,1): one */
+#define DWC_TC_HALO1 3  /* alias kept for diagnostics */
 #define DWC_MAX_TAPS 64
 
 /* ------------------------------------------------------------------------------------------

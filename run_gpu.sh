@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout -k 10 900 python -m pytest tests/test_post_gpu.py tests/test_conv_gpu.py tests/test_modules_gpu.py tests/test_step_gpu.py -q -m gpu -n 4 --tb=short 2>&1 | grep -v "^frame\|python()\|Warning\|warnings.html\|detach()" | tail -12 > gpurun_out/t_net.log; tail -6 gpurun_out/t_net.log
-timeout -k 10 900 python tools/microbench.py --batch 48 --only NONE > gpurun_out/microbench_norm.log 2>&1; grep "^|" gpurun_out/microbench_norm.log || tail -5 gpurun_out/microbench_norm.log
-timeout -k 10 900 python bench.py --steps 10 --warmup 4 --no-cpu-baseline 2>&1 | grep -v Warn | tail -1 | tee gpurun_out/bench9.json
+timeout -k 10 600 python -m pytest tests/test_conv_gpu.py tests/test_rows_gpu.py -q -m gpu -n 4 --tb=short 2>&1 | tail -8 > gpurun_out/t_halo2.log; tail -4 gpurun_out/t_halo2.log
+timeout -k 10 900 python tools/microbench.py --batch 16 --only G7,G8 > gpurun_out/microbench_halo.log 2>&1; grep "^|" gpurun_out/microbench_halo.log
+timeout -k 10 900 python tools/microbench.py --batch 48 --only G7,G8 > gpurun_out/microbench_halo48.log 2>&1; grep "^|" gpurun_out/microbench_halo48.log
