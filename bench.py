@@ -252,9 +252,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        _leave(world)
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     sampler.join(timeout=2)
@@ -280,9 +278,19 @@ def main():
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": round(2 / dt, 4), "unit": "images/s", "cores": torch.get_num_threads(),
                                 "kind": "port", "sample": "1 G+D step of batch 2 (oracle port, torch CPU fp32), %.1f s" % dt}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    _leave(world)
+
+
+def _leave(world):
+    """End the process without tearing NCCL down: captured CUDA graphs still reference the communicator, and a
+    destroy_process_group() that one rank reaches long before the other (rank 0 goes on to the roofline and CPU
+    legs) has been seen to block at exit."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -10,7 +10,7 @@ Parity pinning: the reference ships no golden vectors, so this
 restatement is pinned against the reference itself, imported from
 ``/root/reference`` in the build container by ``tests/golden/make_golden.py``;
 the resulting losses / gradient norms / parameter checksums are committed under
-``tests/golden/`` and re-checked on every run by ``tests/test_oracle.py``.
+``tests/golden/`` and re-checked on every run by ``tests/test_oracle_cpu.py``.
 
 Everything here is written as pure functions over a flat ``{state_dict key:
 tensor}`` parameter dictionary (same keys/shapes as the reference checkpoints,

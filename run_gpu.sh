@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-timeout -k 10 600 python -m pytest tests/test_conv_gpu.py tests/test_rows_gpu.py -q -m gpu -n 4 --tb=short 2>&1 | tail -8 > gpurun_out/t_halo2.log; tail -4 gpurun_out/t_halo2.log
-timeout -k 10 900 python tools/microbench.py --batch 16 --only G7,G8 > gpurun_out/microbench_halo.log 2>&1; grep "^|" gpurun_out/microbench_halo.log
-timeout -k 10 900 python tools/microbench.py --batch 48 --only G7,G8 > gpurun_out/microbench_halo48.log 2>&1; grep "^|" gpurun_out/microbench_halo48.log
+timeout -k 5 170 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 4 > gpurun_out/bench_2gpu.log 2>&1; echo "rc=$?"; grep -v "Warn\|warn" gpurun_out/bench_2gpu.log | tail -3
