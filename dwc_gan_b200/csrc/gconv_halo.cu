@@ -1,12 +1,13 @@
 // gconv_halo: stride-1 k x k convolution (forward over the reflect-haloed input, data gradient over the zero-haloed
-// output gradient) as a tcgen05 implicit GEMM that stages each INPUT pixel once per channel slab.
+// output gradient) as a tcgen05 implicit GEMM that fetches each input pixel k times instead of k*k times.
 //
 //  tile      : 8*MT (x) x 16 (y) output pixels of one image = MT accumulators of 128 rows x BN columns in TMEM;
-//  A operand : per 64-channel slab ONE TMA box of (8*MT+8) x (15+k) input pixels lands in shared memory as
-//              [row][8*MT+8 px][64 ch] (128-byte swizzle).  The A tile of filter tap (dy, dx) and M-tile m is the same
-//              buffer viewed through a UMMA descriptor whose start address is advanced by (dy*pitch + dx + 8m) pixels,
-//              with an 8-row-group stride (SBO) of one image row: k*k taps re-read shared memory, not L2
-//              (the tap-by-tap kernel in gconv.cu re-fetches the 128-pixel tile from L2 for every tap);
+//  A operand : per (64-channel slab, horizontal tap dx) ONE TMA box of 8*MT x (15+k) input pixels lands in shared
+//              memory as [row][8*MT px][64 ch] (128-byte swizzle).  The k vertical taps dy of that column shift are the
+//              same buffer viewed through UMMA descriptors whose start address advances by dy image rows (a multiple
+//              of 1024 B, so every 8-row group stays aligned with the swizzle atom; sliding the window horizontally
+//              inside one buffer also works - the swizzle is applied to absolute smem address bits - but such
+//              unaligned starts were measured to halve the MMA issue rate, see tests/diag_halo.py and profiles/);
 //  B operand : [BN][64] weight tile per (tap, slab) through an mbarrier ring, used by all MT accumulators: with
 //              MT = 2 the weight bytes per MMA cycle halve, so the ring covers the TMA latency;
 //  roles     : warp 0 weight producer, warp 1 MMA issuer, warp 2 lane 0 input producer, warps 2-5 epilogue
@@ -17,7 +18,7 @@ namespace {
 
 constexpr int HT_THREADS = 192;
 constexpr int HT_BK = 64;
-constexpr int HT_NA = 2;          // input-tile stages
+constexpr int HT_NA = 3;          // input-tile stages (one per horizontal tap in flight)
 
 template <int BN, int MT> struct HaloCfg {
   static constexpr int B_BYTES = BN * HT_BK * 2;
@@ -25,7 +26,7 @@ template <int BN, int MT> struct HaloCfg {
   static constexpr int NB = BN >= 256 ? 3 : (BN >= 128 ? 6 : 8);
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;          // TMEM columns per accumulator
   static constexpr int TMEM_COLS = ACC_COLS * MT < 32 ? 32 : ACC_COLS * MT;
-  static constexpr int PITCH = 8 * MT + 8;                     // pixels per staged image row
+  static constexpr int PITCH = 8 * MT;                         // pixels per staged image row
   static constexpr int ROW_BYTES = PITCH * 128;
 };
 
@@ -65,8 +66,6 @@ __global__ void __launch_bounds__(HT_THREADS)
   const int tile = blockIdx.x;
   const int col0 = blockIdx.y * BN;
   const int cblocks = p.C / HT_BK;
-  const int ntaps = ksize * ksize;
-
   int tx = tile % p.tiles_x;
   int t2 = tile / p.tiles_x;
   const int x0 = tx * 8 * MT, y0 = (t2 % p.tiles_y) * 16, n0 = t2 / p.tiles_y;
@@ -97,14 +96,17 @@ __global__ void __launch_bounds__(HT_THREADS)
       int stage = 0;
       uint32_t phase = 0;
       for (int cb = 0; cb < cblocks; ++cb) {
-        for (int t = 0; t < ntaps; ++t) {
-          mbar_wait(&b_empty[stage], phase ^ 1);
-          mbar_expect_tx(&b_full[stage], Cfg::B_BYTES);
-          uint8_t* dst = sB + stage * Cfg::B_BYTES_AL;
-          tma_load_2d(dst, &tmB, &b_full[stage], t * p.C + cb * HT_BK, col0);
-          if (++stage == Cfg::NB) {
-            stage = 0;
-            phase ^= 1;
+        for (int dx = 0; dx < ksize; ++dx) {
+          for (int dy = 0; dy < ksize; ++dy) {
+            const int t = dy * ksize + dx;
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            mbar_expect_tx(&b_full[stage], Cfg::B_BYTES);
+            uint8_t* dst = sB + stage * Cfg::B_BYTES_AL;
+            tma_load_2d(dst, &tmB, &b_full[stage], t * p.C + cb * HT_BK, col0);
+            if (++stage == Cfg::NB) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -117,34 +119,35 @@ __global__ void __launch_bounds__(HT_THREADS)
       uint32_t bphase = 0, aphase = 0;
       uint32_t any = 0;
       for (int cb = 0; cb < cblocks; ++cb) {
-        mbar_wait(&a_full[as], aphase);
-        const uint32_t a_base = smem_u32(sA + as * a_stage);
-        for (int t = 0; t < ntaps; ++t) {
-          mbar_wait(&b_full[bs], bphase);
-          tc_fence_after();
-          const int dy = t / ksize, dx = t - dy * ksize;
-          const uint32_t a_addr = a_base + (uint32_t)(dy * Cfg::PITCH + dx) * 128u;
-          const uint32_t b_addr = smem_u32(sB + bs * Cfg::B_BYTES_AL);
+        for (int dx = 0; dx < ksize; ++dx) {
+          mbar_wait(&a_full[as], aphase);
+          const uint32_t a_base = smem_u32(sA + as * a_stage);
+          for (int dy = 0; dy < ksize; ++dy) {
+            mbar_wait(&b_full[bs], bphase);
+            tc_fence_after();
+            const uint32_t a_addr = a_base + (uint32_t)dy * Cfg::ROW_BYTES;
+            const uint32_t b_addr = smem_u32(sB + bs * Cfg::B_BYTES_AL);
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
+            for (int m = 0; m < MT; ++m) {
 #pragma unroll
-            for (int k = 0; k < HT_BK / 16; ++k) {
-              const uint64_t da = umma_desc_sw128_sbo(a_addr + m * 1024 + k * 32, Cfg::ROW_BYTES);
-              const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-              umma_bf16(tmem_base + m * Cfg::ACC_COLS, da, db, idesc, any | (uint32_t)(k != 0));
+              for (int k = 0; k < HT_BK / 16; ++k) {
+                const uint64_t da = umma_desc_sw128_sbo(a_addr + m * 1024 + k * 32, Cfg::ROW_BYTES);
+                const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+                umma_bf16(tmem_base + m * Cfg::ACC_COLS, da, db, idesc, any | (uint32_t)(k != 0));
+              }
+            }
+            any = 1;
+            umma_commit(&b_empty[bs]);
+            if (++bs == Cfg::NB) {
+              bs = 0;
+              bphase ^= 1;
             }
           }
-          any = 1;
-          umma_commit(&b_empty[bs]);
-          if (++bs == Cfg::NB) {
-            bs = 0;
-            bphase ^= 1;
+          umma_commit(&a_empty[as]);
+          if (++as == HT_NA) {
+            as = 0;
+            aphase ^= 1;
           }
-        }
-        umma_commit(&a_empty[as]);
-        if (++as == HT_NA) {
-          as = 0;
-          aphase ^= 1;
         }
       }
       umma_commit(tmem_full);
@@ -155,12 +158,14 @@ __global__ void __launch_bounds__(HT_THREADS)
       int as = 0;
       uint32_t aphase = 0;
       for (int cb = 0; cb < cblocks; ++cb) {
-        mbar_wait(&a_empty[as], aphase ^ 1);
-        mbar_expect_tx(&a_full[as], (uint32_t)a_stage);
-        tma_load_5d(sA + as * a_stage, &tmA, &a_full[as], cb * HT_BK, x0, y0, 0, n0);
-        if (++as == HT_NA) {
-          as = 0;
-          aphase ^= 1;
+        for (int dx = 0; dx < ksize; ++dx) {
+          mbar_wait(&a_empty[as], aphase ^ 1);
+          mbar_expect_tx(&a_full[as], (uint32_t)a_stage);
+          tma_load_5d(sA + as * a_stage, &tmA, &a_full[as], cb * HT_BK, x0 + dx, y0, 0, n0);
+          if (++as == HT_NA) {
+            as = 0;
+            aphase ^= 1;
+          }
         }
       }
     }

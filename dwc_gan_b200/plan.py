@@ -235,18 +235,24 @@ def out_size(xp: HB, k: int, stride: int):
     return (xp.hp - k) // stride + 1, (xp.wp - k) // stride + 1
 
 
-HALO_MODE = int(os.environ.get("DWC_HALO", "0"))      # 0: tap-by-tap kernel, 1: halo tile 8x16, 2: halo tile 16x16 (2 accumulators)
+# Which stride-1 window sizes run on the halo-tile kernel (csrc/gconv_halo.cu) instead of the tap-by-tap kernel:
+# none by default.  Measured on B200 (profiles/r01c_microbench_halo_vs_tap.md, r01d_*): fetching the input k times
+# instead of k*k times, and halving the weight bytes per MMA cycle with two accumulators, does NOT make these layers
+# faster - the tap-by-tap kernel is not bound by L2 operand traffic but by per-CTA prologue/epilogue time and by the
+# SS-mode A-operand read (>= 64 cycles per M=128 MMA, which caps N<=64 layers at <= 50 %).  DWC_HALO_K="3,5,7"
+# switches the halo kernel on for experiments; it passes the same parity tests.
+HALO_K = tuple(int(v) for v in os.environ.get("DWC_HALO_K", "").split(",") if v)
+HALO_MT = int(os.environ.get("DWC_HALO_MT", "1"))       # accumulators (128-row M tiles) per CTA
 
 
-def halo_backend(backend, k, stride, c):
-    """Stride-1 k x k windows on the tensor cores use the halo-tile kernel (csrc/gconv_halo.cu)."""
-    if backend == L.TC and stride == 1 and k in (3, 5, 7) and c % 64 == 0 and HALO_MODE:
+def halo_backend(backend, k, stride, c, ncols_padded=None):
+    if backend == L.TC and stride == 1 and k in HALO_K and c % 64 == 0:
         return L.TC_HALO
     return backend
 
 
 def halo_box():
-    return (16, 16, 1) if HALO_MODE == 2 else (8, 16, 1)
+    return (16, 16, 1) if HALO_MT == 2 else (8, 16, 1)
 
 
 def plan_conv_fwd(xp: HB, w_packed, ncols, ncols_padded, bias, y: HB, k, stride, backend) -> GConvPlan:
@@ -254,7 +260,7 @@ def plan_conv_fwd(xp: HB, w_packed, ncols, ncols_padded, bias, y: HB, k, stride,
     assert (y.h, y.w, y.n) == (ho, wo, xp.n) and y.layout == 0, ((y.h, y.w), (ho, wo))
     assert (stride == 1 and xp.layout == 0) or (stride == 2 and xp.layout == 1 and k == 4)
     dims, strs = input_view(xp)
-    backend = halo_backend(backend, k, stride, xp.c)
+    backend = halo_backend(backend, k, stride, xp.c, ncols_padded)
     box = halo_box() if backend == L.TC_HALO else choose_box(wo, ho, xp.n, 128)
     tiles = (-(-wo // box[0]), -(-ho // box[1]), -(-xp.n // box[2]))
     cy = y.c
@@ -274,7 +280,7 @@ def plan_conv_dgrad(dy: HB, w_packed, dxp: HB, k, stride, backend, cin_padded=No
     a_dim = (cout, rows, 1, 1, 1)
     a_str = (1, cout, rows * cout, rows * cout, rows * cout)
     plans = []
-    hb = halo_backend(backend, k, stride, cout)
+    hb = halo_backend(backend, k, stride, cout, cin_padded)
     if stride == 1 and hb != backend:
         # full correlation of the zero-haloed gradient with the flipped filter = a valid k x k window over dy's buffer
         assert dy.halo == k - 1 and dxp.layout == 0 and (dxp.hp, dxp.wp) == (dy.hp - k + 1, dy.wp - k + 1)

@@ -25,6 +25,8 @@ GEOMS = [
     ("D2", 64, 128, 4, 2, 1, 64), ("D3", 128, 256, 4, 2, 1, 32), ("D4", 256, 512, 4, 2, 1, 16),
     ("D5", 512, 512, 4, 2, 1, 8), ("D2s", 64, 128, 4, 2, 1, 32), ("D3s", 128, 256, 4, 2, 1, 16),
     ("D4s", 256, 512, 4, 2, 1, 8), ("D5s", 512, 512, 4, 2, 1, 4),
+    ("G10", 64, 4, 7, 1, 3, 128),       # decoder heads (3+1 channels): forward only (backward uses window buffers)
+    ("G1d", 3, 64, 7, 1, 3, 128),       # first encoder conv: data gradient to the generated image only
 ]
 
 _ws = {}
@@ -85,23 +87,30 @@ def bench_geom(g, n, peaks):
           for _ in range(nbuf)]
     w = (torch.randn(cout, k, k, cin, device="cuda") * 0.02)
     bias = torch.zeros(cout, device="cuda")
-    wf = pack(w, 0, cout, cout, k, cin)
-    wd = pack(w, 1 if s == 1 else 2, cin, cout, k, cin)
+    rows_f = cout if cout % 64 == 0 else 16
+    rows_d = cin if cin % 64 == 0 else 16
+    wf = pack(w, 0, rows_f, cout, k, cin)
+    wd = pack(w, 1 if s == 1 else 2, rows_d, cout, k, cin)
     dw = torch.zeros(cout, k, k, cin, device="cuda")
     db = torch.zeros(cout, device="cuda")
     flops = 2.0 * n * ho * ho * cout * k * k * cin
     res = {}
-    fw = [P.plan_conv_fwd(xs[i], wf, cout, cout, bias, ys[i], k, s, L.TC) for i in range(nbuf)]
-    res["fprop"] = timeit([pl.launch for pl in fw])
-    dg = [P.plan_conv_dgrad(ys[i], wd, xs[i], k, s, L.TC) for i in range(nbuf)]
-    res["dgrad"] = timeit([(lambda ps=ps: [q.launch() for q in ps]) for ps in dg])
-    wg = [P.plan_conv_wgrad(ys[i], xs[i], dw, db, k, s, L.TC) for i in range(nbuf)]
-    res["wgrad"] = timeit([(lambda pl=pl: pl.launch(workspace)) for pl in wg])
+    if cin % 64 == 0:
+        fw = [P.plan_conv_fwd(xs[i], wf, cout, rows_f, bias, ys[i], k, s, L.TC) for i in range(nbuf)]
+        res["fprop"] = timeit([pl.launch for pl in fw])
+    if cout % 64 == 0:
+        dg = [P.plan_conv_dgrad(ys[i], wd, xs[i], k, s, L.TC, cin_padded=rows_d) for i in range(nbuf)]
+        res["dgrad"] = timeit([(lambda ps=ps: [q.launch() for q in ps]) for ps in dg])
+    if cin % 64 == 0 and cout % 64 == 0:
+        wg = [P.plan_conv_wgrad(ys[i], xs[i], dw, db, k, s, L.TC) for i in range(nbuf)]
+        res["wgrad"] = timeit([(lambda pl=pl: pl.launch(workspace)) for pl in wg])
     w_bytes = cout * k * k * cin * 2
     ai = flops / (in_bytes + out_bytes + w_bytes)
     bound = min(peaks["tflops"] * 1e12, ai * peaks["hbm"] * 1e9)
     rows = []
     for op in ("fprop", "dgrad", "wgrad"):
+        if op not in res:
+            continue
         t = res[op]
         rows.append(dict(layer=name, op=op, n=n, cin=cin, cout=cout, k=k, stride=s, hw_in=hw, us=round(t * 1e6, 1),
                          tflops=round(flops / t / 1e12, 1), bound_tflops=round(bound / 1e12, 1),
