@@ -74,6 +74,94 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Large problems (LSTM input projections and their gradients): 128 x 128 tile, 256 threads x (8 x 8), K in chunks of 16
+// with register prefetch of the next chunk (double-buffered shared memory).
+template <typename TA>
+__global__ void __launch_bounds__(256)
+    sgemm128_kernel(int M, int N, int K, float alpha, const TA* __restrict__ A, long long a_sm, long long a_sk,
+                    const float* __restrict__ B, long long b_sk, long long b_sn, float beta, float* __restrict__ C,
+                    long long c_sm, long long c_sn, const float* __restrict__ bias, int act) {
+  __shared__ float As[2][16][128 + 4];
+  __shared__ float Bs[2][16][128 + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+  const int ty = tid >> 4, tx = tid & 15;          // rows {ty*4.., 64+ty*4..}, cols {tx*4.., 64+tx*4..}
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const bool a_kfast = (a_sk == 1);
+  const bool b_nfast = (b_sn == 1);
+  float ra[8], rb[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = tid + j * 256;   // 0..2047
+      int mm, kk;
+      if (a_kfast) { kk = e & 15; mm = e >> 4; } else { mm = e & 127; kk = e >> 7; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      ra[j] = (gm < M && gk < K) ? to_f<TA>(A[gm * a_sm + gk * a_sk]) : 0.f;
+      int nn, k2;
+      if (b_nfast) { nn = e & 127; k2 = e >> 7; } else { k2 = e & 15; nn = e >> 4; }
+      const int gn = n0 + nn, gk2 = k0 + k2;
+      rb[j] = (gn < N && gk2 < K) ? B[gk2 * b_sk + gn * b_sn] : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = tid + j * 256;
+      int mm, kk;
+      if (a_kfast) { kk = e & 15; mm = e >> 4; } else { mm = e & 127; kk = e >> 7; }
+      As[buf][kk][mm] = ra[j];
+      int nn, k2;
+      if (b_nfast) { nn = e & 127; k2 = e >> 7; } else { k2 = e & 15; nn = e >> 4; }
+      Bs[buf][k2][nn] = rb[j];
+    }
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const bool more = k0 + 16 < K;
+    if (more) fetch(k0 + 16);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      stash(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (n >= N) continue;
+      float* o = C + m * c_sm + n * c_sn;
+      float v = alpha * acc[i][j] + (bias ? bias[n] : 0.f) + (beta != 0.f ? beta * *o : 0.f);
+      if (act == 1) v = v > 0.f ? v : 0.f;
+      *o = v;
+    }
+  }
+}
+
 __global__ void sgemm_splitk_finish_kernel(int M, int N, int splits, float alpha, const float* __restrict__ ws,
                                            float beta, float* __restrict__ C, long long c_sm, long long c_sn,
                                            const float* __restrict__ bias, int act) {
@@ -90,10 +178,12 @@ __global__ void sgemm_splitk_finish_kernel(int M, int N, int splits, float alpha
 
 // number of K splits for a problem whose (M, N) tile grid alone cannot fill the GPU
 static int sgemm_splits(int m, int n, int k) {
+  // The 64 x 64 kernel has one K chunk in flight per CTA, i.e. it is latency-bound unless several CTAs share an SM:
+  // aim at ~4 CTAs per SM, at least 64 K elements per split.
   const int ctas = cdiv(m, 64) * cdiv(n, 64);
-  if (ctas >= 64 || k < 512) return 1;
-  int s = cdiv(2 * dwc_num_sms(), ctas);
-  const int smax = cdiv(k, 128);
+  if (ctas >= 2 * dwc_num_sms() || k < 128) return 1;
+  int s = cdiv(4 * dwc_num_sms(), ctas);
+  const int smax = cdiv(k, 64);
   if (s > smax) s = smax;
   return s < 1 ? 1 : s;
 }
@@ -107,6 +197,18 @@ extern "C" int dwc_sgemm_ws(int m, int n, int k, float alpha, const void* a, int
                             const float* b, int64_t b_sk, int64_t b_sn, float beta, float* c, int64_t c_sm, int64_t c_sn,
                             const float* bias, int act, float* workspace, int64_t workspace_bytes, dwc_stream_t stream) {
   DWC_CHECK(m > 0 && n > 0 && k > 0, "dwc_sgemm: empty problem (%d,%d,%d)", m, n, k);
+  cudaStream_t st0 = as_stream(stream);
+  if (m >= 192 && n >= 192 && cdiv(m, 128) * cdiv(n, 128) >= dwc_num_sms() / 2) {
+    dim3 g128(cdiv(m, 128), cdiv(n, 128));
+    if (a_dtype == DWC_F32)
+      sgemm128_kernel<float><<<g128, 256, 0, st0>>>(m, n, k, alpha, reinterpret_cast<const float*>(a), a_sm, a_sk, b,
+                                                    b_sk, b_sn, beta, c, c_sm, c_sn, bias, act);
+    else
+      sgemm128_kernel<bf16><<<g128, 256, 0, st0>>>(m, n, k, alpha, reinterpret_cast<const bf16*>(a), a_sm, a_sk, b,
+                                                   b_sk, b_sn, beta, c, c_sm, c_sn, bias, act);
+    DWC_LAUNCH_CHECK();
+    return 0;
+  }
   int splits = workspace ? sgemm_splits(m, n, k) : 1;
   if (splits > 1 && workspace_bytes < (int64_t)splits * m * n * (int64_t)sizeof(float)) splits = 1;
   int kper = cdiv(cdiv(k, splits), 16) * 16;

@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
     post_bwd_apply_fast_kernel(HB dout, HB y, const float4* __restrict__ coef, const float4* __restrict__ bco, int act,
                                HB dy, HB dres, int has_dres) {
   const int hmax = max(dy.halo, has_dres ? dres.halo : 0);
@@ -530,14 +530,16 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// per-(n,c) sums, bf16.  grid (C/32, splits, N); block 256 = 4 channel-vectors x 64 pixel lanes, PF pixels per batch.
+// per-(n,c) sums, bf16.  grid (splits, N); a block covers ALL channels of its pixel range: thread = (8-channel group,
+// pixel lane), so a pixel is one contiguous C*2-byte read; PF pixels per thread are in flight at a time.
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
     nc_reduce_fast_kernel(HB y, HB dout, const float4* __restrict__ coef, int act, int splits, float2* __restrict__ out) {
-  __shared__ float s0[64][33], s1[64][33];
-  const int cv = threadIdx.x & 3, pl = threadIdx.x >> 2;
-  const int c0 = blockIdx.x * 32 + cv * 8;
-  const int split = blockIdx.y, n = blockIdx.z;
+  __shared__ float2 red[2048];                       // [pixel lane][channel], 256/cvs * C == 2048 entries
+  const int cvs = y.c >> 3;
+  const int cv = threadIdx.x % cvs, pl = threadIdx.x / cvs, PL = 256 / cvs;
+  const int c0 = cv * 8;
+  const int split = blockIdx.x, n = blockIdx.y;
   const int hw = y.h * y.w;
   const int per = (hw + splits - 1) / splits;
   const int p_begin = split * per, p_end = min(hw, p_begin + per);
@@ -550,63 +552,62 @@ __global__ void __launch_bounds__(256)
   if (MODE == 1) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      if (coef && c0 < y.c) {
+      if (coef) {
         float4 q = coef[(long long)n * y.c + c0 + e];
         sc[e] = q.x; sh[e] = q.y;
       } else { sc[e] = 1.f; sh[e] = 0.f; }
     }
   }
-  if (c0 < y.c) {
-    for (int pb = p_begin + pl; pb < p_end; pb += 64 * PF) {
-      uint4 vy[PF], vd[PF];
-      int kind[PF], pys[PF], pxs[PF];
+  for (int pb = p_begin + pl; pb < p_end; pb += PL * PF) {
+    uint4 vy[PF], vd[PF];
+    int kind[PF], pys[PF], pxs[PF];
 #pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        const int p = pb + u * 64;
-        kind[u] = 0;
-        if (p < p_end) {
-          const int py = p / y.w, px = p - py * y.w;
-          pys[u] = py; pxs[u] = px;
-          vy[u] = ld16(yb + y.off(n, py, px) + c0);
-          kind[u] = 2;
-          if (MODE == 1) {
-            if (has_reflection(py, dout.h, dout.refl) || has_reflection(px, dout.w, dout.refl)) kind[u] = 3;
-            else vd[u] = ld16(db + dout.off(n, py, px) + c0);
-          }
+    for (int u = 0; u < PF; ++u) {
+      const int p = pb + u * PL;
+      kind[u] = 0;
+      if (p < p_end) {
+        const int py = p / y.w, px = p - py * y.w;
+        pys[u] = py; pxs[u] = px;
+        vy[u] = ld16(yb + y.off(n, py, px) + c0);
+        kind[u] = 2;
+        if (MODE == 1) {
+          if (has_reflection(py, dout.h, dout.refl) || has_reflection(px, dout.w, dout.refl)) kind[u] = 3;
+          else vd[u] = ld16(db + dout.off(n, py, px) + c0);
         }
       }
+    }
 #pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        if (kind[u] == 0) continue;
-        float v[8];
-        unpack8(vy[u], v);
-        if (MODE == 0) {
+    for (int u = 0; u < PF; ++u) {
+      if (kind[u] == 0) continue;
+      float v[8];
+      unpack8(vy[u], v);
+      if (MODE == 0) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { a0[e] += v[e]; a1[e] += v[e] * v[e]; }
-        } else {
-          float g[8];
-          if (kind[u] == 3) fold_read8<bf16>(dout, n, pys[u], pxs[u], c0, g);
-          else unpack8(vd[u], g);
+        for (int e = 0; e < 8; ++e) { a0[e] += v[e]; a1[e] += v[e] * v[e]; }
+      } else {
+        float g[8];
+        if (kind[u] == 3) fold_read8<bf16>(dout, n, pys[u], pxs[u], c0, g);
+        else unpack8(vd[u], g);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float dz = g[e] * act_grad(sc[e] * v[e] + sh[e], act);
-            a0[e] += dz; a1[e] += dz * v[e];
-          }
+        for (int e = 0; e < 8; ++e) {
+          float dz = g[e] * act_grad(sc[e] * v[e] + sh[e], act);
+          a0[e] += dz; a1[e] += dz * v[e];
         }
       }
     }
   }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { s0[pl][cv * 8 + e] = a0[e]; s1[pl][cv * 8 + e] = a1[e]; }
+  for (int e = 0; e < 8; ++e) red[pl * y.c + c0 + e] = make_float2(a0[e], a1[e]);
   __syncthreads();
-  if (threadIdx.x < 32) {
+  for (int c = threadIdx.x; c < y.c; c += 256) {
     float t0 = 0.f, t1 = 0.f;
-    for (int i = 0; i < 64; ++i) { t0 += s0[i][threadIdx.x]; t1 += s1[i][threadIdx.x]; }
-    int c = blockIdx.x * 32 + threadIdx.x;
-    if (c < y.c) out[((long long)n * splits + split) * y.c + c] = make_float2(t0, t1);
+    for (int i = 0; i < PL; ++i) {
+      const float2 v = red[i * y.c + c];
+      t0 += v.x; t1 += v.y;
+    }
+    out[((long long)n * splits + split) * y.c + c] = make_float2(t0, t1);
   }
 }
-
 
 // grid for the per-sample kernels: enough blocks per sample to fill the GPU ~8 CTAs deep
 static inline dim3 ps_grid(int npix, int cvs, int n) {
@@ -1303,9 +1304,12 @@ extern "C" int dwc_nc_stats(const dwc_hbuf_t* y, int splits, float* stats, dwc_s
   DWC_CHECK(y->c % 8 == 0 && y->layout == 0, "dwc_nc_stats: needs C %% 8 == 0 and plain layout");
   HB hy(*y);
   dim3 grid(cdiv(y->c, 32), splits, y->n);
-  if (y->dtype == DWC_BF16)
-    nc_reduce_fast_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(hy, hy, nullptr, 0, splits,
-                                                                  reinterpret_cast<float2*>(stats));
+  if (y->dtype == DWC_BF16 && ps_ok(y->c))
+    nc_reduce_fast_kernel<0><<<dim3(splits, y->n), 256, 0, as_stream(stream)>>>(hy, hy, nullptr, 0, splits,
+                                                                                reinterpret_cast<float2*>(stats));
+  else if (y->dtype == DWC_BF16)
+    nc_reduce_kernel<bf16, 0><<<grid, 256, 0, as_stream(stream)>>>(hy, hy, nullptr, 0, splits,
+                                                                   reinterpret_cast<float2*>(stats));
   else
     nc_reduce_kernel<float, 0><<<grid, 256, 0, as_stream(stream)>>>(hy, hy, nullptr, 0, splits,
                                                                     reinterpret_cast<float2*>(stats));
@@ -1321,9 +1325,12 @@ extern "C" int dwc_post_bwd_reduce(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, 
   HB hy(*y), hd(*dout);
   if (prefolded) hd.refl = 0;
   dim3 grid(cdiv(y->c, 32), splits, y->n);
-  if (y->dtype == DWC_BF16)
-    nc_reduce_fast_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(hy, hd, reinterpret_cast<const float4*>(coef), act,
-                                                                  splits, reinterpret_cast<float2*>(red));
+  if (y->dtype == DWC_BF16 && ps_ok(y->c))
+    nc_reduce_fast_kernel<1><<<dim3(splits, y->n), 256, 0, as_stream(stream)>>>(
+        hy, hd, reinterpret_cast<const float4*>(coef), act, splits, reinterpret_cast<float2*>(red));
+  else if (y->dtype == DWC_BF16)
+    nc_reduce_kernel<bf16, 1><<<grid, 256, 0, as_stream(stream)>>>(hy, hd, reinterpret_cast<const float4*>(coef), act,
+                                                                   splits, reinterpret_cast<float2*>(red));
   else
     nc_reduce_kernel<float, 1><<<grid, 256, 0, as_stream(stream)>>>(hy, hd, reinterpret_cast<const float4*>(coef), act,
                                                                     splits, reinterpret_cast<float2*>(red));

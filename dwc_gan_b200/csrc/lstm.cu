@@ -122,9 +122,19 @@ __global__ void __launch_bounds__(NTHR) lstm_layer_fwd_kernel(const FwdP p) {
         if (b0 == 0) {
           // h_{t-1} of this direction, all samples (written by the sibling CTAs before the last barrier)
           const float* hsrc = p.hbuf + ((long long)((s - 1) & 1) * 2 + dir) * B * H;
-          for (int i = tid; i < B * H; i += NTHR) {
-            const int b = i / H, k = i - b * H;
-            hs[b * HP + k] = __ldcg(hsrc + i);
+          if ((H & 3) == 0) {
+            const int H4 = H >> 2;
+            for (int i = tid; i < B * H4; i += NTHR) {
+              const int b = i / H4, k4 = i - b * H4;
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(hsrc + (long long)b * H) + k4);
+              float* d = hs + b * HP + 4 * k4;
+              d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+          } else {
+            for (int i = tid; i < B * H; i += NTHR) {
+              const int b = i / H, k = i - b * H;
+              hs[b * HP + k] = __ldcg(hsrc + i);
+            }
           }
           __syncthreads();
         }
@@ -251,9 +261,14 @@ __global__ void __launch_bounds__(NTHR) lstm_layer_bwd_kernel(const BwdP p) {
       for (int u = 0; u < UPC; ++u) acc[u] = 0.f;
       if (s > 0) {
         const float* src = p.dgates + (((long long)t_later * B + b0) * 2 + dir) * G;   // sample stride 2*G
-        for (int i = tid; i < nb * G; i += NTHR) {
-          const int b = i / G, g = i - b * G;
-          dgs[b * GP + g] = __ldcg(src + (long long)b * 2 * G + g);
+        {
+          const int G4 = G >> 2;                       // G = 4H is always a multiple of 4; rows are 16-byte aligned
+          for (int i = tid; i < nb * G4; i += NTHR) {
+            const int b = i / G4, g4 = i - b * G4;
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (long long)b * 2 * G) + g4);
+            float* d = dgs + b * GP + 4 * g4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+          }
         }
         __syncthreads();
         const int k0 = (warp * 2 + kh) * KW, k1 = min(G, k0 + KW);

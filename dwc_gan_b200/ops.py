@@ -105,8 +105,10 @@ def _call(fn_name, *args):
     L.check(getattr(L.lib(), fn_name)(*args), fn_name)
 
 
-def _stats_splits(hw):
-    return max(1, min(16, hw // 512))
+def _stats_splits(hw, n=1):
+    """Pixel-range splits of the per-(n,c) reductions: enough (split, sample) blocks to fill the GPU four deep, at
+    least 64 pixels per block."""
+    return max(1, min(64, hw // 64, -(-600 // max(1, n))))
 
 
 # --------------------------------------------------------------------------------------------
@@ -370,7 +372,7 @@ class PostFn(torch.autograd.Function):
         n, c, hw = y.n, y.c, y.h * y.w
         dev = y_t.device
         coef = None
-        splits = _stats_splits(hw)
+        splits = _stats_splits(hw, n)
         if kind != NORM_NONE:
             stats = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
             ys = yh.struct()

@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-DWC_HALO_K=3,5,7 timeout -k 10 600 python -m pytest tests/test_conv_gpu.py tests/test_rows_gpu.py -q -m gpu -n 4 --tb=short 2>&1 | tail -4
-for MT in 2 1; do echo "== halo aligned MT=$MT b16"; DWC_HALO_K=3,5,7 DWC_HALO_MT=$MT timeout -k 10 600 python tools/microbench.py --batch 16 --only G7,G8,G9 2>&1 | grep "^|" | grep -v wgrad; echo "== MT=$MT b48"; DWC_HALO_K=3,5,7 DWC_HALO_MT=$MT timeout -k 10 600 python tools/microbench.py --batch 48 --only G7,G8,G9,G10,G1d 2>&1 | grep "^|" | grep -v wgrad; done > gpurun_out/microbench_halo_aligned.log 2>&1; cat gpurun_out/microbench_halo_aligned.log
+timeout -k 10 900 python -m pytest tests/test_post_gpu.py tests/test_modules_gpu.py tests/test_step_gpu.py tests/test_graph_gpu.py -q -m gpu -n 4 --tb=short 2>&1 | grep -v "^frame\|python()\|Warning\|warnings.html\|detach()" | tail -12 > gpurun_out/t_net.log; tail -5 gpurun_out/t_net.log
+timeout -k 10 900 python tools/microbench.py --batch 48 --only NONE > gpurun_out/microbench_norm.log 2>&1; grep "^|" gpurun_out/microbench_norm.log | grep -v "finalize\|fold" || tail -5 gpurun_out/microbench_norm.log
+timeout -k 10 900 python bench.py --steps 10 --warmup 4 --no-cpu-baseline 2>&1 | grep -v Warn | tail -1 | tee gpurun_out/bench10.json
+timeout -k 10 900 python tools/timeline_step.py 16 2>&1 | grep -v Warn > gpurun_out/timeline.txt; head -45 gpurun_out/timeline.txt

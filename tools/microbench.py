@@ -128,7 +128,7 @@ def bench_post(n, c, hw, kind, peaks, halo_out=1, halo_dy=2):
     st = L.stream
     nbuf = max(2, min(16, int(400e6 // (n * hw * hw * c * 8)) + 1))
     E = n * hw * hw * c
-    splits = ops._stats_splits(hw * hw)
+    splits = ops._stats_splits(hw * hw, n)
     ys = [HB(torch.randn(n, hw, hw, c, device="cuda").to(bt), n, hw, hw, c, 0, 0) for _ in range(nbuf)]
     outs = [HB.empty(n, hw, hw, c, halo_out, 0, bt, "cuda") for _ in range(nbuf)]
     douts = [HB(torch.randn(HB.shape_of(n, hw, hw, c, halo_out, 0), device="cuda").to(bt), n, hw, hw, c, halo_out, 0)
