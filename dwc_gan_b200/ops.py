@@ -691,7 +691,7 @@ class L1Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
         _require_cuda(a)
-        assert a.shape == b.shape and a.stride() == b.stride(), (a.shape, b.shape, a.stride(), b.stride())
+        assert a.shape == b.shape and _same_layout(a, b), (a.shape, b.shape, a.stride(), b.stride())
         loss = torch.zeros(1, dtype=torch.float32, device=a.device)
         _call("dwc_l1_loss_fwd", L.ptr(a), L.dt(a), L.ptr(b), L.dt(b), L.i64(a.numel()), L.ptr(loss), L.stream())
         ctx.save_for_backward(a, b)
@@ -708,6 +708,11 @@ class L1Fn(torch.autograd.Function):
         return da, db
 
 
+def _same_layout(a, b):
+    """Equal strides on every dimension that has more than one element (size-1 dimensions carry arbitrary strides)."""
+    return all(sa == sb for sa, sb, n in zip(a.stride(), b.stride(), a.shape) if n > 1)
+
+
 def _dense(t):
     """The tensor itself if it is a dense (possibly permuted) block, else a contiguous copy."""
     return t if t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last) else t.contiguous()
@@ -715,7 +720,7 @@ def _dense(t):
 
 def l1_loss(a, b):
     a, b = _dense(a), _dense(b)
-    if a.stride() != b.stride():
+    if not _same_layout(a, b):
         a, b = a.contiguous(), b.contiguous()
     return L1Fn.apply(a, b)
 
