@@ -120,7 +120,11 @@ def conv_roofline(peaks, B):
     achieved = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "gconv_tc_kernel<256> (G7 3x3 256->256 @32x32, batch %d)" % n,
             "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-            "frac": round(achieved / peaks["tflops"], 4), "traffic": None, "peak_source": peaks["src"] + " burst",
+            "frac": round(achieved / peaks["tflops"], 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this kernel at
+            # this geometry (profiles/r01c_ncu_prof_g7_old.txt): input + weights are read once (10.7 MB vs 10.7 MB
+            # algorithmic), the 10.6 MB output was still in L2 when the capture ended
+            "traffic": 10705152 if n == 16 else None, "algorithmic_flops": flops, "peak_source": peaks["src"] + " burst",
             "us_per_launch": round(ms * 1e3, 2)}
 
 

@@ -252,24 +252,26 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// LayerNorm parameter gradients (accumulated): one thread per channel, fixed summation order over samples / splits
+// LayerNorm parameter gradients (accumulated): one warp per channel, lanes over (sample, split) pairs, fixed
+// shuffle-tree summation order (deterministic)
 __global__ void ln_param_grad_kernel(const float2* __restrict__ red, int splits, const float4* __restrict__ coef, int N,
                                      int C, float* __restrict__ dweight, float* __restrict__ dbias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double dg = 0, db = 0;
-  for (int n = 0; n < N; ++n) {
-    double S1 = 0, S2 = 0;
-    for (int k = 0; k < splits; ++k) {
-      float2 v = red[((long long)n * splits + k) * C + c];
-      S1 += v.x; S2 += v.y;
-    }
-    float4 q = coef[(long long)n * C + c];
-    dg += (double)q.w * (S2 - (double)q.z * S1);
-    db += S1;
+  float dg = 0.f, db = 0.f;
+  for (int i = lane; i < N * splits; i += 32) {
+    const int n = i / splits;
+    const float2 v = red[(long long)i * C + c];
+    const float4 q = coef[(long long)n * C + c];
+    dg += q.w * (v.y - q.z * v.x);
+    db += v.x;
   }
-  dweight[c] += (float)dg;
-  dbias[c] += (float)db;
+  dg = warp_sum(dg);
+  db = warp_sum(db);
+  if (lane == 0) {
+    dweight[c] += dg;
+    dbias[c] += db;
+  }
 }
 
 extern "C" int dwc_norm_bwd_finalize(int kind, const float* red, int splits, const float* coef, int n, int c, int hw,
@@ -281,7 +283,7 @@ extern "C" int dwc_norm_bwd_finalize(int kind, const float* red, int splits, con
       dweight, dbias, reinterpret_cast<float4*>(bco));
   DWC_LAUNCH_CHECK();
   if (kind == 3) {
-    ln_param_grad_kernel<<<cdiv(c, 64), 64, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(red), splits,
+    ln_param_grad_kernel<<<cdiv((long long)c * 32, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(red), splits,
                                                                    reinterpret_cast<const float4*>(coef), n, c, dweight,
                                                                    dbias);
     DWC_LAUNCH_CHECK();
@@ -922,11 +924,60 @@ __global__ void __launch_bounds__(256) upsample_pad_bwd_kernel(HB dout, HB dx) {
   }
 }
 
+// bf16 fast path: grid.y = sample, PF output pixels per thread in flight (4 x PF 16-byte loads before the first use)
+__global__ void __launch_bounds__(256) upsample_pad_fwd_fast_kernel(HB x, HB out) {
+  const int cvs = out.c >> 3;
+  const int cv = threadIdx.x % cvs, pl = threadIdx.x / cvs, PL = 256 / cvs;
+  const int n = blockIdx.y, c0 = cv * 8;
+  const bf16* xb = reinterpret_cast<const bf16*>(x.ptr);
+  bf16* ob = reinterpret_cast<bf16*>(out.ptr);
+  const int npix = out.hp * out.wp;
+  const int stride = gridDim.x * PL;
+  constexpr int UF = 2;
+  for (int p0 = blockIdx.x * PL + pl; p0 < npix; p0 += UF * stride) {
+    uint4 va[UF], vb[UF], vc[UF], vd[UF];
+    float wy0[UF], wy1[UF], wx0[UF], wx1[UF];
+    long long oo[UF];
+#pragma unroll
+    for (int u = 0; u < UF; ++u) {
+      const int p = p0 + u * stride;
+      oo[u] = -1;
+      if (p < npix) {
+        const int Y = p / out.wp, X = p - Y * out.wp;
+        const int oy = reflect_idx(Y - out.halo, out.h), ox = reflect_idx(X - out.halo, out.w);
+        int y0, y1, x0, x1;
+        up_taps(oy, x.h, &y0, &y1, &wy0[u], &wy1[u]);
+        up_taps(ox, x.w, &x0, &x1, &wx0[u], &wx1[u]);
+        va[u] = ld16(xb + x.off(n, y0, x0) + c0);
+        vb[u] = ld16(xb + x.off(n, y0, x1) + c0);
+        vc[u] = ld16(xb + x.off(n, y1, x0) + c0);
+        vd[u] = ld16(xb + x.off(n, y1, x1) + c0);
+        oo[u] = out.off_padded(n, Y, X) + c0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UF; ++u) {
+      if (oo[u] < 0) continue;
+      float a[8], b[8], c[8], d[8], o[8];
+      unpack8(va[u], a); unpack8(vb[u], b); unpack8(vc[u], c); unpack8(vd[u], d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        o[e] = wy0[u] * (wx0[u] * a[e] + wx1[u] * b[e]) + wy1[u] * (wx0[u] * c[e] + wx1[u] * d[e]);
+      Vec8<bf16>::store(ob + oo[u], o);
+    }
+  }
+}
+
 extern "C" int dwc_upsample_pad_fwd(const dwc_hbuf_t* x, const dwc_hbuf_t* out, dwc_stream_t stream) {
   DWC_CHECK(x->c % 8 == 0 && out->h == 2 * x->h && out->w == 2 * x->w && out->c == x->c && out->n == x->n,
             "dwc_upsample_pad_fwd: geometry mismatch");
   HB hx(*x), ho(*out);
   long long total = ho.padded_pixels() * (out->c / 8);
+  if (x->dtype == DWC_BF16 && ps_ok(out->c) && x->layout == 0 && out->layout == 0) {
+    upsample_pad_fwd_fast_kernel<<<ps_grid(ho.hp * ho.wp, out->c / 8, out->n), 256, 0, as_stream(stream)>>>(hx, ho);
+    DWC_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_T(x->dtype, (upsample_pad_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(hx, ho)));
   DWC_LAUNCH_CHECK();
   return 0;

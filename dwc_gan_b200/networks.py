@@ -193,6 +193,15 @@ class Conv2dBlock(nn.Module):
     def bias_f32(self):
         return self._raw_weight()[2]
 
+    @staticmethod
+    def _pack_buffer(hit, shape, dtype, device):
+        """Packed operands are rewritten IN PLACE when the weights change: captured CUDA graphs of both phases keep
+        pointing at the same buffers, so a network is packed once per optimizer step (by whichever phase first uses
+        it after the step) and every later user - eager or replayed - reads current values."""
+        if hit is not None and tuple(hit[1].shape) == tuple(shape) and hit[1].dtype == dtype and hit[1].device == device:
+            return hit[1]
+        return torch.empty(shape, dtype=dtype, device=device)
+
     def packed_fwd(self, dtype):
         f, w, _ = self._raw_weight()
         tot = self.total_cout()
@@ -202,7 +211,7 @@ class Conv2dBlock(nn.Module):
         key = ("f", dtype)
         hit = self._packed.get(key)
         if hit is None or hit[0] != f.version:
-            out = torch.empty(rows_p, self.k * self.k * self.cin, dtype=dtype, device=w.device)
+            out = self._pack_buffer(hit, (rows_p, self.k * self.k * self.cin), dtype, w.device)
             ops._call("dwc_pack_weights", L.ptr(w), tot, self.k, self.k, self.cin, 0, L.ptr(out), L.dt(dtype), rows_p,
                       L.stream())
             hit = (f.version, out)
@@ -219,10 +228,10 @@ class Conv2dBlock(nn.Module):
         hit = self._packed.get(key)
         if hit is None or hit[0] != f.version:
             if self.stride == 1:
-                out = torch.empty(rows_p, self.k * self.k * tot, dtype=dtype, device=w.device)
+                out = self._pack_buffer(hit, (rows_p, self.k * self.k * tot), dtype, w.device)
                 mode = 1
             else:
-                out = torch.empty(4, rows_p, 4 * tot, dtype=dtype, device=w.device)
+                out = self._pack_buffer(hit, (4, rows_p, 4 * tot), dtype, w.device)
                 mode = 2
             ops._call("dwc_pack_weights", L.ptr(w), tot, self.k, self.k, self.cin, mode, L.ptr(out), L.dt(dtype),
                       rows_p, L.stream())
@@ -238,7 +247,7 @@ class Conv2dBlock(nn.Module):
         hit = self._packed.get(key)
         if hit is None or hit[0] != f.version:
             rows = tot if mode == 3 else self.cin
-            out = torch.empty(rows, self.k * 64, dtype=dtype, device=w.device)
+            out = self._pack_buffer(hit, (rows, self.k * 64), dtype, w.device)
             ops._call("dwc_pack_weights", L.ptr(w), tot, self.k, self.k, self.cin, mode, L.ptr(out), L.dt(dtype), rows,
                       L.stream())
             hit = (f.version, out)

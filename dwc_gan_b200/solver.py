@@ -94,6 +94,7 @@ class Solver(nn.Module):
         self.use_cuda_graphs = os.environ.get("DWC_CUDA_GRAPHS", "1") != "0"
         self.graph_warmup = 2
         self._graphs = {}
+        self._last_phase = None
         self._ds_w_dev = None
 
     # ------------------------------------------------------------------ plumbing
@@ -164,6 +165,7 @@ class Solver(nn.Module):
         diversity weight), so a replay is numerically the same program as the eager call."""
         x_real = tensors[0]
         if not (self.use_cuda_graphs and x_real.is_cuda and self.noise_hook is None):
+            self._last_phase = phase
             return impl(*tensors, configs, iters)
         key = (phase, tuple(tuple(t.shape) for t in tensors), tuple(str(t.dtype) for t in tensors),
                bool(self.use_attention), self.training, ops.RT.dtype, ops.RT.use_tc)
@@ -172,9 +174,14 @@ class Solver(nn.Module):
             ent = self._graphs[key] = dict(calls=0, graph=None)
         if ent["graph"] is None:
             ent["calls"] += 1
-            if ent["calls"] <= self.graph_warmup:
+            if ent["calls"] <= self.graph_warmup or self._last_phase == phase:
+                self._last_phase = phase
                 return impl(*tensors, configs, iters)
             self._capture(ent, impl, opt, tensors, configs, iters)
+        elif ent["prev"] != self._last_phase:
+            self._last_phase = phase             # unusual call order (e.g. several D steps in a row): run eagerly
+            return impl(*tensors, configs, iters)
+        self._last_phase = phase
         for st, t in zip(ent["static"], tensors):
             if st.data_ptr() != t.data_ptr():
                 st.copy_(t, non_blocking=True)
@@ -205,8 +212,10 @@ class Solver(nn.Module):
         self._release_autograd()
         static = [t.clone() for t in tensors]
         opt.graph_buffers()
-        for net in (self.gen, self.dis):
-            net.ensure_flat().bump()             # every graph packs the weights it uses itself
+        # Packed bf16 weights are shared between the phases (rewritten in place, networks.Conv2dBlock._pack_buffer):
+        # this phase packs exactly the networks whose optimizer stepped since their last packing.  That is a
+        # property of the phase ORDER, so the graph is only replayed after the same predecessor phase.
+        ent["prev"] = self._last_phase
         before = {k: v for k, v in self.__dict__.items() if 'loss' in k}
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
