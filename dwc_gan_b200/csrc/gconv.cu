@@ -6,6 +6,7 @@
 //  * gconv_simt_kernel : CUDA-core version of the same abstract operation (fp32 validation mode, the
 //                        3-channel image layers and the 4-channel head gradients).
 #include "gconv.cuh"
+#include <stdlib.h>
 
 // =====================================================================================================
 // SIMT kernel: 128 x 64 tile, 256 threads, each thread 8 rows x 4 columns, fp32 accumulate
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) gconv_simt_kernel(const __grid_constant__
 // =====================================================================================================
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;   // bf16 elements = one 128-byte swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane quadrant)
 
 template <int BN> struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS)
   const int tile = blockIdx.x;
   const int col0 = blockIdx.y * BN;
   const int cblocks = p.C / TC_BK;
-  const int num_kb = p.ntaps * cblocks;
+  const int num_kb = p.debug == 3 ? 0 : p.ntaps * cblocks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS)
       const int x0 = tx * p.box_x, y0 = ty * p.box_y, n0 = tn * p.box_n;
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < p.ntaps; ++t) {
+      for (int t = 0; t < (p.debug == 3 ? 0 : p.ntaps); ++t) {
         const int cx = x0 + p.taps[t][0], cy = y0 + p.taps[t][1], cz = p.taps[t][2];
         for (int cb = 0; cb < cblocks; ++cb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -213,14 +214,63 @@ __global__ void __launch_bounds__(TC_THREADS)
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     constexpr int CHUNK = BN >= 32 ? 32 : 16;
+    const bool staged = BN >= 64 && p.out_dtype == DWC_BF16 && !p.accumulate && (p.ncols & 7) == 0 &&
+                        col0 + BN <= p.ncols && p.debug == 0;
+    if (staged) {
+      // Coalesced epilogue.  A thread owns one accumulator row, so storing straight from registers puts the 32 lanes
+      // of every store instruction on 32 different output rows (16 bytes each, >= 512 bytes apart).  Instead each
+      // warp stages its 32 rows x BN/2 columns (bf16, XOR-swizzled 16-byte pieces) in the now idle pipeline shared
+      // memory and writes whole row segments with consecutive lanes.  Two warps share a TMEM lane quadrant, each
+      // taking half of the columns.
+      constexpr int HB_ = BN / 2;                          // columns per warp
+      constexpr int PIECES = HB_ / 8;                      // 16-byte pieces per row segment (4, 8 or 16)
+      constexpr int RPI = 32 / PIECES;                     // rows per store instruction
+      constexpr int ROWB = HB_ * 2;
+      const int half = (warp - 2) >> 2;
+      const int cw0 = half * HB_;                          // first column of this warp inside the tile
+      uint8_t* stg = smem + (warp - 2) * (32 * ROWB);      // all MMAs have retired: the stage buffers are free
 #pragma unroll 1
-    for (int cc = 0; cc < BN; cc += CHUNK) {
+      for (int cc = 0; cc < HB_; cc += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cw0 + cc), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
+          if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cw0 + cc + j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cw0 + cc + j + 4));
+            f[0] = __uint_as_float(v[j]) + b0.x; f[1] = __uint_as_float(v[j + 1]) + b0.y;
+            f[2] = __uint_as_float(v[j + 2]) + b0.z; f[3] = __uint_as_float(v[j + 3]) + b0.w;
+            f[4] = __uint_as_float(v[j + 4]) + b1.x; f[5] = __uint_as_float(v[j + 5]) + b1.y;
+            f[6] = __uint_as_float(v[j + 6]) + b1.z; f[7] = __uint_as_float(v[j + 7]) + b1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+          }
+          const int piece = (cc + j) >> 3;
+          Vec8<bf16>::store(reinterpret_cast<bf16*>(stg + lane * ROWB + ((piece ^ (lane & (PIECES - 1))) << 4)), f);
+        }
+      }
+      __syncwarp();
+      bf16* outp = reinterpret_cast<bf16*>(p.out) + col0 + cw0;
+#pragma unroll 4
+      for (int i = 0; i < 32; i += RPI) {
+        const int rl = i + lane / PIECES, piece = lane % PIECES;
+        const long long roff = __shfl_sync(0xffffffffu, off, rl);
+        const int rv = __shfl_sync(0xffffffffu, (int)valid, rl);
+        const uint4 dv = *reinterpret_cast<const uint4*>(stg + rl * ROWB + ((piece ^ (rl & (PIECES - 1))) << 4));
+        if (rv) *reinterpret_cast<uint4*>(outp + roff + piece * 8) = dv;
+      }
+    } else if (warp < 6) {
+#pragma unroll 1
+    for (int cc = 0; cc < (p.debug == 2 ? 0 : BN); cc += CHUNK) {
       uint32_t v[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
       if (CHUNK == 32) tmem_ld32(taddr, v);
       else tmem_ld16(taddr, v);
       tmem_ld_wait();
-      if (valid) {
+      if (valid && p.debug != 1) {
         const int cbase = col0 + cc;
         if (p.out_dtype == DWC_BF16) {
           bf16* o = reinterpret_cast<bf16*>(p.out) + off + cbase;
@@ -258,6 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS)
           }
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -306,6 +357,14 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
   d.ntaps = g->ntaps; d.C = (int)g->a_dim[0]; d.K = g->ntaps * d.C;
   d.ncols = g->ncols; d.ncols_padded = g->ncols_padded;
   d.out_dtype = g->out_dtype; d.accumulate = g->accumulate;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("DWC_GCONV_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    d.debug = dbg;
+  }
   for (int t = 0; t < g->ntaps; ++t)
     for (int j = 0; j < 3; ++j) d.taps[t][j] = g->taps[t * 3 + j];
   cudaStream_t st = as_stream(stream);
@@ -321,8 +380,22 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
       DWC_CHECK(ks * ks == g->ntaps, "dwc_gconv(halo): ntaps %d is not a square window", g->ntaps);
       return dwc_launch_gconv_halo(g, d, ks, st);
     }
+    static int cg2 = -1;
+    if (cg2 < 0) {
+      const char* e = getenv("DWC_CG2");
+      cg2 = e ? atoi(e) : 0;
+    }
+    if (cg2 && ntiles >= 2) {
+      const int rc = dwc_launch_gconv_tc2(g, d, st);
+      if (rc >= 0) return rc;
+    }
     const int np = g->ncols_padded;
-    if (np % 256 == 0) return launch_tc<256>(g, d, st);
+    static int bn256 = -1;
+    if (bn256 < 0) {
+      const char* e = getenv("DWC_BN256");
+      bn256 = e ? atoi(e) : 1;
+    }
+    if (np % 256 == 0 && bn256) return launch_tc<256>(g, d, st);
     if (np % 128 == 0) return launch_tc<128>(g, d, st);
     if (np % 64 == 0) return launch_tc<64>(g, d, st);
     if (np == 16) return launch_tc<16>(g, d, st);

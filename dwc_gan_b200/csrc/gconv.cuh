@@ -16,6 +16,7 @@ struct GConvDev {
   int flat, flat_img, flat_pitch, flat_h, flat_w;
   int ntaps, C, K, ncols, ncols_padded;
   int out_dtype, accumulate;
+  int debug;             // diagnostics only (DWC_GCONV_DEBUG): 1 no stores, 2 no epilogue, 3 no mainloop
   int taps[DWC_MAX_TAPS][3];
 };
 
@@ -53,5 +54,7 @@ __device__ __forceinline__ bool out_offset(const GConvDev& p, const RowCoord& rc
 }
 
 
+// CTA-pair (cta_group::2) variant of the tap-by-tap kernel, gconv2.cu; -1 = geometry not handled
+int dwc_launch_gconv_tc2(const dwc_gconv_t* g, const GConvDev& d, cudaStream_t st);
 // launches the halo-tile tcgen05 kernel (stride-1 k x k windows); defined in gconv_halo.cu
 int dwc_launch_gconv_halo(const dwc_gconv_t* g, const GConvDev& d, int ksize, cudaStream_t st);
