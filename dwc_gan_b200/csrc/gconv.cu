@@ -320,6 +320,229 @@ __global__ void __launch_bounds__(TC_THREADS)
 }
 
 // =====================================================================================================
+// persistent tcgen05 kernel: one CTA per SM walks over (tile, column block) work items; the accumulator is
+// double-buffered in TMEM so that the epilogue of item i overlaps the main loop of item i+1 and the per-CTA
+// prologue (barrier init, TMEM allocation, descriptor prefetch) is paid once.  Used for multi-wave launches.
+// =====================================================================================================
+template <int BN> struct TcpCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int B_BYTES_AL = (B_BYTES + 1023) / 1024 * 1024;
+  // BN = 256: one CTA per SM (192 KB of stages, all 512 TMEM columns); narrower tiles: two CTAs per SM, i.e. two
+  // producer / MMA-issuer threads per SM as in the non-persistent kernel
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int CTAS_PER_SM = BN >= 256 ? 1 : 2;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES_AL) + 1024 + 512;
+  static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS)
+    gconv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ GConvDev p) {
+  using Cfg = TcpCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * (Cfg::A_BYTES + Cfg::B_BYTES_AL));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;        // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cblocks = p.C / TC_BK;
+  const int num_kb = p.ntaps * cblocks;
+  const int ntiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int ncb = (p.ncols_padded + BN - 1) / BN;
+  const int nitems = ntiles * ncb;                     // item = column block (fast) x tile: neighbours share the A tile in L2
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 8);                    // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile = item / ncb, col0 = (item - tile * ncb) * BN;
+        int tx = tile % p.tiles_x;
+        int t2 = tile / p.tiles_x;
+        int ty = t2 % p.tiles_y;
+        int tn = t2 / p.tiles_y;
+        const int x0 = tx * p.box_x, y0 = ty * p.box_y, n0 = tn * p.box_n;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int cx = x0 + p.taps[t][0], cy = y0 + p.taps[t][1], cz = p.taps[t][2];
+          for (int cb = 0; cb < cblocks; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+            tma_load_5d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * TC_BK, cx, cy, cz, n0);
+            tma_load_2d(sB + stage * Cfg::B_BYTES_AL, &tmB, &full_bar[stage], t * p.C + cb * TC_BK, col0);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN < 16 ? 16 : BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int li = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++li) {
+        const int acc = li & 1;
+        mbar_wait(&tmem_empty[acc], ((li >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + acc * Cfg::ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES_AL);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_addr, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ================= epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =========
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int HCOLS = Cfg::ACC_COLS / 2;             // columns per warp
+    constexpr int CHUNK = HCOLS >= 32 ? 32 : 16;
+    const int r = q * 32 + lane;
+    int li = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++li) {
+      const int tile = item / ncb, col0 = (item - tile * ncb) * BN;
+      const int acc = li & 1;
+      const RowCoord rc = tile_row(p, tile, r);
+      long long off = 0;
+      const bool valid = out_offset(p, rc, &off);
+      mbar_wait(&tmem_full[acc], (li >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < HCOLS; cc += CHUNK) {
+        uint32_t v[32];
+        __syncwarp();                                    // reconverge after the divergent store path below
+        const int ccol = half * HCOLS + cc;              // column inside the tile
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS + ccol);
+        if (CHUNK == 32) tmem_ld32(taddr, v);
+        else tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        if (cc + CHUNK >= HCOLS) {
+          // last TMEM read of this warp: hand the accumulator back to the MMA warp before the global stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (!valid) continue;
+        const int cbase = col0 + ccol;
+        if (p.out_dtype == DWC_BF16) {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + off + cbase;
+          if (cbase + CHUNK <= p.ncols && (p.ncols & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; j += 8) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+              if (p.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (p.accumulate) {
+                float old[8];
+                Vec8<bf16>::load(o + j, old);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += old[e];
+              }
+              Vec8<bf16>::store(o + j, f);
+            }
+          } else {
+            for (int j = 0; j < CHUNK; ++j) {
+              if (cbase + j < p.ncols) {
+                float f = __uint_as_float(v[j]) + (p.bias ? p.bias[cbase + j] : 0.f);
+                if (p.accumulate) f += __bfloat162float(o[j]);
+                o[j] = __float2bfloat16_rn(f);
+              }
+            }
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + off + cbase;
+          for (int j = 0; j < CHUNK; ++j) {
+            if (cbase + j < p.ncols) {
+              float f = __uint_as_float(v[j]) + (p.bias ? p.bias[cbase + j] : 0.f);
+              if (p.accumulate) f += o[j];
+              o[j] = f;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_tcp(const dwc_gconv_t* g, const GConvDev& d, int nitems, cudaStream_t st) {
+  using Cfg = TcpCfg<BN>;
+  CUtensorMap tmA, tmB;
+  if (dwc_make_tmap5(&tmA, g->a, g->a_dim, g->a_str, g->box[0], g->box[1], 1, g->box[2])) return 1;
+  if (dwc_make_tmap2(&tmB, g->w, g->ncols_padded, d.K, d.K, BN, TC_BK)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DWC_CUDA(cudaFuncSetAttribute(gconv_tcp_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  const int slots = dwc_num_sms() * Cfg::CTAS_PER_SM;
+  const int grid = nitems < slots ? nitems : slots;
+  gconv_tcp_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, d);
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
 // host entry
 // =====================================================================================================
 template <int BN>
@@ -388,6 +611,22 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
     if (cg2 && ntiles >= 2) {
       const int rc = dwc_launch_gconv_tc2(g, d, st);
       if (rc >= 0) return rc;
+    }
+    {
+      static int persist = -1;
+      if (persist < 0) {
+        const char* e = getenv("DWC_PERSISTENT");
+        persist = e ? atoi(e) : 1;
+      }
+      const int npp = g->ncols_padded;
+      const int bnp = npp % 256 == 0 ? 256 : (npp % 128 == 0 ? 128 : (npp % 64 == 0 ? 64 : (npp == 16 ? 16 : 0)));
+      const int nitems = bnp ? (int)ntiles * cdiv(npp, bnp) : 0;
+      if (persist && bnp && nitems > dwc_num_sms() * (bnp >= 256 ? 1 : 2) && d.debug == 0) {   // more than one wave of CTAs
+        if (bnp == 256) return launch_tcp<256>(g, d, nitems, st);
+        if (bnp == 128) return launch_tcp<128>(g, d, nitems, st);
+        if (bnp == 64) return launch_tcp<64>(g, d, nitems, st);
+        return launch_tcp<16>(g, d, nitems, st);
+      }
     }
     const int np = g->ncols_padded;
     static int bn256 = -1;
