@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(TC_THREADS)
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
   const int col0 = blockIdx.y * BN;
+  const int ph = blockIdx.z;                       // phase: weights ph*ncols_padded rows down, output ph*phase_out_off on
   const int cblocks = p.C / TC_BK;
   const int num_kb = p.debug == 3 ? 0 : p.ntaps * cblocks;
 
@@ -171,7 +172,8 @@ __global__ void __launch_bounds__(TC_THREADS)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
           tma_load_5d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * TC_BK, cx, cy, cz, n0);
-          tma_load_2d(sB + stage * Cfg::B_BYTES_AL, &tmB, &full_bar[stage], t * p.C + cb * TC_BK, col0);
+          tma_load_2d(sB + stage * Cfg::B_BYTES_AL, &tmB, &full_bar[stage], t * p.C + cb * TC_BK,
+                      col0 + ph * p.ncols_padded);
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS)
     const RowCoord rc = tile_row(p, tile, r);
     long long off = 0;
     const bool valid = out_offset(p, rc, &off);
+    off += ph * p.phase_out_off;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     constexpr int CHUNK = BN >= 32 ? 32 : 16;
@@ -359,7 +362,8 @@ __global__ void __launch_bounds__(TC_THREADS)
   const int num_kb = p.ntaps * cblocks;
   const int ntiles = p.tiles_x * p.tiles_y * p.tiles_n;
   const int ncb = (p.ncols_padded + BN - 1) / BN;
-  const int nitems = ntiles * ncb;                     // item = column block (fast) x tile: neighbours share the A tile in L2
+  const int per_phase = ntiles * ncb;                  // item = column block (fast) x tile x phase (slow)
+  const int nitems = per_phase * p.nphase;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -386,7 +390,8 @@ __global__ void __launch_bounds__(TC_THREADS)
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int tile = item / ncb, col0 = (item - tile * ncb) * BN;
+        const int ph = item / per_phase, it2 = item - ph * per_phase;
+        const int tile = it2 / ncb, col0 = (it2 - tile * ncb) * BN + ph * p.ncols_padded;
         int tx = tile % p.tiles_x;
         int t2 = tile / p.tiles_x;
         int ty = t2 % p.tiles_y;
@@ -448,11 +453,13 @@ __global__ void __launch_bounds__(TC_THREADS)
     const int r = q * 32 + lane;
     int li = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++li) {
-      const int tile = item / ncb, col0 = (item - tile * ncb) * BN;
+      const int ph = item / per_phase, it2 = item - ph * per_phase;
+      const int tile = it2 / ncb, col0 = (it2 - tile * ncb) * BN;
       const int acc = li & 1;
       const RowCoord rc = tile_row(p, tile, r);
       long long off = 0;
       const bool valid = out_offset(p, rc, &off);
+      off += ph * p.phase_out_off;
       mbar_wait(&tmem_full[acc], (li >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -529,7 +536,7 @@ static int launch_tcp(const dwc_gconv_t* g, const GConvDev& d, int nitems, cudaS
   using Cfg = TcpCfg<BN>;
   CUtensorMap tmA, tmB;
   if (dwc_make_tmap5(&tmA, g->a, g->a_dim, g->a_str, g->box[0], g->box[1], 1, g->box[2])) return 1;
-  if (dwc_make_tmap2(&tmB, g->w, g->ncols_padded, d.K, d.K, BN, TC_BK)) return 1;
+  if (dwc_make_tmap2(&tmB, g->w, (int64_t)g->ncols_padded * d.nphase, d.K, d.K, BN, TC_BK)) return 1;
   static bool attr_set = false;
   if (!attr_set) {
     DWC_CUDA(cudaFuncSetAttribute(gconv_tcp_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -550,13 +557,13 @@ static int launch_tc(const dwc_gconv_t* g, const GConvDev& d, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   CUtensorMap tmA, tmB;
   if (dwc_make_tmap5(&tmA, g->a, g->a_dim, g->a_str, g->box[0], g->box[1], 1, g->box[2])) return 1;
-  if (dwc_make_tmap2(&tmB, g->w, g->ncols_padded, d.K, d.K, BN, TC_BK)) return 1;
+  if (dwc_make_tmap2(&tmB, g->w, (int64_t)g->ncols_padded * d.nphase, d.K, d.K, BN, TC_BK)) return 1;
   static bool attr_set = false;
   if (!attr_set) {
     DWC_CUDA(cudaFuncSetAttribute(gconv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
-  dim3 grid(d.tiles_x * d.tiles_y * d.tiles_n, cdiv(g->ncols_padded, BN));
+  dim3 grid(d.tiles_x * d.tiles_y * d.tiles_n, cdiv(g->ncols_padded, BN), d.nphase);
   gconv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, d);
   DWC_LAUNCH_CHECK();
   return 0;
@@ -568,6 +575,23 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
   const bool halo = g->backend == DWC_TC_HALO || g->backend == DWC_TC_HALO1;
   DWC_CHECK(halo || g->box[0] * g->box[1] * g->box[2] == 128, "dwc_gconv: box must cover 128 rows");
   DWC_CHECK(g->a_str[0] == 1, "dwc_gconv: channel stride must be 1");
+  const int nphase = g->nphase > 1 ? g->nphase : 1;
+  if (nphase > 1) {
+    const bool tc_ok = g->backend == DWC_TC && getenv("DWC_CG2") == nullptr &&
+                       g->phase_w_off == (int64_t)g->ncols_padded * g->ntaps * g->a_dim[0];
+    if (!tc_ok) {
+      // kernels without phase support: one launch per phase
+      const int64_t wes = g->dtype == DWC_BF16 ? 2 : 4, oes = g->out_dtype == DWC_BF16 ? 2 : 4;
+      for (int ph = 0; ph < nphase; ++ph) {
+        dwc_gconv_t q = *g;
+        q.nphase = 1;
+        q.w = reinterpret_cast<const char*>(g->w) + ph * g->phase_w_off * wes;
+        q.out = reinterpret_cast<char*>(g->out) + ph * g->phase_out_off * oes;
+        if (dwc_gconv(&q, stream)) return 1;
+      }
+      return 0;
+    }
+  }
   GConvDev d;
   memset(&d, 0, sizeof(d));
   d.a = g->a; d.w = g->w; d.bias = g->bias; d.out = g->out;
@@ -580,6 +604,7 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
   d.ntaps = g->ntaps; d.C = (int)g->a_dim[0]; d.K = g->ntaps * d.C;
   d.ncols = g->ncols; d.ncols_padded = g->ncols_padded;
   d.out_dtype = g->out_dtype; d.accumulate = g->accumulate;
+  d.nphase = nphase; d.phase_out_off = g->phase_out_off;
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -620,7 +645,7 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
       }
       const int npp = g->ncols_padded;
       const int bnp = npp % 256 == 0 ? 256 : (npp % 128 == 0 ? 128 : (npp % 64 == 0 ? 64 : (npp == 16 ? 16 : 0)));
-      const int nitems = bnp ? (int)ntiles * cdiv(npp, bnp) : 0;
+      const int nitems = bnp ? (int)ntiles * cdiv(npp, bnp) * d.nphase : 0;
       if (persist && bnp && nitems > dwc_num_sms() * (bnp >= 256 ? 1 : 2) && d.debug == 0) {   // more than one wave of CTAs
         if (bnp == 256) return launch_tcp<256>(g, d, nitems, st);
         if (bnp == 128) return launch_tcp<128>(g, d, nitems, st);

@@ -16,6 +16,8 @@ struct GConvDev {
   int flat, flat_img, flat_pitch, flat_h, flat_w;
   int ntaps, C, K, ncols, ncols_padded;
   int out_dtype, accumulate;
+  int nphase;            // >= 1
+  long long phase_out_off;   // element offset of a phase's output; its weights start ncols_padded rows further down
   int debug;             // diagnostics only (DWC_GCONV_DEBUG): 1 no stores, 2 no epilogue, 3 no mainloop
   int taps[DWC_MAX_TAPS][3];
 };

@@ -116,6 +116,9 @@ class GConvPlan:
     o_str: Tuple[int, int, int]
     accumulate: bool = False
     backend: int = L.SIMT
+    nphase: int = 1                # independent problems sharing A / tiling / taps (stride-2 dgrad parity phases)
+    phase_w_off: int = 0           # element offset of phase ph's weights: w_off + ph * phase_w_off
+    phase_out_off: int = 0         # element offset of phase ph's output: out_off + ph * phase_out_off
 
     def launch(self):
         g = L.GConv()
@@ -140,6 +143,7 @@ class GConvPlan:
         g.o_str = (C.c_int64 * 3)(*self.o_str)
         g.out_dtype = L.dt(self.out)
         g.accumulate = int(self.accumulate)
+        g.nphase, g.phase_w_off, g.phase_out_off = self.nphase, self.phase_w_off, self.phase_out_off
         L.check(L.lib().dwc_gconv(C.byref(g), L.stream()), "gconv")
 
 
@@ -304,12 +308,13 @@ def plan_conv_dgrad(dy: HB, w_packed, dxp: HB, k, stride, backend, cin_padded=No
         hq, wq = dxp.hp // 2, dxp.wp // 2
         taps = [(i * dy.wp + j, 0, 0) for i in range(2) for j in range(2)]
         kk = 4 * cout
-        for phase in range(4):
-            plans.append(GConvPlan(a=dy.t, a_off=0, a_dim=a_dim, a_str=a_str, box=(128, 1, 1), tiles=tiles,
-                                   valid=(rows, 1, dy.n), flat=(1, dy.hp * dy.wp, dy.wp, hq, wq), taps=taps,
-                                   w=w_packed, w_off=phase * cin_padded * kk, ncols=cin, ncols_padded=cin_padded,
-                                   bias=None, out=dxp.t, out_off=phase * hq * wq * cin,
-                                   o_str=(cin, wq * cin, 4 * hq * wq * cin), backend=backend))
+        # the four parity phases of the padded input share dy, the tiling and the 2x2 taps: one launch
+        plans.append(GConvPlan(a=dy.t, a_off=0, a_dim=a_dim, a_str=a_str, box=(128, 1, 1), tiles=tiles,
+                               valid=(rows, 1, dy.n), flat=(1, dy.hp * dy.wp, dy.wp, hq, wq), taps=taps,
+                               w=w_packed, w_off=0, ncols=cin, ncols_padded=cin_padded,
+                               bias=None, out=dxp.t, out_off=0,
+                               o_str=(cin, wq * cin, 4 * hq * wq * cin), backend=backend,
+                               nphase=4, phase_w_off=cin_padded * kk, phase_out_off=hq * wq * cin))
     return plans
 
 

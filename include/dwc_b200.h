@@ -77,6 +77,13 @@ typedef struct {
   int64_t o_str[3];     /* element strides of out for x, y, n (columns contiguous) */
   int32_t out_dtype;
   int32_t accumulate;   /* out += ... */
+  /* Phases: nphase (0 or 1 = single) independent problems that share A, the tiling and the taps; phase ph uses the
+   * weight matrix at w + ph*phase_w_off elements and writes to out + ph*phase_out_off elements.  The four parity
+   * phases of a stride-2 data gradient are one launch this way. */
+  int32_t nphase;
+  int32_t reserved0;
+  int64_t phase_w_off;
+  int64_t phase_out_off;
 } dwc_gconv_t;
 
 int dwc_gconv(const dwc_gconv_t* p, dwc_stream_t stream);

@@ -30,6 +30,15 @@ def _gather(storage, off, dims, strs, x, y, z, n, cols):
 
 
 def emu_gconv(plan):
+    import copy
+    if getattr(plan, "nphase", 1) > 1:
+        for ph in range(plan.nphase):
+            q = copy.copy(plan)
+            q.nphase = 1
+            q.w_off = plan.w_off + ph * plan.phase_w_off
+            q.out_off = plan.out_off + ph * plan.phase_out_off
+            emu_gconv(q)
+        return
     a = plan.a.reshape(-1).double()
     C = plan.a_dim[0]
     x, y, n = _rows(plan)
