@@ -968,6 +968,64 @@ __global__ void __launch_bounds__(256) upsample_pad_fwd_fast_kernel(HB x, HB out
   }
 }
 
+// bf16 fast path of the backward: gradient already folded into the interior (refl == 0); one input pixel per thread
+// iteration, its 4 x 4 candidate output pixels loaded together (16 x 16-byte loads in flight)
+__global__ void __launch_bounds__(256) upsample_pad_bwd_fast_kernel(HB dout, HB dx) {
+  const int cvs = dx.c >> 3;
+  const int cv = threadIdx.x % cvs, pl = threadIdx.x / cvs, PL = 256 / cvs;
+  const int n = blockIdx.y, c0 = cv * 8;
+  const bf16* db = reinterpret_cast<const bf16*>(dout.ptr);
+  bf16* dxb = reinterpret_cast<bf16*>(dx.ptr);
+  const int npix = dx.hp * dx.wp;
+  for (int p = blockIdx.x * PL + pl; p < npix; p += gridDim.x * PL) {
+    const int Y = p / dx.wp, X = p - Y * dx.wp;
+    const int iy = Y - dx.halo, ix = X - dx.halo;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    if (iy >= 0 && iy < dx.h && ix >= 0 && ix < dx.w) {
+      float wy[4], wx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int oy = 2 * iy - 1 + j, ox = 2 * ix - 1 + j;
+        wy[j] = 0.f;
+        wx[j] = 0.f;
+        if (oy >= 0 && oy < dout.h) {
+          int a, b;
+          float w0, w1;
+          up_taps(oy, dx.h, &a, &b, &w0, &w1);
+          wy[j] = (a == iy ? w0 : 0.f) + (b == iy ? w1 : 0.f);
+        }
+        if (ox >= 0 && ox < dout.w) {
+          int a, b;
+          float w0, w1;
+          up_taps(ox, dx.w, &a, &b, &w0, &w1);
+          wx[j] = (a == ix ? w0 : 0.f) + (b == ix ? w1 : 0.f);
+        }
+      }
+      uint4 v[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int oy = min(max(2 * iy - 1 + j, 0), dout.h - 1), ox = min(max(2 * ix - 1 + i, 0), dout.w - 1);
+          v[j * 4 + i] = ld16(db + dout.off(n, oy, ox) + c0);      // clamped address; weight is 0 outside
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float w = wy[j] * wx[i];
+          float g[8];
+          unpack8(v[j * 4 + i], g);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, g[e], acc[e]);
+        }
+    }
+    Vec8<bf16>::store(dxb + dx.off_padded(n, Y, X) + c0, acc);
+  }
+}
+
 extern "C" int dwc_upsample_pad_fwd(const dwc_hbuf_t* x, const dwc_hbuf_t* out, dwc_stream_t stream) {
   DWC_CHECK(x->c % 8 == 0 && out->h == 2 * x->h && out->w == 2 * x->w && out->c == x->c && out->n == x->n,
             "dwc_upsample_pad_fwd: geometry mismatch");
@@ -987,6 +1045,11 @@ extern "C" int dwc_upsample_pad_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* dx
             "dwc_upsample_pad_bwd: geometry mismatch");
   HB hd(*dout), hx(*dx);
   if (prefolded) hd.refl = 0;
+  if (dx->dtype == DWC_BF16 && hd.refl == 0 && ps_ok(dx->c) && dx->layout == 0 && dout->layout == 0) {
+    upsample_pad_bwd_fast_kernel<<<ps_grid(hx.hp * hx.wp, dx->c / 8, dx->n), 256, 0, as_stream(stream)>>>(hd, hx);
+    DWC_LAUNCH_CHECK();
+    return 0;
+  }
   long long total = hx.padded_pixels() * (dx->c / 8);
   DISPATCH_T(dx->dtype, (upsample_pad_bwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(hd, hx)));
   DWC_LAUNCH_CHECK();

@@ -7,6 +7,7 @@
 //  * wgrad_simt_kernel : CUDA-core version (fp32 validation mode and the 3 / 4 channel layers).
 //  Partial sums are written to a workspace and reduced in a fixed order (deterministic).
 #include "common.cuh"
+#include <stdlib.h>
 
 struct WgradDev {
   const void* m_ptr;   // operand whose channels become accumulator rows
@@ -19,6 +20,9 @@ struct WgradDev {
   int ntiles, splits, tiles_per_split;
   int ntaps;
   float* ws;           // [split][tap][cm][cn]
+  int ngroup;          // taps per item on the N operand (1 = classic); > 1: N boxes are the SAME channels of `ngroup`
+                       // taps, read at pixel - tap (the M operand is untapped and the tiles walk ITS pixel grid)
+  int ntaps_total;     // real tap count (items cover ceil(ntaps_total / ngroup) groups)
   int taps[DWC_MAX_TAPS][3];
 };
 
@@ -146,11 +150,11 @@ __global__ void __launch_bounds__(WG_THREADS)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mblocks = p.cm / MR, nblocks = p.cn / BN;
+  const int mblocks = p.cm / MR, nblocks = p.ngroup > 1 ? 1 : p.cn / BN;
   int wid = blockIdx.x;
   const int mb = wid % mblocks; wid /= mblocks;
   const int nb = wid % nblocks; wid /= nblocks;
-  const int t = wid;
+  const int t = wid;                 // tap, or tap group when p.ngroup > 1
   const int split = blockIdx.y;
   const int tile_begin = split * p.tiles_per_split;
   const int tile_end = min(p.ntiles, tile_begin + p.tiles_per_split);
@@ -173,10 +177,15 @@ __global__ void __launch_bounds__(WG_THREADS)
 
   if (warp == 0) {
     if (lane == 0) {
-      const int mdx = p.m_tap ? p.taps[t][0] : 0, mdy = p.m_tap ? p.taps[t][1] : 0, mdz = p.m_tap ? p.taps[t][2] : 0;
-      const int ndx = p.n_tap ? p.taps[t][0] : 0, ndy = p.n_tap ? p.taps[t][1] : 0, ndz = p.n_tap ? p.taps[t][2] : 0;
+      const bool grp = p.ngroup > 1;
+      const int mdx = (p.m_tap && !grp) ? p.taps[t][0] : 0, mdy = (p.m_tap && !grp) ? p.taps[t][1] : 0,
+                mdz = (p.m_tap && !grp) ? p.taps[t][2] : 0;
+      const int ndx = (p.n_tap && !grp) ? p.taps[t][0] : 0, ndy = (p.n_tap && !grp) ? p.taps[t][1] : 0,
+                ndz = (p.n_tap && !grp) ? p.taps[t][2] : 0;
       int stage = 0;
       uint32_t phase = 0;
+      // (an L2 prefetch of the tiles ahead of the ring - cp.async.bulk.prefetch.tensor - was measured to slow every
+      // geometry down by 1.4-1.8x: the extra TMA instructions compete with the loads themselves)
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         int x0, y0, n0;
         wg_tile_origin(p, tile, &x0, &y0, &n0);
@@ -186,10 +195,22 @@ __global__ void __launch_bounds__(WG_THREADS)
 #pragma unroll
         for (int j = 0; j < MR / 64; ++j)
           tma_load_5d(s + j * WG_BOX_BYTES, &tmM, &full_bar[stage], mb * MR + j * 64, x0 + mdx, y0 + mdy, mdz, n0);
+        if (p.ngroup > 1) {
+          const int bpt = (BN / 64) / p.ngroup;          // 64-channel boxes per tap
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j)
-          tma_load_5d(s + Cfg::M_BYTES + j * WG_BOX_BYTES, &tmN, &full_bar[stage], nb * BN + j * 64, x0 + ndx,
-                      y0 + ndy, ndz, n0);
+          for (int j = 0; j < BN / 64; ++j) {
+            const int tj = t * p.ngroup + j / bpt;
+            // taps beyond the real count read far outside the tensor (zero fill): their accumulator columns are unused
+            const int sx = tj < p.ntaps_total ? x0 - p.taps[tj][0] : -(1 << 20);
+            const int sy = tj < p.ntaps_total ? y0 - p.taps[tj][1] : 0;
+            tma_load_5d(s + Cfg::M_BYTES + j * WG_BOX_BYTES, &tmN, &full_bar[stage], (j % bpt) * 64, sx, sy, 0, n0);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_5d(s + Cfg::M_BYTES + j * WG_BOX_BYTES, &tmN, &full_bar[stage], nb * BN + j * 64, x0 + ndx,
+                        y0 + ndy, ndz, n0);
+        }
         if (++stage == Cfg::STAGES) {
           stage = 0;
           phase ^= 1;
@@ -228,7 +249,34 @@ __global__ void __launch_bounds__(WG_THREADS)
     const int m = MR == 128 ? mb * 128 + q * 32 + lane : mb * 64 + q * 16 + (lane & 15);
     const bool row_ok = MR == 128 || lane < 16;
     float* ws = p.ws + (((long long)split * p.ntaps + t) * p.cm + m) * p.cn + nb * BN;
-    if (tile_end > tile_begin) {
+    if (p.ngroup > 1 && tile_end > tile_begin) {
+      // grouped taps: accumulator column c = (tap within the group, channel); cn channels per tap
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+        tmem_ld_wait();
+        const int tj = t * p.ngroup + cc / p.cn, ch = cc % p.cn;
+        if (row_ok && tj < p.ntaps_total) {
+          float* w2 = p.ws + (((long long)split * p.ntaps_total + tj) * p.cm + m) * p.cn + ch;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(w2 + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+        }
+      }
+    } else if (p.ngroup > 1) {
+      for (int cc = 0; cc < BN; cc += 32) {
+        const int tj = t * p.ngroup + cc / p.cn, ch = cc % p.cn;
+        if (row_ok && tj < p.ntaps_total) {
+          float* w2 = p.ws + (((long long)split * p.ntaps_total + tj) * p.cm + m) * p.cn + ch;
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(w2 + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else if (tile_end > tile_begin) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
 #pragma unroll 1
@@ -340,10 +388,14 @@ __global__ void dbias_final_kernel(const float* part, int ca, float* dbias, int 
 struct WgPlan {
   bool swap;
   int cm, cn, bn, mr, splits, tiles_per_split, ntiles, items;
+  int ngroup;                       // > 1: tap-grouped N operand (see WgradDev::ngroup)
+  int box[3], tiles[3];             // pixel boxes / tile counts actually used (grouped mode re-tiles the M grid)
 };
 
 static int wg_plan(const dwc_wgrad_t* g, WgPlan* pl) {
   pl->ntiles = g->tiles[0] * g->tiles[1] * g->tiles[2];
+  pl->ngroup = 1;
+  for (int i = 0; i < 3; ++i) { pl->box[i] = g->box[i]; pl->tiles[i] = g->tiles[i]; }
   if (g->backend == DWC_TC) {
     // accumulator rows need a multiple of 128 channels
     DWC_CHECK(g->ca % 64 == 0 && g->cb % 64 == 0, "dwc_wgrad: tcgen05 needs channel counts (%d,%d) %% 64 == 0", g->ca,
@@ -355,6 +407,35 @@ static int wg_plan(const dwc_wgrad_t* g, WgPlan* pl) {
     pl->bn = pl->cn % 256 == 0 ? 256 : (pl->cn % 128 == 0 ? 128 : 64);
     if (pl->mr == 64) pl->bn = 64;
     pl->items = (pl->cm / pl->mr) * (pl->cn / pl->bn) * g->ntaps;
+    // Few output channels (cout 64 / 128 after the operand swap: N would be 64 / 128 wide and every M = 128 MMA is
+    // bound by its shared-memory A read): put 256 / cout taps side by side in N.  dW[co,tap,ci] = sum_p' dY[p'-tap,co]
+    // X[p',ci]: X is read untapped over ITS (padded) pixel grid, dY at p' - tap (zero outside, by TMA fill).
+    static int grp_on = -1;
+    if (grp_on < 0) {
+      const char* e = getenv("DWC_WGRAD_GROUP");
+      grp_on = e ? atoi(e) : 1;
+    }
+    bool plain = g->remap_axis == 0 && g->ntaps >= 4;
+    for (int t = 0; t < g->ntaps && plain; ++t)
+      plain = g->taps[t * 3 + 2] == 0 && g->taps[t * 3] >= 0 && g->taps[t * 3 + 1] >= 0;
+    if (grp_on && pl->swap && plain && pl->mr == 128 && (pl->cn == 64 || pl->cn == 128) && g->b_dim[3] == 1) {
+      pl->ngroup = 256 / pl->cn;
+      pl->bn = 256;
+      pl->items = (pl->cm / 128) * cdiv(g->ntaps, pl->ngroup);
+      // 64-pixel boxes over the M operand's grid (b = padded input) with the least padding
+      const long long W = g->b_dim[1], H = g->b_dim[2];
+      long long best = -1;
+      for (int bx = 64; bx >= 8; bx >>= 1) {
+        const int by = 64 / bx;
+        const long long area = (long long)cdiv(W, bx) * bx * cdiv(H, by) * by;
+        if (best < 0 || area < best) {
+          best = area;
+          pl->box[0] = bx; pl->box[1] = by; pl->box[2] = 1;
+        }
+      }
+      pl->tiles[0] = cdiv(W, pl->box[0]); pl->tiles[1] = cdiv(H, pl->box[1]); pl->tiles[2] = (int)g->b_dim[4];
+      pl->ntiles = pl->tiles[0] * pl->tiles[1] * pl->tiles[2];
+    }
   } else {
     pl->swap = false;
     pl->cm = g->ca;
@@ -386,11 +467,11 @@ static int launch_wg_tc(const dwc_wgrad_t* g, const WgradDev& d, const WgPlan& p
   using Cfg = WgCfg<BN, MR>;
   CUtensorMap tmM, tmN;
   const bool sw = pl.swap;
-  if (dwc_make_tmap5(&tmM, sw ? g->b : g->a, sw ? g->b_dim : g->a_dim, sw ? g->b_str : g->a_str, g->box[0], g->box[1],
-                     1, g->box[2]))
+  if (dwc_make_tmap5(&tmM, sw ? g->b : g->a, sw ? g->b_dim : g->a_dim, sw ? g->b_str : g->a_str, pl.box[0], pl.box[1],
+                     1, pl.box[2]))
     return 1;
-  if (dwc_make_tmap5(&tmN, sw ? g->a : g->b, sw ? g->a_dim : g->b_dim, sw ? g->a_str : g->b_str, g->box[0], g->box[1],
-                     1, g->box[2]))
+  if (dwc_make_tmap5(&tmN, sw ? g->a : g->b, sw ? g->a_dim : g->b_dim, sw ? g->a_str : g->b_str, pl.box[0], pl.box[1],
+                     1, pl.box[2]))
     return 1;
   static bool attr_set = false;
   if (!attr_set) {
@@ -428,10 +509,12 @@ extern "C" int dwc_wgrad(const dwc_wgrad_t* g, dwc_stream_t stream) {
   d.m_tap = sw ? 1 : 0;
   d.n_tap = sw ? 0 : 1;
   d.cm = pl.cm; d.cn = pl.cn;
-  d.box_x = g->box[0]; d.box_y = g->box[1]; d.box_n = g->box[2];
-  d.tiles_x = g->tiles[0]; d.tiles_y = g->tiles[1]; d.tiles_n = g->tiles[2];
+  d.box_x = pl.box[0]; d.box_y = pl.box[1]; d.box_n = pl.box[2];
+  d.tiles_x = pl.tiles[0]; d.tiles_y = pl.tiles[1]; d.tiles_n = pl.tiles[2];
   d.ntiles = pl.ntiles; d.splits = pl.splits; d.tiles_per_split = pl.tiles_per_split;
-  d.ntaps = g->ntaps;
+  d.ntaps = pl.ngroup > 1 ? cdiv(g->ntaps, pl.ngroup) : g->ntaps;
+  d.ngroup = pl.ngroup;
+  d.ntaps_total = g->ntaps;
   d.ws = g->workspace;
   for (int t = 0; t < g->ntaps; ++t)
     for (int j = 0; j < 3; ++j) d.taps[t][j] = g->taps[t * 3 + j];

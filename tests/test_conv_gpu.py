@@ -49,6 +49,8 @@ CASES = [
     (3, 8, 8, 512, 512, 4, 2, 1),
     (3, 16, 16, 256, 512, 4, 2, 1),
     (2, 16, 16, 64, 4, 7, 1, 3),
+    (2, 16, 16, 128, 64, 5, 1, 2),      # G9 geometry: tap-grouped weight gradient (N = 4 taps x 64 channels)
+    (3, 20, 12, 128, 64, 3, 1, 1),
 ]
 MODES = [("simt", torch.float32), ("simt", torch.bfloat16), ("tc", torch.bfloat16)]
 
