@@ -795,6 +795,276 @@ extern "C" int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, c
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Fused InstanceNorm / AdaIN sites for small feature maps (H*W <= 1536: the 32x32 residual blocks, i.e. most norm
+// sites of the network).  One CTA owns a (sample, channel group) slab that fits in shared memory, so the site is ONE
+// kernel and ONE read of its inputs: forward = statistics + coefficients + normalise/activation/residual/reflect pad;
+// backward = reflect fold + per-channel reductions + coefficients + apply.  (The three-pass kernels above read the
+// tensors twice and need two more launches for the coefficients.)
+// ---------------------------------------------------------------------------------------------------
+template <int CG>
+__global__ void __launch_bounds__(256)
+    post_fused_fwd_kernel(HB y, int kind, const float* __restrict__ weight, const float* __restrict__ bias, float eps,
+                          int act, HB res, int has_res, HB out, float4* __restrict__ coef_out) {
+  extern __shared__ __align__(16) uint8_t fsm[];
+  constexpr int CVS = CG / 8, PL = 256 / CVS;
+  const int hw = y.h * y.w;
+  bf16* slab = reinterpret_cast<bf16*>(fsm);                         // [hw][CG]
+  float2* red = reinterpret_cast<float2*>(fsm + (size_t)hw * CG * 2);  // [PL][CG]
+  float2* scoef = red + PL * CG;                                      // [CG] scale, shift
+  const int cv = threadIdx.x % CVS, pl = threadIdx.x / CVS;
+  const int n = blockIdx.y, cbase = blockIdx.x * CG, c0 = cbase + cv * 8;
+  const bf16* yb = reinterpret_cast<const bf16*>(y.ptr);
+  float a0[8], a1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a0[e] = a1[e] = 0.f;
+  for (int pb = pl; pb < hw; pb += PL * PF) {
+    uint4 v[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int p = pb + u * PL;
+      if (p < hw) {
+        const int py = p / y.w, px = p - py * y.w;
+        v[u] = ld16(yb + y.off(n, py, px) + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int p = pb + u * PL;
+      if (p < hw) {
+        *reinterpret_cast<uint4*>(slab + (size_t)p * CG + cv * 8) = v[u];
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a0[e] += f[e]; a1[e] += f[e] * f[e]; }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[pl * CG + cv * 8 + e] = make_float2(a0[e], a1[e]);
+  __syncthreads();
+  if (threadIdx.x < CG) {
+    double s = 0, q = 0;
+    for (int i = 0; i < PL; ++i) {
+      const float2 t = red[i * CG + threadIdx.x];
+      s += t.x; q += t.y;
+    }
+    const int c = cbase + threadIdx.x;
+    const double mean = s / hw;
+    double var = q / hw - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float w = kind == 2 ? weight[(long long)n * y.c + c] : 1.f;
+    const float b = kind == 2 ? bias[(long long)n * y.c + c] : 0.f;
+    const float4 cf = make_float4(w * rstd, b - (float)mean * rstd * w, (float)mean, rstd);
+    coef_out[(long long)n * y.c + c] = cf;
+    scoef[threadIdx.x] = make_float2(cf.x, cf.y);
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float2 t = scoef[cv * 8 + e];
+    sc[e] = t.x; sh[e] = t.y;
+  }
+  const bf16* rb = reinterpret_cast<const bf16*>(res.ptr);
+  bf16* ob = reinterpret_cast<bf16*>(out.ptr);
+  const int npix = out.hp * out.wp;
+  for (int p = pl; p < npix; p += PL) {
+    const int Y = p / out.wp, X = p - Y * out.wp;
+    const int iy = reflect_idx(Y - out.halo, out.h), ix = reflect_idx(X - out.halo, out.w);
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(slab + (size_t)(iy * y.w + ix) * CG + cv * 8), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = act_fwd(sc[e] * v[e] + sh[e], act);
+    if (has_res) {
+      float rr[8];
+      unpack8(ld16(rb + res.off(n, iy, ix) + c0), rr);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += rr[e];
+    }
+    Vec8<bf16>::store(ob + out.off_padded(n, Y, X) + c0, v);
+  }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(256)
+    post_fused_bwd_kernel(HB dout, HB y, const float4* __restrict__ coef, int kind, int act,
+                          const float* __restrict__ weight, float* __restrict__ dweight, float* __restrict__ dbias,
+                          HB dy, HB dres, int has_dres) {
+  extern __shared__ __align__(16) uint8_t fsm[];
+  constexpr int CVS = CG / 8, PL = 256 / CVS;
+  const int hw = y.h * y.w;
+  bf16* ys = reinterpret_cast<bf16*>(fsm);                            // [hw][CG]
+  bf16* gs = ys + (size_t)hw * CG;                                    // [hw][CG] folded gradient
+  float2* red = reinterpret_cast<float2*>(fsm + (size_t)hw * CG * 4);  // [PL][CG]
+  float4* sbco = reinterpret_cast<float4*>(red + PL * CG);            // [CG] a, b, c
+  const int cv = threadIdx.x % CVS, pl = threadIdx.x / CVS;
+  const int n = blockIdx.y, cbase = blockIdx.x * CG, c0 = cbase + cv * 8;
+  const bf16* yb = reinterpret_cast<const bf16*>(y.ptr);
+  const bf16* db = reinterpret_cast<const bf16*>(dout.ptr);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float4 q = coef[(long long)n * y.c + c0 + e];
+    sc[e] = q.x; sh[e] = q.y;
+  }
+  float a0[8], a1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a0[e] = a1[e] = 0.f;
+  for (int pb = pl; pb < hw; pb += PL * PF) {
+    uint4 vy[PF], vd[PF];
+    int kind_u[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int p = pb + u * PL;
+      kind_u[u] = 0;
+      if (p < hw) {
+        const int py = p / y.w, px = p - py * y.w;
+        vy[u] = ld16(yb + y.off(n, py, px) + c0);
+        if (has_reflection(py, dout.h, dout.refl) || has_reflection(px, dout.w, dout.refl)) kind_u[u] = 3;
+        else {
+          kind_u[u] = 2;
+          vd[u] = ld16(db + dout.off(n, py, px) + c0);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      if (kind_u[u] == 0) continue;
+      const int p = pb + u * PL;
+      float v[8], g[8];
+      unpack8(vy[u], v);
+      if (kind_u[u] == 3) {
+        const int py = p / y.w, px = p - py * y.w;
+        fold_read8<bf16>(dout, n, py, px, c0, g);
+        Vec8<bf16>::store(gs + (size_t)p * CG + cv * 8, g);
+        Vec8<bf16>::load(gs + (size_t)p * CG + cv * 8, g);          // the folded gradient is a bf16 tensor (dres)
+      } else {
+        unpack8(vd[u], g);
+        *reinterpret_cast<uint4*>(gs + (size_t)p * CG + cv * 8) = vd[u];
+      }
+      *reinterpret_cast<uint4*>(ys + (size_t)p * CG + cv * 8) = vy[u];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dz = g[e] * act_grad(sc[e] * v[e] + sh[e], act);
+        a0[e] += dz; a1[e] += dz * v[e];
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[pl * CG + cv * 8 + e] = make_float2(a0[e], a1[e]);
+  __syncthreads();
+  if (threadIdx.x < CG) {
+    double S1 = 0, S2 = 0;
+    for (int i = 0; i < PL; ++i) {
+      const float2 t = red[i * CG + threadIdx.x];
+      S1 += t.x; S2 += t.y;
+    }
+    const int c = cbase + threadIdx.x;
+    const float4 q = coef[(long long)n * y.c + c];
+    const double mean = q.z, rstd = q.w;
+    const double w = kind == 2 ? (double)weight[(long long)n * y.c + c] : 1.0;
+    const double m1 = S1 / hw;
+    const double m2 = rstd * (S2 / hw - mean * m1);
+    if (kind == 2) {
+      dbias[(long long)n * y.c + c] = (float)S1;
+      dweight[(long long)n * y.c + c] = (float)(rstd * (S2 - mean * S1));
+    }
+    const double a = w * rstd;
+    const double b = -rstd * rstd * w * m2;
+    const double cc = -rstd * w * m1 - b * mean;
+    sbco[threadIdx.x] = make_float4((float)a, (float)b, (float)cc, 0.f);
+  }
+  __syncthreads();
+  float ba[8], bb[8], bc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float4 t = sbco[cv * 8 + e];
+    ba[e] = t.x; bb[e] = t.y; bc[e] = t.z;
+  }
+  const int hmax = max(dy.halo, has_dres ? dres.halo : 0);
+  const int HP = y.h + 2 * hmax, WP = y.w + 2 * hmax;
+  bf16* dyb = reinterpret_cast<bf16*>(dy.ptr);
+  bf16* drb = reinterpret_cast<bf16*>(dres.ptr);
+  for (int p = pl; p < HP * WP; p += PL) {
+    const int Y = p / WP, X = p - Y * WP;
+    const int iy = Y - hmax, ix = X - hmax;
+    float g[8], o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = o[e] = 0.f;
+    if (iy >= 0 && iy < y.h && ix >= 0 && ix < y.w) {
+      const size_t so = (size_t)(iy * y.w + ix) * CG + cv * 8;
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(ys + so), v);
+      unpack8(*reinterpret_cast<const uint4*>(gs + so), g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dz = g[e] * act_grad(sc[e] * v[e] + sh[e], act);
+        o[e] = ba[e] * dz + bb[e] * v[e] + bc[e];
+      }
+    }
+    {
+      const int py = iy + dy.halo, px = ix + dy.halo;
+      if (py >= 0 && py < dy.hp && px >= 0 && px < dy.wp) Vec8<bf16>::store(dyb + dy.off_padded(n, py, px) + c0, o);
+    }
+    if (has_dres) {
+      const int py = iy + dres.halo, px = ix + dres.halo;
+      if (py >= 0 && py < dres.hp && px >= 0 && px < dres.wp)
+        Vec8<bf16>::store(drb + dres.off_padded(n, py, px) + c0, g);
+    }
+  }
+}
+
+constexpr int FUSED_FWD_CG = 32, FUSED_BWD_CG = 16;
+constexpr int FUSED_MAX_HW = 1536;
+
+extern "C" int dwc_post_fused_ok(int c, int hw, int dtype) {
+  return dtype == DWC_BF16 && hw <= FUSED_MAX_HW && c % FUSED_FWD_CG == 0;
+}
+
+extern "C" int dwc_post_fused_fwd(const dwc_hbuf_t* y, int kind, const float* weight, const float* bias, float eps,
+                                  int act, const dwc_hbuf_t* res, const dwc_hbuf_t* out, float* coef,
+                                  dwc_stream_t stream) {
+  DWC_CHECK((kind == 1 || kind == 2) && dwc_post_fused_ok(y->c, y->h * y->w, y->dtype) && y->layout == 0,
+            "dwc_post_fused_fwd: unsupported site (kind %d, C %d, %dx%d)", kind, y->c, y->h, y->w);
+  DWC_CHECK(y->n == out->n && y->h == out->h && y->w == out->w && y->c == out->c && out->dtype == DWC_BF16,
+            "dwc_post_fused_fwd: geometry mismatch");
+  HB hy(*y), ho(*out), hr = res ? HB(*res) : HB(*y);
+  constexpr int CG = FUSED_FWD_CG;
+  const size_t smem = (size_t)y->h * y->w * CG * 2 + (256 / (CG / 8)) * CG * sizeof(float2) + CG * sizeof(float2);
+  static size_t attr = 0;
+  if (smem > attr) {
+    DWC_CUDA(cudaFuncSetAttribute(post_fused_fwd_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  post_fused_fwd_kernel<CG><<<dim3(y->c / CG, y->n), 256, smem, as_stream(stream)>>>(
+      hy, kind, weight, bias, eps, act, hr, res != nullptr, ho, reinterpret_cast<float4*>(coef));
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dwc_post_fused_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, int kind, int act,
+                                  const float* weight, float* dweight, float* dbias, const dwc_hbuf_t* dy,
+                                  const dwc_hbuf_t* dres, dwc_stream_t stream) {
+  DWC_CHECK((kind == 1 || kind == 2) && dwc_post_fused_ok(y->c, y->h * y->w, y->dtype) && y->layout == 0 &&
+                dy->layout == 0,
+            "dwc_post_fused_bwd: unsupported site (kind %d, C %d, %dx%d)", kind, y->c, y->h, y->w);
+  DWC_CHECK(dout->n == y->n && dout->h == y->h && dout->w == y->w && dout->c == y->c, "dwc_post_fused_bwd: geometry mismatch");
+  HB hd(*dout), hy(*y), hdy(*dy), hr = dres ? HB(*dres) : HB(*dy);
+  constexpr int CG = FUSED_BWD_CG;
+  const size_t smem = (size_t)y->h * y->w * CG * 4 + (256 / (CG / 8)) * CG * sizeof(float2) + CG * sizeof(float4);
+  static size_t attr = 0;
+  if (smem > attr) {
+    DWC_CUDA(cudaFuncSetAttribute(post_fused_bwd_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  post_fused_bwd_kernel<CG><<<dim3(y->c / CG, y->n), 256, smem, as_stream(stream)>>>(
+      hd, hy, reinterpret_cast<const float4*>(coef), kind, act, weight, dweight, dbias, hdy, hr, dres != nullptr);
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // In-place fold of a reflect halo's gradient into the interior: interior pixels whose mirror images lie in the halo
 // (a band of `halo` rows / columns next to each edge) take the sum of their reflections.  Only those band pixels are
 // visited; afterwards the backward passes stream the interior without any gather (refl = 0).

@@ -12,6 +12,7 @@ the hot path is one of our CUDA kernels.  Conventions:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -37,6 +38,7 @@ class Runtime:
         self.side_keep = []
         self.side_main = None
         self.use_side_stream = True
+        self.use_fused_norm = os.environ.get("DWC_FUSED_NORM", "1") != "0"
 
     def set_mode(self, mode: str):
         if mode == "bf16":
@@ -373,21 +375,29 @@ class PostFn(torch.autograd.Function):
         dev = y_t.device
         coef = None
         splits = _stats_splits(hw, n)
-        if kind != NORM_NONE:
-            stats = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
-            ys = yh.struct()
-            _call("dwc_nc_stats", C.byref(ys), splits, L.ptr(stats), L.stream())
-            coef = torch.empty(n * c * 4, dtype=torch.float32, device=dev)
-            if kind == NORM_ADAIN:
-                nw = nw.contiguous().float()
-                nb = nb.contiguous().float()
-            _call("dwc_norm_finalize", kind, L.ptr(stats), splits, n, c, hw, L.f32(eps), L.ptr(nw), L.ptr(nb),
-                  L.ptr(coef), L.stream())
+        fused = kind in (NORM_IN, NORM_ADAIN) and RT.use_fused_norm and \
+            bool(L.lib().dwc_post_fused_ok(c, hw, L.dt(y_t)))
         out = HB.empty(n, y.h, y.w, c, out_halo, out_layout, y_t.dtype, dev)
         ys, os_ = yh.struct(), out.struct()
         rs = HB(res_t, res.n, res.h, res.w, res.c, res.halo, res.layout).struct() if res is not None else None
-        _call("dwc_post_fwd", C.byref(ys), L.ptr(coef), act, C.byref(rs) if rs is not None else None, C.byref(os_),
-              L.stream())
+        if kind == NORM_ADAIN:
+            nw = nw.contiguous().float()
+            nb = nb.contiguous().float()
+        if fused:
+            # small feature map: statistics, coefficients and the normalise / activation / pad pass in one kernel
+            coef = torch.empty(n * c * 4, dtype=torch.float32, device=dev)
+            _call("dwc_post_fused_fwd", C.byref(ys), kind, L.ptr(nw), L.ptr(nb), L.f32(eps), act,
+                  C.byref(rs) if rs is not None else None, C.byref(os_), L.ptr(coef), L.stream())
+        else:
+            if kind != NORM_NONE:
+                stats = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
+                _call("dwc_nc_stats", C.byref(ys), splits, L.ptr(stats), L.stream())
+                coef = torch.empty(n * c * 4, dtype=torch.float32, device=dev)
+                _call("dwc_norm_finalize", kind, L.ptr(stats), splits, n, c, hw, L.f32(eps), L.ptr(nw), L.ptr(nb),
+                      L.ptr(coef), L.stream())
+            _call("dwc_post_fwd", C.byref(ys), L.ptr(coef), act, C.byref(rs) if rs is not None else None, C.byref(os_),
+                  L.stream())
+        ctx.fused = fused
         ctx.meta = (y.n, y.h, y.w, y.c, y.halo, kind, act, out_halo, out_layout, eps, splits,
                     (res.n, res.h, res.w, res.c, res.halo, res.layout) if res is not None else None)
         ctx.ln_mod = ln_mod
@@ -402,23 +412,7 @@ class PostFn(torch.autograd.Function):
         dout = HB(dout_t.contiguous(), n, h, w, c, out_halo, out_layout)
         yh = HB(y_t, n, h, w, c, yhalo, 0)
         ds, ys = dout.struct(), yh.struct()
-        pre = _prefold(dout)
-        bco = None
         dnw = dnb = None
-        if kind != NORM_NONE:
-            red = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
-            _call("dwc_post_bwd_reduce", C.byref(ds), C.byref(ys), L.ptr(coef), act, splits, L.ptr(red), pre, L.stream())
-            bco = torch.empty(n * c * 4, dtype=torch.float32, device=dev)
-            if kind == NORM_ADAIN:
-                dnw = torch.empty(n, c, dtype=torch.float32, device=dev)
-                dnb = torch.empty(n, c, dtype=torch.float32, device=dev)
-                gw, gb = dnw, dnb
-            elif kind == NORM_LN:
-                gw, gb = ctx.ln_mod.grad_buffers()
-            else:
-                gw = gb = None
-            _call("dwc_norm_bwd_finalize", kind, L.ptr(red), splits, L.ptr(coef), n, c, h * w, L.f32(eps), L.ptr(nw),
-                  L.ptr(gw), L.ptr(gb), L.ptr(bco), L.stream())
         dy = HB.empty(n, h, w, c, yhalo, 0, dout_t.dtype, dev)
         dys = dy.struct()
         dres = drs = None
@@ -426,8 +420,32 @@ class PostFn(torch.autograd.Function):
             dres = HB.empty(*res_meta[:5], res_meta[5], dout_t.dtype, dev)
             assert dres.layout == 0
             drs = dres.struct()
-        _call("dwc_post_bwd_apply", C.byref(ds), C.byref(ys), L.ptr(coef), L.ptr(bco), act, C.byref(dys),
-              C.byref(drs) if drs is not None else None, pre, L.stream())
+        if ctx.fused:
+            if kind == NORM_ADAIN:
+                dnw = torch.empty(n, c, dtype=torch.float32, device=dev)
+                dnb = torch.empty(n, c, dtype=torch.float32, device=dev)
+            _call("dwc_post_fused_bwd", C.byref(ds), C.byref(ys), L.ptr(coef), kind, act, L.ptr(nw), L.ptr(dnw),
+                  L.ptr(dnb), C.byref(dys), C.byref(drs) if drs is not None else None, L.stream())
+        else:
+            pre = _prefold(dout) if kind != NORM_NONE else 0     # one pass only: gather the reflections in it
+            bco = None
+            if kind != NORM_NONE:
+                red = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
+                _call("dwc_post_bwd_reduce", C.byref(ds), C.byref(ys), L.ptr(coef), act, splits, L.ptr(red), pre,
+                      L.stream())
+                bco = torch.empty(n * c * 4, dtype=torch.float32, device=dev)
+                if kind == NORM_ADAIN:
+                    dnw = torch.empty(n, c, dtype=torch.float32, device=dev)
+                    dnb = torch.empty(n, c, dtype=torch.float32, device=dev)
+                    gw, gb = dnw, dnb
+                elif kind == NORM_LN:
+                    gw, gb = ctx.ln_mod.grad_buffers()
+                else:
+                    gw = gb = None
+                _call("dwc_norm_bwd_finalize", kind, L.ptr(red), splits, L.ptr(coef), n, c, h * w, L.f32(eps), L.ptr(nw),
+                      L.ptr(gw), L.ptr(gb), L.ptr(bco), L.stream())
+            _call("dwc_post_bwd_apply", C.byref(ds), C.byref(ys), L.ptr(coef), L.ptr(bco), act, C.byref(dys),
+                  C.byref(drs) if drs is not None else None, pre, L.stream())
         return (dy.t, dnw, dnb, dres.t if dres is not None else None, None, None, None, None, None, None, None, None,
                 None)
 

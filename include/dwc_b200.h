@@ -167,6 +167,17 @@ int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float*
 /* nn.Upsample(2, bilinear, align_corners=False) + reflect pad (networks_v2.py:154, networks.py:531). */
 int dwc_upsample_pad_fwd(const dwc_hbuf_t* x, const dwc_hbuf_t* out, dwc_stream_t stream);
 int dwc_upsample_pad_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* dx, int prefolded, dwc_stream_t stream);
+/* Fused InstanceNorm (kind 1) / AdaIN (kind 2) site for small feature maps (dwc_post_fused_ok: bf16, H*W <= 1536,
+ * C % 32 == 0): one kernel per site and direction, each (sample, channel group) slab staged once in shared memory.
+ * Forward = dwc_nc_stats + dwc_norm_finalize + dwc_post_fwd (also writes coef [N,C,4] for the backward);
+ * backward = dwc_fold_halo + dwc_post_bwd_reduce + dwc_norm_bwd_finalize + dwc_post_bwd_apply (dout is NOT modified).
+ * Same arithmetic as the separate passes (networks.py:514-522,545,693-722). */
+int dwc_post_fused_ok(int c, int hw, int dtype);
+int dwc_post_fused_fwd(const dwc_hbuf_t* y, int kind, const float* weight, const float* bias, float eps, int act,
+                       const dwc_hbuf_t* res, const dwc_hbuf_t* out, float* coef, dwc_stream_t stream);
+int dwc_post_fused_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, int kind, int act,
+                       const float* weight, float* dweight, float* dbias, const dwc_hbuf_t* dy,
+                       const dwc_hbuf_t* dres, dwc_stream_t stream);
 /* In-place backward of a reflect halo: every interior pixel whose mirror images lie in the halo receives their sum
  * (the halo itself is left as is).  After it the three backward passes above take prefolded = 1 and stream the
  * interior without gathering reflections.  Needs h, w >= 2*halo + 2. */
