@@ -3,6 +3,8 @@
 // image <-> haloed-buffer conversion, decoder heads, attention blend, global average pooling.
 // All are HBM-bound: 16-byte (bf16) / 32-byte (fp32) accesses along the channel axis, fp32 math.
 #include "common.cuh"
+#include "rowpipe.cuh"
+#include <stdlib.h>
 
 #define DISPATCH_T(dtype, ...)                     \
   do {                                             \
@@ -637,6 +639,16 @@ extern "C" int dwc_post_fwd(const dwc_hbuf_t* y, const float* coef, int act, con
             "dwc_post_fwd: plane layout needs even padded extent");
   HB hy(*y), ho(*out), hr = res ? HB(*res) : HB(*y);
   long long total = ho.padded_pixels() * (out->c / 8);
+  {
+    RowP rp;
+    if (rowpipe_geom(y, &rp.nseg, &rp.segw, &rp.segbytes) && out->dtype == DWC_BF16 && (!res || res->layout == 0) &&
+        out->halo <= y->h - 1 && out->halo <= y->w - 1) {
+      rp.y = hy; rp.d = hr; rp.o1 = ho; rp.o2 = ho;
+      rp.coef = reinterpret_cast<const float4*>(coef); rp.bco = nullptr; rp.part = nullptr;
+      rp.act = act; rp.has_d = res != nullptr; rp.has_o2 = 0;
+      return rowpipe_launch<RM_FWD>(rp, res ? 2 : 1, 0, y->n, as_stream(stream));
+    }
+  }
   if (ps_ok(out->c)) {
     if (y->dtype == DWC_BF16)
       post_fwd_fast_kernel<<<ps_grid(ho.hp * ho.wp, out->c / 8, out->n), 256, 0, as_stream(stream)>>>(
@@ -772,6 +784,17 @@ extern "C" int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, c
   DWC_CHECK(dout->n == y->n && dout->h == y->h && dout->w == y->w && dout->c == y->c, "dwc_post_bwd_apply: geometry mismatch");
   HB hd(*dout), hy(*y), hdy(*dy), hr = dres ? HB(*dres) : HB(*dy);
   if (prefolded) hd.refl = 0;
+  {
+    RowP rp;
+    if (rowpipe_geom(y, &rp.nseg, &rp.segw, &rp.segbytes) && (prefolded || dout->halo == 0) && dy->dtype == DWC_BF16 &&
+        dout->dtype == DWC_BF16 && (!dres || (dres->layout == 0 && dres->dtype == DWC_BF16)) &&
+        (dout->layout == 0 || rp.nseg == 1)) {
+      rp.y = hy; rp.d = hd; rp.o1 = hdy; rp.o2 = hr;
+      rp.coef = reinterpret_cast<const float4*>(coef); rp.bco = reinterpret_cast<const float4*>(bco); rp.part = nullptr;
+      rp.act = act; rp.has_d = 1; rp.has_o2 = dres != nullptr;
+      return rowpipe_launch<RM_BAPPLY>(rp, 2, 0, y->n, as_stream(stream));
+    }
+  }
   int hmax = dy->halo;
   if (dres && dres->halo > hmax) hmax = dres->halo;
   long long total = (long long)y->n * (y->h + 2 * hmax) * (y->w + 2 * hmax) * (y->c / 8);
@@ -1687,6 +1710,15 @@ extern "C" int dwc_heads_bwd_rows(const float* dimg, const float* datt, const fl
 extern "C" int dwc_nc_stats(const dwc_hbuf_t* y, int splits, float* stats, dwc_stream_t stream) {
   DWC_CHECK(y->c % 8 == 0 && y->layout == 0, "dwc_nc_stats: needs C %% 8 == 0 and plain layout");
   HB hy(*y);
+  {
+    RowP rp;
+    if (rowpipe_geom(y, &rp.nseg, &rp.segw, &rp.segbytes)) {
+      rp.y = hy; rp.d = hy; rp.o1 = hy; rp.o2 = hy;
+      rp.coef = nullptr; rp.bco = nullptr; rp.part = reinterpret_cast<float2*>(stats);
+      rp.act = 0; rp.has_d = 0; rp.has_o2 = 0;
+      return rowpipe_launch<RM_STATS>(rp, 1, splits, y->n, as_stream(stream));
+    }
+  }
   dim3 grid(cdiv(y->c, 32), splits, y->n);
   if (y->dtype == DWC_BF16 && ps_ok(y->c))
     nc_reduce_fast_kernel<0><<<dim3(splits, y->n), 256, 0, as_stream(stream)>>>(hy, hy, nullptr, 0, splits,
@@ -1708,6 +1740,16 @@ extern "C" int dwc_post_bwd_reduce(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, 
             "dwc_post_bwd_reduce: geometry mismatch");
   HB hy(*y), hd(*dout);
   if (prefolded) hd.refl = 0;
+  {
+    RowP rp;
+    if (rowpipe_geom(y, &rp.nseg, &rp.segw, &rp.segbytes) && (prefolded || dout->halo == 0) &&
+        (dout->layout == 0 || rp.nseg == 1)) {
+      rp.y = hy; rp.d = hd; rp.o1 = hy; rp.o2 = hy;
+      rp.coef = reinterpret_cast<const float4*>(coef); rp.bco = nullptr; rp.part = reinterpret_cast<float2*>(red);
+      rp.act = act; rp.has_d = 1; rp.has_o2 = 0;
+      return rowpipe_launch<RM_BRED>(rp, 2, splits, y->n, as_stream(stream));
+    }
+  }
   dim3 grid(cdiv(y->c, 32), splits, y->n);
   if (y->dtype == DWC_BF16 && ps_ok(y->c))
     nc_reduce_fast_kernel<1><<<dim3(splits, y->n), 256, 0, as_stream(stream)>>>(

@@ -1,0 +1,327 @@
+// Row-streaming bf16 versions of the HBM-bound norm passes (statistics, normalise + activation + residual + reflect pad,
+// backward reductions, backward apply).
+//
+// The per-thread 16-byte-load kernels in elementwise.cu are latency bound (ncu: 10-35 % of DRAM throughput at 20-40 %
+// occupancy, ~128 registers): the bytes a thread can keep in flight are tied to its registers.  Here the loads are 1-D
+// bulk copies (cp.async.bulk, the TMA engine without a tensor map) of whole image rows - W*C contiguous bf16, 16 KB at
+// every resolution of the 128x128 network - into a shared-memory ring guarded by mbarriers, issued by one thread
+// several rows ahead.  The 256 threads of the CTA consume a row from shared memory (conflict-free 16-byte reads), keep
+// their per-channel coefficients in registers and write results with fully contiguous 16-byte stores.
+// grid (row splits, N); a CTA owns a contiguous range of rows of one sample, all channels.
+#pragma once
+#include "common.cuh"
+
+enum { RM_STATS = 0, RM_BRED = 1, RM_FWD = 2, RM_BAPPLY = 3 };
+
+struct RowP {
+  HB y;            // primary input (plain layout, any halo): conv output
+  HB d;            // RM_BRED / RM_BAPPLY: upstream gradient (reflections already folded, or no halo); RM_FWD: residual
+  HB o1;           // RM_FWD: output (reflect halo, plain or parity planes); RM_BAPPLY: dy (zero halo)
+  HB o2;           // RM_BAPPLY: dres (zero halo)
+  const float4* coef;   // per (n,c): scale, shift, (mean, rstd)
+  const float4* bco;    // per (n,c): a, b, c of dy = a*dz + b*y + c
+  float2* part;         // RM_STATS / RM_BRED: [n][split][c]
+  int act, has_d, has_o2;
+  int nseg, segw, segbytes, stages;
+  int dbytes;      // bytes of the second operand per stage (0: none).  d in parity-plane layout: the two plane rows of the
+  int d_planes;    // padded row (even X, odd X), wq*C elements each, loaded whole (nseg == 1)
+};
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void rp_unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 rp_pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ float rp_act_fwd(float z, int act) {
+  if (act == 1) return z > 0.f ? z : 0.f;
+  if (act == 2) return z > 0.f ? z : 0.1f * z;
+  return z;
+}
+__device__ __forceinline__ float rp_act_grad(float z, int act) {
+  if (act == 1) return z > 0.f ? 1.f : 0.f;
+  if (act == 2) return z > 0.f ? 1.f : 0.1f;
+  return 1.f;
+}
+
+// zero the halo of row `iy` (left / right pixels), and the top / bottom halo rows when iy is the first / last row
+__device__ __forceinline__ void rp_zero_halo(const HB& b, int n, int iy, int cvs, int tid) {
+  if (b.halo == 0) return;
+  bf16* base = reinterpret_cast<bf16*>(b.ptr);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const int side = b.halo * cvs;
+  for (int q = tid; q < 2 * side; q += 256) {
+    const int r = q >= side ? q - side : q;
+    const int X = (q >= side ? b.halo + b.w : 0) + r / cvs;
+    *reinterpret_cast<uint4*>(base + b.off_padded(n, iy + b.halo, X) + (r % cvs) * 8) = z;
+  }
+  const int rowchunks = b.wp * cvs;
+  if (iy == 0) {
+    for (int q = tid; q < b.halo * rowchunks; q += 256) {
+      const int Y = q / rowchunks, r = q - Y * rowchunks;
+      *reinterpret_cast<uint4*>(base + b.off_padded(n, Y, r / cvs) + (r % cvs) * 8) = z;
+    }
+  }
+  if (iy == b.h - 1) {
+    for (int q = tid; q < b.halo * rowchunks; q += 256) {
+      const int Y = q / rowchunks, r = q - Y * rowchunks;
+      *reinterpret_cast<uint4*>(base + b.off_padded(n, b.halo + b.h + Y, r / cvs) + (r % cvs) * 8) = z;
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p) {
+  extern __shared__ __align__(128) uint8_t rsm[];
+  __shared__ uint64_t full[8];
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y;
+  const int H = p.y.h, W = p.y.w, C = p.y.c;
+  const int cvs = C >> 3, cv = tid % cvs, c0 = cv * 8;
+  const int nb = MODE == RM_STATS ? 1 : (MODE == RM_FWD ? (p.has_d ? 2 : 1) : 2);
+  const int S = p.stages;
+  // balanced contiguous row ranges (they differ by at most one row)
+  const int r0 = (int)(((long long)blockIdx.x * H) / gridDim.x), r1 = (int)(((long long)(blockIdx.x + 1) * H) / gridDim.x);
+  const int cnt = (r1 - r0) * p.nseg;
+  const int stage_bytes = p.segbytes + (nb == 2 ? p.dbytes : 0);
+  const bf16* yb = reinterpret_cast<const bf16*>(p.y.ptr);
+  const bf16* db = reinterpret_cast<const bf16*>(p.d.ptr);
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int i) {
+    const int u = r0 * p.nseg + i;
+    const int row = u / p.nseg, x0 = (u - row * p.nseg) * p.segw;
+    const int s = i % S;
+    uint8_t* dst = rsm + (size_t)s * stage_bytes;
+    mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+    bulk_load_1d(dst, yb + p.y.off(n, row, x0), (uint32_t)p.segbytes, &full[s]);
+    if (nb == 2) {
+      if (p.d_planes) {
+        const int Y = row + p.d.halo;
+        bulk_load_1d(dst + p.segbytes, db + p.d.off_padded(n, Y, 0), (uint32_t)(p.dbytes >> 1), &full[s]);
+        bulk_load_1d(dst + p.segbytes + (p.dbytes >> 1), db + p.d.off_padded(n, Y, 1), (uint32_t)(p.dbytes >> 1),
+                     &full[s]);
+      } else {
+        bulk_load_1d(dst + p.segbytes, db + p.d.off(n, row, x0), (uint32_t)p.segbytes, &full[s]);
+      }
+    }
+  };
+  // shared-memory byte offset (inside the d part of a stage) of chunk q = (pixel q / cvs, channel group cv)
+  auto d_off = [&](int q) -> size_t {
+    if (!p.d_planes) return (size_t)q * 16;
+    const int X = q / cvs + p.d.halo;
+    return ((size_t)((X & 1) * (p.d.wp >> 1) + (X >> 1)) * C + c0) * 2;
+  };
+  if (tid == 0)
+    for (int i = 0; i < S - 1 && i < cnt; ++i) issue(i);
+
+  // per-channel coefficients of this thread's 8 channels
+  float sc[8], sh[8], ba[8], bb[8], bc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = 1.f; sh[e] = 0.f; ba[e] = 1.f; bb[e] = 0.f; bc[e] = 0.f;
+  }
+  if (MODE != RM_STATS && p.coef) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float4 q = __ldg(p.coef + (long long)n * C + c0 + e);
+      sc[e] = q.x; sh[e] = q.y;
+    }
+  }
+  if (MODE == RM_BAPPLY && p.bco) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float4 q = __ldg(p.bco + (long long)n * C + c0 + e);
+      ba[e] = q.x; bb[e] = q.y; bc[e] = q.z;
+    }
+  }
+  float a0[8], a1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a0[e] = a1[e] = 0.f;
+
+  const int nchunks = p.segbytes >> 4;
+  const int act = p.act;
+  for (int i = 0; i < cnt; ++i) {
+    __syncthreads();                                   // everyone is done with unit i-1: its stage may be refilled
+    if (tid == 0 && i + S - 1 < cnt) issue(i + S - 1);
+    const int s = i % S;
+    mbar_wait(&full[s], (uint32_t)((i / S) & 1));
+    const uint8_t* sy = rsm + (size_t)s * stage_bytes;
+    const uint8_t* sd = sy + p.segbytes;
+    const int u = r0 * p.nseg + i;
+    const int row = u / p.nseg, x0 = (u - row * p.nseg) * p.segw;
+
+    if (MODE == RM_STATS) {
+      for (int q = tid; q < nchunks; q += 256) {
+        float v[8];
+        rp_unpack8(*reinterpret_cast<const uint4*>(sy + (size_t)q * 16), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a0[e] += v[e]; a1[e] += v[e] * v[e]; }
+      }
+    } else if (MODE == RM_BRED) {
+      for (int q = tid; q < nchunks; q += 256) {
+        float v[8], g[8];
+        rp_unpack8(*reinterpret_cast<const uint4*>(sy + (size_t)q * 16), v);
+        rp_unpack8(*reinterpret_cast<const uint4*>(sd + d_off(q)), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dz = g[e] * rp_act_grad(sc[e] * v[e] + sh[e], act);
+          a0[e] += dz; a1[e] += dz * v[e];
+        }
+      }
+    } else if (MODE == RM_FWD) {
+      bf16* ob = reinterpret_cast<bf16*>(p.o1.ptr);
+      const int halo = p.o1.halo;
+      int Ys[3], ny = 0;
+      Ys[ny++] = row + halo;
+      if (halo > 0) {
+        if (row >= 1 && row <= halo) Ys[ny++] = halo - row;
+        if (row >= H - 1 - halo && row <= H - 2) Ys[ny++] = halo + 2 * (H - 1) - row;
+      }
+      for (int q = tid; q < nchunks; q += 256) {
+        const int px = x0 + q / cvs;
+        float v[8];
+        rp_unpack8(*reinterpret_cast<const uint4*>(sy + (size_t)q * 16), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = rp_act_fwd(sc[e] * v[e] + sh[e], act);
+        if (p.has_d) {
+          float r[8];
+          rp_unpack8(*reinterpret_cast<const uint4*>(sd + (size_t)q * 16), r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] += r[e];
+        }
+        const uint4 o = rp_pack8(v);
+        int Xs[3], nx = 0;
+        Xs[nx++] = px + halo;
+        if (halo > 0) {
+          if (px >= 1 && px <= halo) Xs[nx++] = halo - px;
+          if (px >= W - 1 - halo && px <= W - 2) Xs[nx++] = halo + 2 * (W - 1) - px;
+        }
+        for (int a = 0; a < ny; ++a)
+          for (int b = 0; b < nx; ++b)
+            *reinterpret_cast<uint4*>(ob + p.o1.off_padded(n, Ys[a], Xs[b]) + c0) = o;
+      }
+    } else {
+      bf16* dyb = reinterpret_cast<bf16*>(p.o1.ptr);
+      bf16* drb = reinterpret_cast<bf16*>(p.o2.ptr);
+      for (int q = tid; q < nchunks; q += 256) {
+        const int px = x0 + q / cvs;
+        float v[8], g[8], o[8];
+        const uint4 gu = *reinterpret_cast<const uint4*>(sd + d_off(q));
+        rp_unpack8(*reinterpret_cast<const uint4*>(sy + (size_t)q * 16), v);
+        rp_unpack8(gu, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dz = g[e] * rp_act_grad(sc[e] * v[e] + sh[e], act);
+          o[e] = ba[e] * dz + bb[e] * v[e] + bc[e];
+        }
+        *reinterpret_cast<uint4*>(dyb + p.o1.off(n, row, px) + c0) = rp_pack8(o);
+        if (p.has_o2) *reinterpret_cast<uint4*>(drb + p.o2.off(n, row, px) + c0) = gu;
+      }
+      if (x0 == 0) {
+        rp_zero_halo(p.o1, n, row, cvs, tid);
+        if (p.has_o2) rp_zero_halo(p.o2, n, row, cvs, tid);
+      }
+    }
+  }
+
+  if (MODE == RM_STATS || MODE == RM_BRED) {
+    // block reduction over the pixel lanes (threads with the same channel group), through the drained ring
+    __syncthreads();
+    float2* red = reinterpret_cast<float2*>(rsm);      // [256 / cvs][C]
+    const int pl = tid / cvs, PL = 256 / cvs;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[pl * C + c0 + e] = make_float2(a0[e], a1[e]);
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int j = 0; j < PL; ++j) {
+        const float2 v = red[j * C + c];
+        t0 += v.x; t1 += v.y;
+      }
+      p.part[((long long)n * gridDim.x + blockIdx.x) * C + c] = make_float2(t0, t1);
+    }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+static inline bool rowpipe_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DWC_ROWPIPE");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0;
+}
+
+// geometry check + segmentation of a row into <= 16 KB pieces
+static inline bool rowpipe_geom(const dwc_hbuf_t* y, int* nseg, int* segw, int* segbytes) {
+  if (!rowpipe_enabled() || y->dtype != DWC_BF16 || y->layout != 0 || y->c % 8 != 0) return false;
+  const int cvs = y->c / 8;
+  if (cvs > 256 || 256 % cvs != 0) return false;
+  const long long rowbytes = (long long)y->w * y->c * 2;
+  if (rowbytes < 2048) return false;
+  int k = 1;
+  while (k <= y->w && !(y->w % k == 0 && rowbytes / k <= 16384)) ++k;
+  if (k > y->w) return false;
+  *nseg = k;
+  *segw = y->w / k;
+  *segbytes = (int)(rowbytes / k);
+  return (*segbytes % 16) == 0;
+}
+
+// row_splits <= 0: pick the split count so that the whole grid is ONE wave of resident CTAs (a CTA streams many rows, so
+// a partial second wave would cost as much as a full one)
+template <int MODE>
+static int rowpipe_launch(RowP& p, int nb, int row_splits, int n, cudaStream_t st) {
+  p.d_planes = 0;
+  p.dbytes = nb == 2 ? p.segbytes : 0;
+  if (nb == 2 && p.d.layout == 1) {
+    p.d_planes = 1;
+    p.dbytes = p.d.wp * p.d.c * 2;
+  }
+  const int stage_bytes = p.segbytes + p.dbytes;
+  int stages = 98304 / stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  size_t smem = (size_t)stages * stage_bytes;
+  if (smem < 16384) smem = 16384;                      // the reduction scratch needs 256 * 8 float2
+  static size_t attr = 0;
+  if (smem > attr) {
+    DWC_CUDA(cudaFuncSetAttribute(row_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  if (row_splits <= 0) {
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    row_splits = (per_sm * dwc_num_sms()) / n;
+    if (row_splits > p.y.h) row_splits = p.y.h;
+    if (row_splits < 1) row_splits = 1;
+  }
+  row_kernel<MODE><<<dim3(row_splits, n), 256, smem, st>>>(p);
+  DWC_LAUNCH_CHECK();
+  return 0;
+}

@@ -309,14 +309,55 @@ struct WgRemap {
   int axis, div, lo_limit, hi_limit;
   long long hi_stride, lo_stride;
 };
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int ntaps, int cm, int cn, float* dw,
-                                    long long s_m, long long s_t, long long s_n, int accumulate, WgRemap rm) {
+// One 32 (m) x 32 (n) tile of one tap per block: the partial tiles are read along n (contiguous in the workspace) with
+// four independent rows per thread in flight, summed over the splits in a fixed order, and written along whichever of
+// m / n is the unit-stride axis of dw (through a shared-memory transpose when that is m).
+__global__ void __launch_bounds__(256)
+    wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int ntaps, int cm, int cn, float* dw, long long s_m,
+                        long long s_t, long long s_n, int accumulate, WgRemap rm) {
+  __shared__ float tile[32][33];
   const long long total = (long long)ntaps * cm * cn;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int n = (int)(i % cn);
-    long long r = i / cn;
-    int m = (int)(r % cm);
-    int t = (int)(r / cm);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int t = blockIdx.z, m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  {
+    const int n = n0 + tx;
+    const float* q[4];
+    bool ok[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int m = m0 + ty + 8 * r;
+      ok[r] = m < cm && n < cn;
+      q[r] = ws + ((long long)t * cm + (ok[r] ? m : 0)) * cn + (ok[r] ? n : 0);
+    }
+    int k = 0;
+    for (; k + 4 <= splits; k += 4) {
+      float v[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[j][r] = ok[r] ? __ldg(q[r] + (k + j) * total) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s[r] += v[j][r];
+    }
+    for (; k < splits; ++k)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) s[r] += ok[r] ? __ldg(q[r] + k * total) : 0.f;
+  }
+  const bool along_m = s_m < s_n;            // which axis is contiguous in dw
+  if (along_m) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) tile[ty + 8 * r][tx] = s[r];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int m = along_m ? m0 + tx : m0 + ty + 8 * r;
+    const int n = along_m ? n0 + ty + 8 * r : n0 + tx;
+    if (m >= cm || n >= cn) continue;
+    const float v = along_m ? tile[tx][ty + 8 * r] : s[r];
     long long om = m * s_m, on = n * s_n;
     if (rm.axis == 1) {
       if (m % rm.div >= rm.lo_limit || m / rm.div >= rm.hi_limit) continue;
@@ -325,10 +366,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, in
       if (n % rm.div >= rm.lo_limit || n / rm.div >= rm.hi_limit) continue;
       on = (n / rm.div) * rm.hi_stride + (n % rm.div) * rm.lo_stride;
     }
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += ws[k * total + i];
     float* o = dw + om + t * s_t + on;
-    *o = accumulate ? (*o + s) : s;
+    *o = accumulate ? (*o + v) : v;
   }
 }
 
@@ -539,7 +578,8 @@ extern "C" int dwc_wgrad(const dwc_wgrad_t* g, dwc_stream_t stream) {
   rm.lo_limit = g->remap_lo_limit; rm.hi_limit = g->remap_hi_limit;
   rm.hi_stride = g->remap_hi_stride; rm.lo_stride = g->remap_lo_stride;
   const long long total = (long long)g->ntaps * pl.cm * pl.cn;
-  wgrad_reduce_kernel<<<cdiv(total, 256 * 4) > 1184 ? 1184 : cdiv(total, 256 * 4), 256, 0, st>>>(
+  DWC_CHECK(g->ntaps <= 65535 && cdiv(pl.cm, 32) <= 65535, "dwc_wgrad: reduce grid too large");
+  wgrad_reduce_kernel<<<dim3(cdiv(pl.cn, 32), cdiv(pl.cm, 32), g->ntaps), 256, 0, st>>>(
       g->workspace, pl.splits, g->ntaps, pl.cm, pl.cn, g->dw, sw ? g->s_b : g->s_a, g->s_t, sw ? g->s_a : g->s_b,
       g->accumulate, rm);
   DWC_LAUNCH_CHECK();

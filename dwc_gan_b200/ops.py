@@ -38,7 +38,7 @@ class Runtime:
         self.side_keep = []
         self.side_main = None
         self.use_side_stream = True
-        self.use_fused_norm = os.environ.get("DWC_FUSED_NORM", "1") != "0"
+        self.use_fused_norm = os.environ.get("DWC_FUSED_NORM", "0") != "0"   # opt-in: the row-streaming passes are faster
 
     def set_mode(self, mode: str):
         if mode == "bf16":
@@ -108,9 +108,10 @@ def _call(fn_name, *args):
 
 
 def _stats_splits(hw, n=1):
-    """Pixel-range splits of the per-(n,c) reductions: enough (split, sample) blocks to fill the GPU four deep, at
-    least 64 pixels per block."""
-    return max(1, min(64, hw // 64, -(-600 // max(1, n))))
+    """Splits of the per-(n,c) reductions: (split, sample) blocks that fill the GPU as ONE wave of two resident
+    CTAs per SM (the row-streaming kernels give each block a long contiguous range of rows, so a partial second wave
+    would cost a full one), at least 64 pixels per block."""
+    return max(1, min(64, hw // 64, 296 // max(1, n)))
 
 
 # --------------------------------------------------------------------------------------------

@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout -k 10 600 python -m pytest tests/test_post_gpu.py tests/test_modules_gpu.py tests/test_step_gpu.py tests/test_graph_gpu.py -q -m gpu --tb=short 2>&1 | grep -v "Warning\|warnings.html\|detach()" | tail -30
+timeout -k 10 900 python tools/timeline_step.py 16 2>&1 | grep -v Warn > gpurun_out/timeline.txt; head -60 gpurun_out/timeline.txt

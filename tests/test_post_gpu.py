@@ -38,6 +38,13 @@ CASES = [
     (2, 64, 32, 32, 3, 1, False, 3, 0, 4),
     (2, 64, 16, 16, 1, 1, False, 1, 1, 6),
     (2, 8, 2, 2, 0, 1, False, 1, 1, 1),
+    # rows of 16 KB (the row-streaming kernels at their in-network shapes), parity-plane output / gradient
+    (2, 64, 128, 128, 1, 1, False, 3, 1, 4),
+    (1, 128, 64, 64, 3, 1, False, 2, 0, 4),
+    (2, 256, 32, 32, 1, 1, True, 1, 0, 2),
+    # 32 KB rows: two segments per row
+    (1, 64, 8, 256, 1, 1, True, 1, 0, 2),
+    (1, 64, 6, 256, 3, 2, False, 2, 0, 1),
 ]
 
 
@@ -109,6 +116,17 @@ def test_post(n, c, h, w, kind, act, use_res, oh, ol, yh, mode):
     if kind == 3:
         assert (LN.gw.double().cpu() - nwr.grad).abs().max() < tol * 8 * nwr.grad.abs().max()
         assert (LN.gb.double().cpu() - nbr.grad).abs().max() < tol * 8 * nbr.grad.abs().max()
+
+
+@pytest.mark.parametrize("n,c,h,w,kind,act,use_res,oh,ol,yh", [c for c in CASES if c[4] in (1, 2)])
+def test_post_three_pass(n, c, h, w, kind, act, use_res, oh, ol, yh):
+    """The same sites with the single-kernel small-map path switched off: statistics / finalize / apply passes."""
+    old = ops.RT.use_fused_norm
+    ops.RT.use_fused_norm = False
+    try:
+        test_post(n, c, h, w, kind, act, use_res, oh, ol, yh, "bf16")
+    finally:
+        ops.RT.use_fused_norm = old
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
