@@ -63,6 +63,12 @@ class HBuf(C.Structure):
                 ("halo", C.c_int32), ("layout", C.c_int32), ("dtype", C.c_int32)]
 
 
+class PackEntry(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("cout", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+                ("cin", C.c_int32), ("mode", C.c_int32), ("rows_padded", C.c_int32), ("out_dtype", C.c_int32),
+                ("reserved", C.c_int32), ("total", C.c_int64)]
+
+
 EXPORTS = [
     "dwc_last_error", "dwc_abi_version", "dwc_tc_available", "dwc_gconv", "dwc_wgrad_workspace_bytes", "dwc_wgrad",
     "dwc_nc_stats", "dwc_norm_finalize", "dwc_post_fwd", "dwc_post_bwd_reduce", "dwc_norm_bwd_finalize",
@@ -71,7 +77,7 @@ EXPORTS = [
     "dwc_sgemm", "dwc_sgemm_ws", "dwc_sgemm_workspace_bytes", "dwc_colsum", "dwc_relu_bwd", "dwc_mul", "dwc_embed_concat_fwd", "dwc_embed_concat_bwd",
     "dwc_lstm_workspace_bytes", "dwc_lstm_layer_fwd", "dwc_lstm_layer_bwd", "dwc_transpose", "dwc_gmm_sample", "dwc_gmm_kl", "dwc_l1_loss_fwd", "dwc_l1_loss_bwd",
     "dwc_mse_const_loss_fwd", "dwc_mse_const_loss_bwd", "dwc_bce_logits_loss_fwd", "dwc_bce_logits_loss_bwd",
-    "dwc_adam_step", "dwc_ema_step", "dwc_pack_weights", "dwc_cast", "dwc_fill",
+    "dwc_adam_step", "dwc_ema_step", "dwc_pack_weights", "dwc_pack_weights_batch", "dwc_cast", "dwc_fill",
 ]
 
 

@@ -3,7 +3,6 @@
 // image <-> haloed-buffer conversion, decoder heads, attention blend, global average pooling.
 // All are HBM-bound: 16-byte (bf16) / 32-byte (fp32) accesses along the channel axis, fp32 math.
 #include "common.cuh"
-#include "rowpipe.cuh"
 #include <stdlib.h>
 
 #define DISPATCH_T(dtype, ...)                     \
@@ -396,6 +395,8 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 __device__ __forceinline__ bool has_reflection(int i, int size, int halo) {
   return halo > 0 && ((i >= 1 && i <= halo) || (i >= size - 1 - halo && i <= size - 2));
 }
+
+#include "rowpipe.cuh"
 
 __global__ void __launch_bounds__(256)
     post_fwd_fast_kernel(HB y, const float4* __restrict__ coef, int act, HB res, int has_res, HB out) {

@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(TC_THREADS)
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     constexpr int CHUNK = BN >= 32 ? 32 : 16;
-    const bool staged = BN >= 64 && p.out_dtype == DWC_BF16 && !p.accumulate && (p.ncols & 7) == 0 &&
-                        col0 + BN <= p.ncols && p.debug == 0;
+    const bool staged = BN >= 64 && p.out_dtype == DWC_BF16 && (p.ncols & 7) == 0 && col0 + BN <= p.ncols &&
+                        p.debug == 0;
     if (staged) {
       // Coalesced epilogue.  A thread owns one accumulator row, so storing straight from registers puts the 32 lanes
       // of every store instruction on 32 different output rows (16 bytes each, >= 512 bytes apart).  Instead each
@@ -263,7 +263,20 @@ __global__ void __launch_bounds__(TC_THREADS)
         const long long roff = __shfl_sync(0xffffffffu, off, rl);
         const int rv = __shfl_sync(0xffffffffu, (int)valid, rl);
         const uint4 dv = *reinterpret_cast<const uint4*>(stg + rl * ROWB + ((piece ^ (rl & (PIECES - 1))) << 4));
-        if (rv) *reinterpret_cast<uint4*>(outp + roff + piece * 8) = dv;
+        if (rv) {
+          uint4* dst = reinterpret_cast<uint4*>(outp + roff + piece * 8);
+          if (p.accumulate) {
+            // out += result: the sum of two bf16 tensors (e.g. the skip-connection gradient already in `out`)
+            float a[8], b[8];
+            Vec8<bf16>::load(reinterpret_cast<const bf16*>(&dv), a);
+            Vec8<bf16>::load(reinterpret_cast<const bf16*>(dst), b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] += b[e];
+            Vec8<bf16>::store(reinterpret_cast<bf16*>(dst), a);
+          } else {
+            *dst = dv;
+          }
+        }
       }
     } else if (warp < 6) {
 #pragma unroll 1

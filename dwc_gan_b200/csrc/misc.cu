@@ -213,53 +213,79 @@ extern "C" int dwc_ema_step(const float* param, float* avg, int64_t count, float
 // ---------------------------------------------------------------------------------------------------
 // weight packing (master fp32 [Cout][KH][KW][Cin] -> GEMM operands)
 // ---------------------------------------------------------------------------------------------------
+// value of element i of the packed operand
+__device__ __forceinline__ float pack_elem(const float* __restrict__ w, int Cout, int KH, int KW, int Cin, int mode,
+                                           int rows_padded, long long i) {
+  const int taps = KH * KW;
+  float v = 0.f;
+  if (mode == 0) {
+    // out[row=co][t][ci]
+    long long K = (long long)taps * Cin;
+    int row = (int)(i / K);
+    if (row < Cout) v = w[i];
+  } else if (mode == 1) {
+    // out[row=ci][t'][co] = w[co][taps-1-t'][ci]
+    long long K = (long long)taps * Cout;
+    int row = (int)(i / K);
+    long long r = i % K;
+    int tp = (int)(r / Cout), co = (int)(r % Cout);
+    if (row < Cin) v = w[((long long)co * taps + (taps - 1 - tp)) * Cin + row];
+  } else if (mode == 3) {
+    // out[row=co][kh][j*8+ci] = w[co][kh][j][ci]
+    long long K = (long long)KH * 64;
+    int row = (int)(i / K);
+    int r = (int)(i % K);
+    int kh = r >> 6, j = (r >> 3) & 7, ci = r & 7;
+    if (row < Cout && j < KW && ci < Cin) v = w[(((long long)row * KH + kh) * KW + j) * Cin + ci];
+  } else if (mode == 4) {
+    // out[row=ci][kh'][j*8+co] = w[co][KH-1-kh'][KW-1-j][ci]
+    long long K = (long long)KH * 64;
+    int row = (int)(i / K);
+    int r = (int)(i % K);
+    int khp = r >> 6, j = (r >> 3) & 7, co = r & 7;
+    if (row < Cin && j < KW && co < Cout) v = w[(((long long)co * KH + (KH - 1 - khp)) * KW + (KW - 1 - j)) * Cin + row];
+  } else {
+    // 4 phases: out[phase][row=ci][(i',j')][co] = w[co][2(1-i')+py][2(1-j')+px][ci]   (KH = KW = 4)
+    long long K = 4LL * Cout;
+    long long per_phase = (long long)rows_padded * K;
+    int phase = (int)(i / per_phase);
+    long long r = i % per_phase;
+    int row = (int)(r / K);
+    r %= K;
+    int tp = (int)(r / Cout), co = (int)(r % Cout);
+    int ip = tp >> 1, jp = tp & 1, py = phase >> 1, px = phase & 1;
+    int kh = 2 * (1 - ip) + py, kw = 2 * (1 - jp) + px;
+    if (row < Cin) v = w[(((long long)co * KH + kh) * KW + kw) * Cin + row];
+  }
+  return v;
+}
+
 template <typename T>
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int KH, int KW, int Cin, int mode,
                                     T* __restrict__ out, int rows_padded, long long total) {
-  const int taps = KH * KW;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    if (mode == 0) {
-      // out[row=co][t][ci]
-      long long K = (long long)taps * Cin;
-      int row = (int)(i / K);
-      if (row < Cout) v = w[i];
-    } else if (mode == 1) {
-      // out[row=ci][t'][co] = w[co][taps-1-t'][ci]
-      long long K = (long long)taps * Cout;
-      int row = (int)(i / K);
-      long long r = i % K;
-      int tp = (int)(r / Cout), co = (int)(r % Cout);
-      if (row < Cin) v = w[((long long)co * taps + (taps - 1 - tp)) * Cin + row];
-    } else if (mode == 3) {
-      // out[row=co][kh][j*8+ci] = w[co][kh][j][ci]
-      long long K = (long long)KH * 64;
-      int row = (int)(i / K);
-      int r = (int)(i % K);
-      int kh = r >> 6, j = (r >> 3) & 7, ci = r & 7;
-      if (row < Cout && j < KW && ci < Cin) v = w[(((long long)row * KH + kh) * KW + j) * Cin + ci];
-    } else if (mode == 4) {
-      // out[row=ci][kh'][j*8+co] = w[co][KH-1-kh'][KW-1-j][ci]
-      long long K = (long long)KH * 64;
-      int row = (int)(i / K);
-      int r = (int)(i % K);
-      int khp = r >> 6, j = (r >> 3) & 7, co = r & 7;
-      if (row < Cin && j < KW && co < Cout) v = w[(((long long)co * KH + (KH - 1 - khp)) * KW + (KW - 1 - j)) * Cin + row];
-    } else {
-      // 4 phases: out[phase][row=ci][(i',j')][co] = w[co][2(1-i')+py][2(1-j')+px][ci]   (KH = KW = 4)
-      long long K = 4LL * Cout;
-      long long per_phase = (long long)rows_padded * K;
-      int phase = (int)(i / per_phase);
-      long long r = i % per_phase;
-      int row = (int)(r / K);
-      r %= K;
-      int tp = (int)(r / Cout), co = (int)(r % Cout);
-      int ip = tp >> 1, jp = tp & 1, py = phase >> 1, px = phase & 1;
-      int kh = 2 * (1 - ip) + py, kw = 2 * (1 - jp) + px;
-      if (row < Cin) v = w[(((long long)co * KH + kh) * KW + kw) * Cin + row];
-    }
-    out[i] = from_f<T>(v);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    out[i] = from_f<T>(pack_elem(w, Cout, KH, KW, Cin, mode, rows_padded, i));
+}
+
+// every packed operand of a network in ONE launch: blockIdx.y = table entry (the table lives in device memory)
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const dwc_pack_entry_t* __restrict__ table) {
+  const dwc_pack_entry_t e = table[blockIdx.y];
+  const float* __restrict__ w = e.w;
+  if (e.out_dtype == DWC_F32) {
+    float* out = reinterpret_cast<float*>(e.out);
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < e.total; i += gridDim.x * 256LL)
+      out[i] = pack_elem(w, e.cout, e.kh, e.kw, e.cin, e.mode, e.rows_padded, i);
+  } else {
+    bf16* out = reinterpret_cast<bf16*>(e.out);
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < e.total; i += gridDim.x * 256LL)
+      out[i] = __float2bfloat16_rn(pack_elem(w, e.cout, e.kh, e.kw, e.cin, e.mode, e.rows_padded, i));
   }
+}
+extern "C" int dwc_pack_weights_batch(const dwc_pack_entry_t* table_dev, int count, dwc_stream_t stream) {
+  DWC_CHECK(table_dev != nullptr && count > 0 && count <= 65535, "dwc_pack_weights_batch: bad table");
+  pack_weights_batch_kernel<<<dim3(48, count), 256, 0, as_stream(stream)>>>(table_dev);
+  DWC_LAUNCH_CHECK();
+  return 0;
 }
 extern "C" int dwc_pack_weights(const float* w, int cout, int taps_h, int taps_w, int cin, int mode, void* out,
                                 int out_dtype, int rows_padded, dwc_stream_t stream) {

@@ -171,7 +171,6 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
     const uint8_t* sd = sy + p.segbytes;
     const int u = r0 * p.nseg + i;
     const int row = u / p.nseg, x0 = (u - row * p.nseg) * p.segw;
-
     if (MODE == RM_STATS) {
       for (int q = tid; q < nchunks; q += 256) {
         float v[8];

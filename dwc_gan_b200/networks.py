@@ -202,6 +202,46 @@ class Conv2dBlock(nn.Module):
             return hit[1]
         return torch.empty(shape, dtype=dtype, device=device)
 
+    def _pack(self, f, key, w, tot, mode, out, rows_p):
+        """(Re)pack one operand.  The first request registers it with the network's flat buffer; once the set of
+        operands is stable, the first stale operand of a step repacks ALL of them in one launch
+        (dwc_pack_weights_batch) instead of one small kernel in front of every convolution."""
+        reg = f.__dict__.get("_pack_reg")
+        if reg is None or reg["base"] != f.data.data_ptr():          # new flat buffer: every pointer is stale
+            reg = f.__dict__["_pack_reg"] = {"entries": {}, "table": None, "dirty": True, "base": f.data.data_ptr()}
+        ek = (id(self), key)
+        ent = reg["entries"].get(ek)
+        if ent is None or ent["out"] is not out or ent["w_ptr"] != w.data_ptr():
+            reg["entries"][ek] = dict(layer=self, key=key, out=out, w_ptr=w.data_ptr(), tot=tot, mode=mode,
+                                      rows_p=rows_p)
+            reg["dirty"] = True
+        capturing = torch.cuda.is_current_stream_capturing() if out.is_cuda else False
+        if ops.RT.batch_pack and not (reg["dirty"] and capturing):
+            if reg["dirty"]:
+                ents = list(reg["entries"].values())
+                arr = (L.PackEntry * len(ents))()
+                for i, e in enumerate(ents):
+                    o, ly = e["out"], e["layer"]
+                    arr[i] = L.PackEntry(e["w_ptr"], o.data_ptr(), e["tot"], ly.k, ly.k, ly.cin, e["mode"], e["rows_p"],
+                                         L.dt(o), 0, o.numel())
+                host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+                reg["table"] = host.to(out.device)
+                reg["order"] = ents
+                reg["dirty"] = False
+                reg["calls"] = 0
+            reg["calls"] += 1
+            # the batch is only worth it (and only complete) once a whole step has registered its operands
+            if reg["calls"] > 1 or len(reg["order"]) > 8:
+                ops._call("dwc_pack_weights_batch", L.ptr(reg["table"]), len(reg["order"]), L.stream())
+                for e in reg["order"]:
+                    e["layer"]._packed[e["key"]] = (f.version, e["out"])
+                return self._packed[key]
+        ops._call("dwc_pack_weights", L.ptr(w), tot, self.k, self.k, self.cin, mode, L.ptr(out), L.dt(out), rows_p,
+                  L.stream())
+        hit = (f.version, out)
+        self._packed[key] = hit
+        return hit
+
     def packed_fwd(self, dtype):
         f, w, _ = self._raw_weight()
         tot = self.total_cout()
@@ -212,10 +252,7 @@ class Conv2dBlock(nn.Module):
         hit = self._packed.get(key)
         if hit is None or hit[0] != f.version:
             out = self._pack_buffer(hit, (rows_p, self.k * self.k * self.cin), dtype, w.device)
-            ops._call("dwc_pack_weights", L.ptr(w), tot, self.k, self.k, self.cin, 0, L.ptr(out), L.dt(dtype), rows_p,
-                      L.stream())
-            hit = (f.version, out)
-            self._packed[key] = hit
+            hit = self._pack(f, key, w, tot, 0, out, rows_p)
         return hit[1], rows_p
 
     def packed_dgrad(self, dtype, pad_rows=False):
@@ -233,10 +270,7 @@ class Conv2dBlock(nn.Module):
             else:
                 out = self._pack_buffer(hit, (4, rows_p, 4 * tot), dtype, w.device)
                 mode = 2
-            ops._call("dwc_pack_weights", L.ptr(w), tot, self.k, self.k, self.cin, mode, L.ptr(out), L.dt(dtype),
-                      rows_p, L.stream())
-            hit = (f.version, out)
-            self._packed[key] = hit
+            hit = self._pack(f, key, w, tot, mode, out, rows_p)
         return hit[1], rows_p
 
     def packed_rows(self, dtype, mode):
@@ -248,10 +282,7 @@ class Conv2dBlock(nn.Module):
         if hit is None or hit[0] != f.version:
             rows = tot if mode == 3 else self.cin
             out = self._pack_buffer(hit, (rows, self.k * 64), dtype, w.device)
-            ops._call("dwc_pack_weights", L.ptr(w), tot, self.k, self.k, self.cin, mode, L.ptr(out), L.dt(dtype), rows,
-                      L.stream())
-            hit = (f.version, out)
-            self._packed[key] = hit
+            hit = self._pack(f, key, w, tot, mode, out, rows)
         return hit[1]
 
     def grad_buffers(self):
@@ -275,20 +306,21 @@ class Conv2dBlock(nn.Module):
     def in_layout(self):
         return 1 if self.stride == 2 else 0
 
-    def run(self, xp: HB, out_halo=0, out_layout=0, res: Optional[HB] = None, raw=False) -> HB:
-        """xp: reflect-haloed input (halo == padding, parity planes if stride 2)."""
+    def run(self, xp: HB, out_halo=0, out_layout=0, res: Optional[HB] = None, raw=False, skip_box=None,
+            res_box=None) -> HB:
+        """xp: reflect-haloed input (halo == padding, parity planes if stride 2).  skip_box / res_box: see ResBlock."""
         assert xp.halo == self.padding and xp.layout == self.in_layout() and xp.c == self.cin
-        y = _ConvProxy.conv(xp, self)
+        y = _ConvProxy.conv(xp, self, skip_box)
         if raw:
             return y
-        return self.finish(y, out_halo, out_layout, res)
+        return self.finish(y, out_halo, out_layout, res, res_box)
 
     def run_first(self, img, rows_t, pool, out_halo=0, out_layout=0, raw=False) -> HB:
         """First layer of a network: img NCHW fp32 (3 channels), rows_t = ops.image_rows(img, pool, self)."""
         y = ops.first_conv(img, rows_t, self, pool)
         return y if raw else self.finish(y, out_halo, out_layout, None)
 
-    def finish(self, y: HB, out_halo=0, out_layout=0, res: Optional[HB] = None) -> HB:
+    def finish(self, y: HB, out_halo=0, out_layout=0, res: Optional[HB] = None, res_box=None) -> HB:
         n = y.n
         nw = nb = None
         ln = None
@@ -305,7 +337,7 @@ class Conv2dBlock(nn.Module):
             ln = self.norm
         eps = self.norm.eps if self.norm is not None else 1e-5
         return ops.post(y, self.norm_kind, _ACT[self.act_name], nw, nb, res, out_halo, out_layout, ln, eps,
-                        anchor=ln.gamma if ln is not None else None)
+                        anchor=ln.gamma if ln is not None else None, skip_box=res_box)
 
     def forward(self, x):
         """API-compatible entry: logical NCHW tensor in, logical NCHW tensor (compute dtype) out."""
@@ -320,8 +352,8 @@ class Conv2dBlock(nn.Module):
 
 class _ConvProxy:
     @staticmethod
-    def conv(xp: HB, layer: Conv2dBlock) -> HB:
-        return ops.conv(xp, layer)
+    def conv(xp: HB, layer: Conv2dBlock, skip_box=None) -> HB:
+        return ops.conv(xp, layer, skip_box)
 
 
 class ResBlock(nn.Module):
@@ -334,8 +366,12 @@ class ResBlock(nn.Module):
             Conv2dBlock(dim, dim, 3, 1, 1, norm=norm, activation="none", pad_type=pad_type))
 
     def run(self, p0: HB, out_halo) -> HB:
-        p1 = self.model[0].run(p0, out_halo=1)
-        return self.model[1].run(p1, out_halo=out_halo, res=p0)
+        # The block input receives two gradients: the skip connection's (produced by the backward of the second
+        # conv's norm pass) and the first conv's data gradient.  The box carries the former to the latter's dgrad
+        # kernel, which adds onto it in its epilogue (backward order guarantees it is there first).
+        box = {} if ops.RT.fuse_skip_grad and p0.t.requires_grad else None
+        p1 = self.model[0].run(p0, out_halo=1, skip_box=box)
+        return self.model[1].run(p1, out_halo=out_halo, res=p0, res_box=box)
 
 
 class ResBlocks(nn.Module):

@@ -38,6 +38,8 @@ class Runtime:
         self.side_keep = []
         self.side_main = None
         self.use_side_stream = True
+        self.fuse_skip_grad = os.environ.get("DWC_FUSE_SKIP_GRAD", "1") != "0"
+        self.batch_pack = os.environ.get("DWC_BATCH_PACK", "1") != "0"
         self.use_fused_norm = os.environ.get("DWC_FUSED_NORM", "0") != "0"   # opt-in: the row-streaming passes are faster
 
     def set_mode(self, mode: str):
@@ -157,8 +159,9 @@ class ConvFn(torch.autograd.Function):
     (networks.py:577-580 and aten::convolution_backward)."""
 
     @staticmethod
-    def forward(ctx, xp_t, weight, layer, xp: HB):
+    def forward(ctx, xp_t, weight, layer, xp: HB, skip_box=None):
         _require_cuda(xp_t)
+        ctx.skip_box = skip_box
         k, s, cout = layer.k, layer.stride, layer.total_cout()
         ho, wo = P.out_size(xp, k, s)
         hy = k - 1 if s == 1 else 1
@@ -184,10 +187,16 @@ class ConvFn(torch.autograd.Function):
         xp = HB(xp_t, n, h, w, c, halo, layout)
         dxp_t = None
         if ctx.needs_input_grad[0]:
-            dxp = HB.empty(n, h, w, c, halo, layout, dy_t.dtype, dy_t.device)
+            # ResBlock: the skip-connection gradient (PostFn.backward of the block's second conv left it in the box,
+            # same geometry as this conv's input, zero halo) is the buffer the data gradient is added to, instead of
+            # a separate element-wise add of two full tensors by the autograd engine
+            skip = ctx.skip_box.pop("dres", None) if ctx.skip_box is not None else None
+            dxp = skip if skip is not None else HB.empty(n, h, w, c, halo, layout, dy_t.dtype, dy_t.device)
+            assert (dxp.n, dxp.h, dxp.w, dxp.c, dxp.halo, dxp.layout) == (n, h, w, c, halo, layout)
             tc = RT.tc_ok(c, cout)
             wd, rows_p = layer.packed_dgrad(dy_t.dtype)
-            for q in P.plan_conv_dgrad(dy, wd, dxp, k, s, L.TC if tc else L.SIMT, cin_padded=rows_p):
+            for q in P.plan_conv_dgrad(dy, wd, dxp, k, s, L.TC if tc else L.SIMT, cin_padded=rows_p,
+                                       accumulate=skip is not None):
                 RT.launches += 1
                 q.launch()
             dxp_t = dxp.t
@@ -199,13 +208,13 @@ class ConvFn(torch.autograd.Function):
             wp = P.plan_conv_wgrad(dy, xp, gw, gb, k, s, L.TC if tc else L.SIMT, accumulate=True)
             RT.launches += 3
             side_launch(lambda: wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device)), (dy.t, xp_t))
-        return dxp_t, None, None, None
+        return dxp_t, None, None, None, None
 
 
-def conv(xp: HB, layer) -> HB:
+def conv(xp: HB, layer, skip_box=None) -> HB:
     k, s = layer.k, layer.stride
     ho, wo = P.out_size(xp, k, s)
-    t = ConvFn.apply(xp.t, layer.weight_param, layer, xp)
+    t = ConvFn.apply(xp.t, layer.weight_param, layer, xp, skip_box)
     return HB(t, xp.n, ho, wo, layer.total_cout(), k - 1 if s == 1 else 1, 0)
 
 
@@ -369,8 +378,9 @@ class PostFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y_t, nw, nb, res_t, anchor, y: HB, kind, act, res: Optional[HB], out_halo, out_layout, ln_mod,
-                eps):
+                eps, skip_box=None):
         _require_cuda(y_t)
+        ctx.skip_box = skip_box
         yh = HB(y_t, y.n, y.h, y.w, y.c, y.halo, 0)
         n, c, hw = y.n, y.c, y.h * y.w
         dev = y_t.device
@@ -428,7 +438,8 @@ class PostFn(torch.autograd.Function):
             _call("dwc_post_fused_bwd", C.byref(ds), C.byref(ys), L.ptr(coef), kind, act, L.ptr(nw), L.ptr(dnw),
                   L.ptr(dnb), C.byref(dys), C.byref(drs) if drs is not None else None, L.stream())
         else:
-            pre = _prefold(dout) if kind != NORM_NONE else 0     # one pass only: gather the reflections in it
+            # fold the reflect-halo gradient once, in place: the streaming passes then read whole interior rows
+            pre = _prefold(dout)
             bco = None
             if kind != NORM_NONE:
                 red = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
@@ -447,14 +458,17 @@ class PostFn(torch.autograd.Function):
                       L.ptr(gw), L.ptr(gb), L.ptr(bco), L.stream())
             _call("dwc_post_bwd_apply", C.byref(ds), C.byref(ys), L.ptr(coef), L.ptr(bco), act, C.byref(dys),
                   C.byref(drs) if drs is not None else None, pre, L.stream())
-        return (dy.t, dnw, dnb, dres.t if dres is not None else None, None, None, None, None, None, None, None, None,
-                None)
+        dres_t = dres.t if dres is not None else None
+        if dres is not None and ctx.skip_box is not None:
+            ctx.skip_box["dres"] = dres          # handed to ConvFn.backward of the block's first conv (see there)
+            dres_t = None
+        return (dy.t, dnw, dnb, dres_t, None, None, None, None, None, None, None, None, None, None)
 
 
 def post(y: HB, kind=NORM_NONE, act=ACT_NONE, nw=None, nb=None, res: Optional[HB] = None, out_halo=0, out_layout=0,
-         ln_mod=None, eps=1e-5, anchor=None) -> HB:
+         ln_mod=None, eps=1e-5, anchor=None, skip_box=None) -> HB:
     t = PostFn.apply(y.t, nw, nb, res.t if res is not None else None, anchor, y, kind, act, res, out_halo, out_layout,
-                     ln_mod, eps)
+                     ln_mod, eps, skip_box)
     return HB(t, y.n, y.h, y.w, y.c, out_halo, out_layout)
 
 

@@ -274,9 +274,11 @@ def plan_conv_fwd(xp: HB, w_packed, ncols, ncols_padded, bias, y: HB, k, stride,
                      o_str=(cy, y.wp * cy, y.hp * y.wp * cy), backend=backend)
 
 
-def plan_conv_dgrad(dy: HB, w_packed, dxp: HB, k, stride, backend, cin_padded=None) -> List[GConvPlan]:
+def plan_conv_dgrad(dy: HB, w_packed, dxp: HB, k, stride, backend, cin_padded=None, accumulate=False) -> List[GConvPlan]:
     """dy: zero-haloed output gradient (halo k-1 for stride 1, 1 for the stride-2 4x4 conv).
-    dxp: gradient of the padded input (same geometry as the forward input buffer); fully overwritten."""
+    dxp: gradient of the padded input (same geometry as the forward input buffer); fully overwritten, or added to
+    when `accumulate` (stride 1 only: the skip-connection gradient of a ResBlock is already in it)."""
+    assert not accumulate or stride == 1
     cout, cin = dy.c, dxp.c
     cin_padded = cin_padded or cin
     rows = dy.n * dy.hp * dy.wp
@@ -295,14 +297,15 @@ def plan_conv_dgrad(dy: HB, w_packed, dxp: HB, k, stride, backend, cin_padded=No
                                tiles=(-(-dxp.wp // hbx[0]), -(-dxp.hp // 16), dy.n), valid=(dxp.wp, dxp.hp, dy.n),
                                flat=(0, 0, 0, 0, 0), taps=conv_taps(k, 1), w=w_packed, w_off=0, ncols=cin,
                                ncols_padded=cin_padded, bias=None, out=dxp.t, out_off=0,
-                               o_str=(cin, dxp.wp * cin, dxp.hp * dxp.wp * cin), backend=hb))
+                               o_str=(cin, dxp.wp * cin, dxp.hp * dxp.wp * cin), backend=hb, accumulate=accumulate))
     elif stride == 1:
         assert dy.halo == k - 1 and dxp.layout == 0
         taps = [(kh * dy.wp + kw, 0, 0) for kh in range(k) for kw in range(k)]
         plans.append(GConvPlan(a=dy.t, a_off=0, a_dim=a_dim, a_str=a_str, box=(128, 1, 1), tiles=tiles,
                                valid=(rows, 1, dy.n), flat=(1, dy.hp * dy.wp, dy.wp, dxp.hp, dxp.wp), taps=taps,
                                w=w_packed, w_off=0, ncols=cin, ncols_padded=cin_padded, bias=None, out=dxp.t, out_off=0,
-                               o_str=(cin, dxp.wp * cin, dxp.hp * dxp.wp * cin), backend=backend))
+                               o_str=(cin, dxp.wp * cin, dxp.hp * dxp.wp * cin), backend=backend,
+                               accumulate=accumulate))
     else:
         assert k == 4 and dy.halo == 1 and dxp.layout == 1
         hq, wq = dxp.hp // 2, dxp.wp // 2

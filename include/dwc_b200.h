@@ -312,6 +312,16 @@ int dwc_ema_step(const float* param, float* avg, int64_t count, float beta, dwc_
  * mode 4: stride-1 dgrad over row-im2col dY   wr[ci][kh'][j*8+co] = w[co][KH-1-kh'][KW-1-j][ci]  (else 0) */
 int dwc_pack_weights(const float* w, int cout, int taps_h, int taps_w, int cin, int mode, void* out,
                      int out_dtype, int rows_padded, dwc_stream_t stream);
+/* The same for every operand of a network in one launch: `table_dev` is a DEVICE array of `count` entries (built once
+ * by the host; the pointers it holds - slices of the flat parameter buffer and the in-place rewritten operands - do not
+ * change between optimizer steps).  total = number of elements of `out`. */
+typedef struct {
+  const float* w;
+  void* out;
+  int32_t cout, kh, kw, cin, mode, rows_padded, out_dtype, reserved;
+  int64_t total;
+} dwc_pack_entry_t;
+int dwc_pack_weights_batch(const dwc_pack_entry_t* table_dev, int count, dwc_stream_t stream);
 int dwc_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t count, dwc_stream_t stream);
 int dwc_fill(void* dst, int dtype, float value, int64_t count, dwc_stream_t stream);
 
