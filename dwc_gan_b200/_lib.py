@@ -77,7 +77,7 @@ EXPORTS = [
     "dwc_sgemm", "dwc_sgemm_ws", "dwc_sgemm_workspace_bytes", "dwc_colsum", "dwc_relu_bwd", "dwc_mul", "dwc_embed_concat_fwd", "dwc_embed_concat_bwd",
     "dwc_lstm_workspace_bytes", "dwc_lstm_layer_fwd", "dwc_lstm_layer_bwd", "dwc_transpose", "dwc_gmm_sample", "dwc_gmm_kl", "dwc_l1_loss_fwd", "dwc_l1_loss_bwd",
     "dwc_mse_const_loss_fwd", "dwc_mse_const_loss_bwd", "dwc_bce_logits_loss_fwd", "dwc_bce_logits_loss_bwd",
-    "dwc_adam_step", "dwc_ema_step", "dwc_pack_weights", "dwc_pack_weights_batch", "dwc_cast", "dwc_fill",
+    "dwc_adam_step", "dwc_ema_step", "dwc_pack_weights", "dwc_pack_weights_batch", "dwc_conv7_few", "dwc_cast", "dwc_fill",
 ]
 
 
@@ -99,6 +99,9 @@ def lib():
         _lib.dwc_sgemm_ws.argtypes = list(_lib.dwc_sgemm.argtypes[:-1]) + [C.c_void_p, C.c_int64, C.c_void_p]
         _lib.dwc_sgemm_workspace_bytes.restype = C.c_int64
         _lib.dwc_colsum.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+        _lib.dwc_conv7_few.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                       C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
         _lib.dwc_norm_finalize.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.dwc_post_fused_fwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p,

@@ -301,27 +301,53 @@ __global__ void embed_concat_fwd_kernel(const int64_t* __restrict__ tok, const f
     x[i] = v;
   }
 }
-// demb[token] += dx (atomics; token rows collide), dstyle[b] = sum_t dx[t,b,E:]
-__global__ void embed_concat_bwd_kernel(const int64_t* __restrict__ tok, const float* __restrict__ dx,
-                                        const float* __restrict__ mask, float* __restrict__ demb,
-                                        float* __restrict__ dstyle, int B, int T, int E, int S, int pad_idx) {
+// dstyle[b] = sum_t dx[t,b,E:]
+__global__ void embed_concat_bwd_style_kernel(const float* __restrict__ dx, float* __restrict__ dstyle, int B, int T,
+                                              int E, int S) {
   const int D = E + S;
-  const long long total = (long long)B * D;
+  const long long total = (long long)B * S;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int d = (int)(i % D);
-    int b = (int)(i / D);
-    if (d >= E) {
-      float s = 0.f;
-      for (int t = 0; t < T; ++t) s += dx[((long long)t * B + b) * D + d];
-      dstyle[(long long)b * S + (d - E)] = s;
-    } else if (demb) {
-      for (int t = 0; t < T; ++t) {
-        long long token = tok[(long long)b * T + t];
-        if (token == pad_idx) continue;
-        float g = dx[((long long)t * B + b) * D + d];
-        if (mask) g *= mask[((long long)t * B + b) * E + d];
-        atomicAdd(demb + token * E + d, g);
+    const int d = E + (int)(i % S);
+    const int b = (int)(i / S);
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += dx[((long long)t * B + b) * D + d];
+    dstyle[(long long)b * S + (d - E)] = s;
+  }
+}
+// demb[token] += sum over the positions holding that token of dx * mask, WITHOUT atomics: one block per position; the
+// block of the FIRST position of a token (in b-major, t-minor order) owns the token's row and adds the contributions of
+// all its positions in that fixed order, every other block exits.  Bit-reproducible run to run (float atomics in
+// arrival order are not, and Adam turns a one-ulp gradient difference into a full +-lr step for near-zero gradients).
+__global__ void __launch_bounds__(128)
+    embed_bwd_owner_kernel(const int64_t* __restrict__ tok, const float* __restrict__ dx, const float* __restrict__ mask,
+                           float* __restrict__ demb, int B, int T, int E, int S, int pad_idx) {
+  const int P = B * T, p = blockIdx.x;
+  const long long token = tok[p];
+  if (token == pad_idx) return;
+  int earlier = 0;
+  for (int q = threadIdx.x; q < p; q += blockDim.x) earlier |= (tok[q] == token);
+  if (__syncthreads_or(earlier)) return;
+  const int D = E + S;
+  for (int d0 = 0; d0 < E; d0 += 4 * 128) {            // 4 dims per thread and sweep over the positions
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = p; q < P; ++q) {
+      if (tok[q] != token) continue;
+      const int b = q / T, t = q - b * T;
+      const long long row = (long long)t * B + b;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = d0 + j * 128 + threadIdx.x;
+        if (d < E) {
+          float g = dx[row * D + d];
+          if (mask) g *= mask[row * E + d];
+          acc[j] += g;
+        }
       }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = d0 + j * 128 + threadIdx.x;
+      if (d < E) demb[token * E + d] += acc[j];
     }
   }
 }
@@ -334,9 +360,12 @@ extern "C" int dwc_embed_concat_fwd(const int64_t* tokens, const float* emb, con
 }
 extern "C" int dwc_embed_concat_bwd(const int64_t* tokens, const float* dx, const float* mask, float* demb,
                                     float* dstyle, int b, int t, int e, int s, int pad_idx, dwc_stream_t stream) {
-  embed_concat_bwd_kernel<<<grid1d((long long)b * (e + s)), 256, 0, as_stream(stream)>>>(tokens, dx, mask, demb, dstyle,
-                                                                                          b, t, e, s, pad_idx);
+  embed_concat_bwd_style_kernel<<<grid1d((long long)b * s), 256, 0, as_stream(stream)>>>(dx, dstyle, b, t, e, s);
   DWC_LAUNCH_CHECK();
+  if (demb) {
+    embed_bwd_owner_kernel<<<b * t, 128, 0, as_stream(stream)>>>(tokens, dx, mask, demb, b, t, e, s, pad_idx);
+    DWC_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -37,9 +37,11 @@ class Runtime:
         self.side_streams = {}
         self.side_keep = []
         self.side_main = None
-        self.use_side_stream = True
+        self.use_side_stream = os.environ.get("DWC_SIDE", "1") != "0"
         self.fuse_skip_grad = os.environ.get("DWC_FUSE_SKIP_GRAD", "1") != "0"
         self.batch_pack = os.environ.get("DWC_BATCH_PACK", "1") != "0"
+        self.use_conv7 = os.environ.get("DWC_CONV7", "1") != "0"
+        self.conv7_which = os.environ.get("DWC_CONV7", "1")          # diagnostics: "h" heads only, "d" dgrad only
         self.use_fused_norm = os.environ.get("DWC_FUSED_NORM", "0") != "0"   # opt-in: the row-streaming passes are faster
 
     def set_mode(self, mode: str):
@@ -265,10 +267,18 @@ class FirstConvFn(torch.autograd.Function):
             layout = 1 if s == 2 else 0
             dxp = HB.empty(n, h // pool, w // pool, c, p, layout, dy_t.dtype, dy_t.device)
             tc = RT.tc_ok(cout)
-            wd, rows_p = layer.packed_dgrad(dy_t.dtype, pad_rows=tc)
-            for q in P.plan_conv_dgrad(dy, wd, dxp, k, s, L.TC if tc else L.SIMT, cin_padded=rows_p):
-                RT.launches += 1
-                q.launch()
+            if conv7_few_ok(dy_t.dtype, k, s, cout, c) and hy == 6 and layout == 0 and RT.conv7_which != "h":
+                # image gradient = valid 7x7 conv of the zero-haloed dy with the flipped filter, 64 -> c channels:
+                # element (o = ci, ky, kx, i = co) of that filter is W[co][6-ky][6-kx][ci] of the master [64][7][7][c]
+                _, wm, _ = layer._raw_weight()
+                kk = k * k * c
+                conv7_few(dy.t, n, dy.hp, dy.wp, wm, 6 * k * c + 6 * c, 1, -k * c, -c, kk, None, c, dxp.t,
+                          (c, dxp.wp * c, dxp.hp * dxp.wp * c))
+            else:
+                wd, rows_p = layer.packed_dgrad(dy_t.dtype, pad_rows=tc)
+                for q in P.plan_conv_dgrad(dy, wd, dxp, k, s, L.TC if tc else L.SIMT, cin_padded=rows_p):
+                    RT.launches += 1
+                    q.launch()
             dimg = torch.empty(n, c, h, w, dtype=torch.float32, device=dy_t.device)
             ds = dxp.struct()
             _call("dwc_image_pad_bwd", C.byref(ds), pool, L.ptr(dimg), n, c, h, w, 0, L.stream())
@@ -291,6 +301,30 @@ def first_conv(img, rows_t, layer, pool) -> HB:
     return HB(t, n, ho, wo, layer.cout, k - 1 if s == 1 else 1, 0)
 
 
+def conv7_few(x_t, n, hin, win, w_master, w_base, s_o, s_ky, s_kx, s_i, bias, cout, out_t, out_str):
+    """7x7 stride-1 valid conv, 64 -> cout <= 4 channels, on the dedicated tcgen05 kernel (csrc/conv7few.cu).
+    x_t: bf16 [n, hin, win, 64] contiguous; out_t: bf16 buffer addressed by out_str = (x, y, n) element strides."""
+    assert x_t.dtype == torch.bfloat16 and x_t.is_contiguous() and out_t.dtype == torch.bfloat16
+    istr = (C.c_int64 * 3)(64, win * 64, hin * win * 64)
+    ostr = (C.c_int64 * 3)(*out_str)
+    _call("dwc_conv7_few", L.ptr(x_t), n, hin, win, istr, L.ptr(w_master), w_base, s_o, s_ky, s_kx, s_i, L.ptr(bias),
+          cout, L.ptr(out_t), ostr, L.stream())
+    if os.environ.get("DWC_CONV7_CHECK"):          # diagnostics: the kernel must be bit-reproducible in situ
+        first = out_t.clone()
+        for rep in range(3):
+            _call("dwc_conv7_few", L.ptr(x_t), n, hin, win, istr, L.ptr(w_master), w_base, s_o, s_ky, s_kx, s_i,
+                  L.ptr(bias), cout, L.ptr(out_t), ostr, L.stream())
+            if not torch.equal(first, out_t):
+                d = (first.float() - out_t.float()).abs()
+                print("conv7 NOT reproducible: n %d hin %d cout %d rep %d: %d elements differ, max %.4g, nan %d/%d" % (
+                    n, hin, cout, rep, int((d > 0).sum()), float(d.max()), int(torch.isnan(first).sum()),
+                    int(torch.isnan(out_t).sum())), flush=True)
+
+
+def conv7_few_ok(dtype, k, stride, c64, cfew):
+    return RT.use_conv7 and RT.use_tc and dtype == torch.bfloat16 and k == 7 and stride == 1 and c64 == 64 and cfew <= 4
+
+
 class HeadsConvFn(torch.autograd.Function):
     """Decoder heads (networks_v2.py:162-169): the two 7x7 convolutions as one 4-channel gconv + tanh / sigmoid.
     Backward builds 64-wide window buffers of the 4-channel gradient so that dgrad and wgrad run on the tensor cores."""
@@ -301,11 +335,15 @@ class HeadsConvFn(torch.autograd.Function):
         k, cout = layer.k, layer.total_cout()
         n, h, w = xp.n, xp.h, xp.w
         y = HB.empty(n, h, w, cout, 0, 0, xp_t.dtype, xp_t.device)
-        wf, rows_p = layer.packed_fwd(xp_t.dtype)
-        tc = RT.tc_ok(xp.c) and rows_p == 16
-        RT.launches += 1
-        P.plan_conv_fwd(HB(xp_t, n, h, w, xp.c, xp.halo, 0), wf, cout, rows_p, layer.bias_f32(), y, k, 1,
-                        L.TC if tc else L.SIMT).launch()
+        if conv7_few_ok(xp_t.dtype, k, 1, xp.c, cout) and xp.layout == 0 and xp.halo == 3 and RT.conv7_which != "d":
+            _, wm, bm = layer._raw_weight()                    # fp32 master [cout][7][7][64]
+            conv7_few(xp_t, n, xp.hp, xp.wp, wm, 0, 49 * 64, 7 * 64, 64, 1, bm, cout, y.t, (cout, w * cout, h * w * cout))
+        else:
+            wf, rows_p = layer.packed_fwd(xp_t.dtype)
+            tc = RT.tc_ok(xp.c) and rows_p == 16
+            RT.launches += 1
+            P.plan_conv_fwd(HB(xp_t, n, h, w, xp.c, xp.halo, 0), wf, cout, rows_p, layer.bias_f32(), y, k, 1,
+                            L.TC if tc else L.SIMT).launch()
         img = torch.empty(n, cout - 1, h, w, dtype=torch.float32, device=xp_t.device)
         att = torch.empty(n, 1, h, w, dtype=torch.float32, device=xp_t.device)
         ys = y.struct()

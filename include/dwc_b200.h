@@ -304,6 +304,17 @@ int dwc_adam_step(float* param, const float* grad, float* m, float* v, int64_t c
                   const uint8_t* active /*per 1024-element chunk, device, may be NULL*/,
                   const float* hyper, dwc_stream_t stream);
 int dwc_ema_step(const float* param, float* avg, int64_t count, float beta, dwc_stream_t stream);
+/* 7x7 stride-1 valid convolution from 64 channels to cout <= 4 channels (bf16 in / out, fp32 accumulation) on tcgen05:
+ * the decoder heads (networks_v2.py:162-169, reflect-haloed input) and the image gradient of a first encoder
+ * convolution (transpose of networks_v2.py:52, zero-haloed output gradient, flipped taps).  Vertical taps are folded
+ * into K, horizontal taps into N (7 x 4 columns) and summed by warp shuffles in the epilogue.
+ * in: [n, hin, win, 64], element strides in_str = {x, y, n}; out: (hin-6) x (win-6) x cout per image, out_str = {x, y, n}.
+ * The weights are read from the fp32 master copy: element (o, ky, kx, i) at w[w_base + o*s_o + ky*s_ky + kx*s_kx + i*s_i]
+ * (strides may be negative: a data gradient walks the taps backwards).  bias may be NULL. */
+int dwc_conv7_few(const void* in, int n, int hin, int win, const int64_t* in_str, const float* w, int64_t w_base,
+                  int64_t s_o, int64_t s_ky, int64_t s_kx, int64_t s_i, const float* bias, int cout, void* out,
+                  const int64_t* out_str, dwc_stream_t stream);
+
 /* master float32 weights [Cout][taps][Cin] -> packed compute-dtype GEMM operands.
  * mode 0: forward  wf[co][t][ci]                (cast only, rows padded to ncols_padded)
  * mode 1: stride-1 dgrad  wd[ci][T-1-t][co]     (taps reversed)

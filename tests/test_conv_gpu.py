@@ -4,6 +4,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+import dwc_gan_b200
 from dwc_gan_b200 import _lib as L
 from dwc_gan_b200 import plan as P
 from dwc_gan_b200.plan import HB
@@ -124,3 +125,31 @@ def test_conv_fwd_dgrad_wgrad(n, h, w, cin, cout, k, s, p, backend, dtype):
     assert err < tol, "wgrad rel err %g" % err
     errb = ((db.cpu().double() - 1) - dy.sum((0, 2, 3))).abs().max().item() / dy.sum((0, 2, 3)).abs().max().item()
     assert errb < tol, "dbias rel err %g" % errb
+
+
+@pytest.mark.parametrize("n,hin,win,cout,flip", [(2, 134, 134, 4, False), (1, 31, 45, 3, False), (2, 140, 140, 3, True),
+                                                 (1, 13, 58, 4, True), (3, 7, 7, 1, False)])
+def test_conv7_few(n, hin, win, cout, flip):
+    """dwc_conv7_few (decoder heads / first-conv image gradient) against F.conv2d on the same bf16-rounded operands."""
+    import torch.nn.functional as F
+    from dwc_gan_b200 import ops
+    dwc_gan_b200.set_mode("bf16")
+    torch.manual_seed(3)
+    x = torch.randn(n, hin, win, 64, device="cuda").to(torch.bfloat16)
+    hout, wout = hin - 6, win - 6
+    out = torch.full((n, hout, wout, cout), 7.0, device="cuda", dtype=torch.bfloat16)
+    if not flip:
+        w = torch.randn(cout, 7, 7, 64, device="cuda") * 0.05          # [o][ky][kx][i]
+        bias = torch.randn(cout, device="cuda")
+        ops.conv7_few(x, n, hin, win, w.reshape(-1), 0, 49 * 64, 7 * 64, 64, 1, bias, cout, out,
+                      (cout, wout * cout, hout * wout * cout))
+        w_oihw = w.permute(0, 3, 1, 2)
+    else:
+        wf = torch.randn(64, 7, 7, cout, device="cuda") * 0.05          # forward weights [co][ky][kx][ci]
+        bias = None
+        ops.conv7_few(x, n, hin, win, wf.reshape(-1), 6 * 7 * cout + 6 * cout, 1, -7 * cout, -cout, 49 * cout, None,
+                      cout, out, (cout, wout * cout, hout * wout * cout))
+        w_oihw = wf.flip(1, 2).permute(3, 0, 1, 2)                      # [o = ci][i = co][ky][kx], taps reversed
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w_oihw.to(torch.bfloat16).float(), bias).permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
