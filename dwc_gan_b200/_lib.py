@@ -72,7 +72,7 @@ class PackEntry(C.Structure):
 EXPORTS = [
     "dwc_last_error", "dwc_abi_version", "dwc_tc_available", "dwc_gconv", "dwc_wgrad_workspace_bytes", "dwc_wgrad",
     "dwc_nc_stats", "dwc_norm_finalize", "dwc_post_fwd", "dwc_post_bwd_reduce", "dwc_norm_bwd_finalize",
-    "dwc_post_bwd_apply", "dwc_fold_halo", "dwc_post_fused_ok", "dwc_post_fused_fwd", "dwc_post_fused_bwd", "dwc_upsample_pad_fwd", "dwc_upsample_pad_bwd", "dwc_image_pad_fwd", "dwc_image_pad_bwd",
+    "dwc_post_bwd_apply", "dwc_post_fwd_norm", "dwc_post_bwd_apply_norm", "dwc_fold_halo", "dwc_post_fused_ok", "dwc_post_fused_fwd", "dwc_post_fused_bwd", "dwc_upsample_pad_fwd", "dwc_upsample_pad_bwd", "dwc_image_pad_fwd", "dwc_image_pad_bwd",
     "dwc_heads_fwd", "dwc_heads_bwd", "dwc_image_rows_fwd", "dwc_heads_bwd_rows", "dwc_blend_fwd", "dwc_blend_bwd", "dwc_relu_gap_fwd", "dwc_relu_gap_bwd",
     "dwc_sgemm", "dwc_sgemm_ws", "dwc_sgemm_workspace_bytes", "dwc_colsum", "dwc_relu_bwd", "dwc_mul", "dwc_embed_concat_fwd", "dwc_embed_concat_bwd",
     "dwc_lstm_workspace_bytes", "dwc_lstm_layer_fwd", "dwc_lstm_layer_bwd", "dwc_transpose", "dwc_gmm_sample", "dwc_gmm_kl", "dwc_l1_loss_fwd", "dwc_l1_loss_bwd",
@@ -102,6 +102,11 @@ def lib():
         _lib.dwc_conv7_few.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
+        _lib.dwc_post_fwd_norm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.dwc_post_bwd_apply_norm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                                 C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.dwc_norm_finalize.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.dwc_post_fused_fwd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p,

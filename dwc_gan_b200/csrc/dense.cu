@@ -321,17 +321,40 @@ __global__ void embed_concat_bwd_style_kernel(const float* __restrict__ dx, floa
 __global__ void __launch_bounds__(128)
     embed_bwd_owner_kernel(const int64_t* __restrict__ tok, const float* __restrict__ dx, const float* __restrict__ mask,
                            float* __restrict__ demb, int B, int T, int E, int S, int pad_idx) {
+  extern __shared__ int stok[];                          // all P tokens: the scans below run out of shared memory
   const int P = B * T, p = blockIdx.x;
-  const long long token = tok[p];
+  for (int q = threadIdx.x; q < P; q += blockDim.x) stok[q] = (int)tok[q];
+  __syncthreads();
+  const int token = stok[p];
   if (token == pad_idx) return;
   int earlier = 0;
-  for (int q = threadIdx.x; q < p; q += blockDim.x) earlier |= (tok[q] == token);
+  for (int q = threadIdx.x; q < p; q += blockDim.x) earlier |= (stok[q] == token);
   if (__syncthreads_or(earlier)) return;
+  // ordered list of this token's positions (128 candidates per round, compacted with warp ballots)
+  int* mlist = stok + P;
+  __shared__ int wcount[4], total;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int base = p; base < P; base += 128) {
+    const int q = base + threadIdx.x;
+    const bool m = q < P && stok[q] == token;
+    const unsigned bal = __ballot_sync(0xffffffffu, m);
+    if (lane == 0) wcount[warp] = __popc(bal);
+    __syncthreads();
+    int off = total;
+    for (int w2 = 0; w2 < warp; ++w2) off += wcount[w2];
+    if (m) mlist[off + __popc(bal & ((1u << lane) - 1u))] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) total += wcount[0] + wcount[1] + wcount[2] + wcount[3];
+    __syncthreads();
+  }
+  const int cnt = total;
   const int D = E + S;
-  for (int d0 = 0; d0 < E; d0 += 4 * 128) {            // 4 dims per thread and sweep over the positions
+  for (int d0 = 0; d0 < E; d0 += 4 * 128) {            // 4 dims per thread, positions in fixed (b, t) order
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int q = p; q < P; ++q) {
-      if (tok[q] != token) continue;
+    for (int i = 0; i < cnt; ++i) {
+      const int q = mlist[i];
       const int b = q / T, t = q - b * T;
       const long long row = (long long)t * B + b;
 #pragma unroll
@@ -347,7 +370,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int d = d0 + j * 128 + threadIdx.x;
-      if (d < E) demb[token * E + d] += acc[j];
+      if (d < E) demb[(long long)token * E + d] += acc[j];
     }
   }
 }
@@ -363,7 +386,9 @@ extern "C" int dwc_embed_concat_bwd(const int64_t* tokens, const float* dx, cons
   embed_concat_bwd_style_kernel<<<grid1d((long long)b * s), 256, 0, as_stream(stream)>>>(dx, dstyle, b, t, e, s);
   DWC_LAUNCH_CHECK();
   if (demb) {
-    embed_bwd_owner_kernel<<<b * t, 128, 0, as_stream(stream)>>>(tokens, dx, mask, demb, b, t, e, s, pad_idx);
+    DWC_CHECK((long long)b * t * 8 <= 48 * 1024, "dwc_embed_concat_bwd: %d x %d tokens exceed the shared-memory lists", b, t);
+    embed_bwd_owner_kernel<<<b * t, 128, (size_t)b * t * 8, as_stream(stream)>>>(tokens, dx, mask, demb, b, t, e, s,
+                                                                                 pad_idx);
     DWC_LAUNCH_CHECK();
   }
   return 0;

@@ -641,7 +641,7 @@ extern "C" int dwc_post_fwd(const dwc_hbuf_t* y, const float* coef, int act, con
   HB hy(*y), ho(*out), hr = res ? HB(*res) : HB(*y);
   long long total = ho.padded_pixels() * (out->c / 8);
   {
-    RowP rp;
+    RowP rp{};
     if (rowpipe_geom(y, &rp.nseg, &rp.segw, &rp.segbytes) && out->dtype == DWC_BF16 && (!res || res->layout == 0) &&
         out->halo <= y->h - 1 && out->halo <= y->w - 1) {
       rp.y = hy; rp.d = hr; rp.o1 = ho; rp.o2 = ho;
@@ -663,6 +663,30 @@ extern "C" int dwc_post_fwd(const dwc_hbuf_t* y, const float* coef, int act, con
   }
   DWC_LAUNCH_CHECK();
   return 0;
+}
+
+// statistics -> coefficients -> normalise / activation / residual / pad: the coefficient step runs inside the
+// row-streaming kernel when the site is eligible (no dwc_norm_finalize launch), else as the separate passes
+extern "C" int dwc_post_fwd_norm(const dwc_hbuf_t* y, int kind, const float* stats, int splits, float eps,
+                                 const float* weight, const float* bias, int act, const dwc_hbuf_t* res,
+                                 const dwc_hbuf_t* out, float* coef, dwc_stream_t stream) {
+  DWC_CHECK(kind >= 1 && kind <= 3, "dwc_post_fwd_norm: bad kind");
+  DWC_CHECK(y->n == out->n && y->h == out->h && y->w == out->w && y->c == out->c && y->dtype == out->dtype,
+            "dwc_post_fwd_norm: geometry mismatch");
+  RowP rp{};
+  if (rowpipe_geom(y, &rp.nseg, &rp.segw, &rp.segbytes) && y->c <= 512 && (!res || res->layout == 0) &&
+      out->halo <= y->h - 1 && out->halo <= y->w - 1 &&
+      (out->layout == 0 || ((out->h + 2 * out->halo) % 2 == 0 && (out->w + 2 * out->halo) % 2 == 0))) {
+    HB hy(*y), ho(*out), hr = res ? HB(*res) : HB(*y);
+    rp.y = hy; rp.d = hr; rp.o1 = ho; rp.o2 = ho;
+    rp.act = act; rp.has_d = res != nullptr; rp.has_o2 = 0;
+    rp.nstats = reinterpret_cast<const float2*>(stats); rp.nweight = weight; rp.nbias = bias;
+    rp.coef_out = reinterpret_cast<float4*>(coef);
+    rp.nkind = kind; rp.nsplits = splits; rp.nhw = y->h * y->w; rp.neps = eps;
+    return rowpipe_launch<RM_FWD>(rp, res ? 2 : 1, 0, y->n, as_stream(stream));
+  }
+  if (dwc_norm_finalize(kind, stats, splits, y->n, y->c, y->h * y->w, eps, weight, bias, coef, stream)) return 1;
+  return dwc_post_fwd(y, coef, act, res, out, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -786,7 +810,7 @@ extern "C" int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, c
   HB hd(*dout), hy(*y), hdy(*dy), hr = dres ? HB(*dres) : HB(*dy);
   if (prefolded) hd.refl = 0;
   {
-    RowP rp;
+    RowP rp{};
     if (rowpipe_geom(y, &rp.nseg, &rp.segw, &rp.segbytes) && (prefolded || dout->halo == 0) && dy->dtype == DWC_BF16 &&
         dout->dtype == DWC_BF16 && (!dres || (dres->layout == 0 && dres->dtype == DWC_BF16)) &&
         (dout->layout == 0 || rp.nseg == 1)) {
@@ -816,6 +840,41 @@ extern "C" int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, c
   }
   DWC_LAUNCH_CHECK();
   return 0;
+}
+
+// reductions -> coefficients (+ parameter gradients) -> apply: the coefficient step runs inside the row-streaming
+// kernel when the site is eligible (no dwc_norm_bwd_finalize launch), else as the separate passes (bco = scratch [N,C,4])
+extern "C" int dwc_post_bwd_apply_norm(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, int kind,
+                                       const float* red, int splits, float eps, const float* weight, float* dweight,
+                                       float* dbias, float* bco, int act, const dwc_hbuf_t* dy, const dwc_hbuf_t* dres,
+                                       int prefolded, dwc_stream_t stream) {
+  DWC_CHECK(kind >= 1 && kind <= 3, "dwc_post_bwd_apply_norm: bad kind");
+  DWC_CHECK(y->c % 8 == 0 && y->layout == 0 && dy->layout == 0, "dwc_post_bwd_apply_norm: needs C %% 8 == 0, plain y/dy");
+  DWC_CHECK(dout->n == y->n && dout->h == y->h && dout->w == y->w && dout->c == y->c,
+            "dwc_post_bwd_apply_norm: geometry mismatch");
+  RowP rp{};
+  if (rowpipe_geom(y, &rp.nseg, &rp.segw, &rp.segbytes) && y->c <= 512 && (prefolded || dout->halo == 0) &&
+      dy->dtype == DWC_BF16 && dout->dtype == DWC_BF16 && (!dres || (dres->layout == 0 && dres->dtype == DWC_BF16)) &&
+      (dout->layout == 0 || rp.nseg == 1)) {
+    HB hd(*dout), hy(*y), hdy(*dy), hr = dres ? HB(*dres) : HB(*dy);
+    hd.refl = 0;
+    rp.y = hy; rp.d = hd; rp.o1 = hdy; rp.o2 = hr;
+    rp.coef = reinterpret_cast<const float4*>(coef);
+    rp.act = act; rp.has_d = 1; rp.has_o2 = dres != nullptr;
+    rp.nstats = reinterpret_cast<const float2*>(red); rp.nweight = weight;
+    rp.dweight = dweight; rp.dbias = dbias;
+    rp.nkind = kind; rp.nsplits = splits; rp.nhw = y->h * y->w; rp.neps = eps;
+    if (rowpipe_launch<RM_BAPPLY>(rp, 2, 0, y->n, as_stream(stream))) return 1;
+    if (kind == 3) {
+      ln_param_grad_kernel<<<cdiv((long long)y->c * 32, 256), 256, 0, as_stream(stream)>>>(
+          reinterpret_cast<const float2*>(red), splits, reinterpret_cast<const float4*>(coef), y->n, y->c, dweight, dbias);
+      DWC_LAUNCH_CHECK();
+    }
+    return 0;
+  }
+  if (dwc_norm_bwd_finalize(kind, red, splits, coef, y->n, y->c, y->h * y->w, eps, weight, dweight, dbias, bco, stream))
+    return 1;
+  return dwc_post_bwd_apply(dout, y, coef, bco, act, dy, dres, prefolded, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1712,7 +1771,7 @@ extern "C" int dwc_nc_stats(const dwc_hbuf_t* y, int splits, float* stats, dwc_s
   DWC_CHECK(y->c % 8 == 0 && y->layout == 0, "dwc_nc_stats: needs C %% 8 == 0 and plain layout");
   HB hy(*y);
   {
-    RowP rp;
+    RowP rp{};
     if (rowpipe_geom(y, &rp.nseg, &rp.segw, &rp.segbytes)) {
       rp.y = hy; rp.d = hy; rp.o1 = hy; rp.o2 = hy;
       rp.coef = nullptr; rp.bco = nullptr; rp.part = reinterpret_cast<float2*>(stats);
@@ -1742,7 +1801,7 @@ extern "C" int dwc_post_bwd_reduce(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, 
   HB hy(*y), hd(*dout);
   if (prefolded) hd.refl = 0;
   {
-    RowP rp;
+    RowP rp{};
     if (rowpipe_geom(y, &rp.nseg, &rp.segw, &rp.segbytes) && (prefolded || dout->halo == 0) &&
         (dout->layout == 0 || rp.nseg == 1)) {
       rp.y = hy; rp.d = hd; rp.o1 = hy; rp.o2 = hy;

@@ -23,6 +23,15 @@ struct RowP {
   float2* part;         // RM_STATS / RM_BRED: [n][split][c]
   int act, has_d, has_o2;
   int nseg, segw, segbytes, stages;
+  // optional in-kernel coefficient computation (replaces the separate finalize launches): kind 1 IN, 2 AdaIN, 3 LN
+  const float2* nstats;    // RM_FWD: per-(n, split, c) {sum, sum of squares}; RM_BAPPLY: {sum dz, sum dz*y}; null = use coef/bco
+  const float* nweight;    // AdaIN [N,C] / LN [C] scale
+  const float* nbias;      // AdaIN [N,C] / LN [C] shift (RM_FWD)
+  float4* coef_out;        // RM_FWD: {scale, shift, mean, rstd} for the backward pass
+  float* dweight;          // RM_BAPPLY, AdaIN: [N,C] parameter gradients (overwritten)
+  float* dbias;
+  int nkind, nsplits, nhw;
+  float neps;
   int dbytes;      // bytes of the second operand per stage (0: none).  d in parity-plane layout: the two plane rows of the
   int d_planes;    // padded row (even X, odd X), wq*C elements each, loaded whole (nseg == 1)
 };
@@ -87,6 +96,102 @@ __device__ __forceinline__ void rp_zero_halo(const HB& b, int n, int iy, int cvs
   }
 }
 
+// Forward coefficients of sample n for all C channels -> shared memory (and global memory for the backward pass when
+// `write`): the arithmetic of norm_finalize_kernel, executed by every CTA of the sample on the (L2-resident) partial sums.
+__device__ __forceinline__ void rp_fwd_coef(const RowP& p, int n, int C, float2* sco, double* dsm, bool write) {
+  const int tid = threadIdx.x, splits = p.nsplits, hw = p.nhw;
+  if (p.nkind == 3) {
+    double s = 0, q = 0;
+    for (int c = tid; c < C; c += 256)
+      for (int k = 0; k < splits; ++k) {
+        const float2 v = p.nstats[((long long)n * splits + k) * C + c];
+        s += v.x; q += v.y;
+      }
+    s = block_sum_d(s, dsm);
+    q = block_sum_d(q, dsm);
+    const double M = (double)C * hw;
+    const double mean = s / M;
+    double var = (q - M * mean * mean) / (M - 1.0);
+    if (var < 0) var = 0;
+    const float inv = (float)(1.0 / (sqrt(var) + (double)p.neps));
+    for (int c = tid; c < C; c += 256) {
+      const float g = p.nweight[c], b = p.nbias[c];
+      const float4 cf = make_float4(g * inv, b - (float)mean * g * inv, (float)mean, inv);
+      sco[c] = make_float2(cf.x, cf.y);
+      if (write) p.coef_out[(long long)n * C + c] = cf;
+    }
+  } else {
+    for (int c = tid; c < C; c += 256) {
+      double s = 0, q = 0;
+      for (int k = 0; k < splits; ++k) {
+        const float2 v = p.nstats[((long long)n * splits + k) * C + c];
+        s += v.x; q += v.y;
+      }
+      const double mean = s / hw;
+      double var = q / hw - mean * mean;
+      if (var < 0) var = 0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)p.neps));
+      const float w = p.nkind == 2 ? p.nweight[(long long)n * C + c] : 1.f;
+      const float b = p.nkind == 2 ? p.nbias[(long long)n * C + c] : 0.f;
+      const float4 cf = make_float4(w * rstd, b - (float)mean * rstd * w, (float)mean, rstd);
+      sco[c] = make_float2(cf.x, cf.y);
+      if (write) p.coef_out[(long long)n * C + c] = cf;
+    }
+  }
+  __syncthreads();
+}
+
+// Backward coefficients {a, b, c} of dy = a*dz + b*y + c (norm_bwd_finalize_kernel's arithmetic) -> shared memory;
+// AdaIN parameter gradients are written by the sample's first CTA.
+__device__ __forceinline__ void rp_bwd_coef(const RowP& p, int n, int C, float4* sbco, double* dsm, bool write) {
+  const int tid = threadIdx.x, splits = p.nsplits, hw = p.nhw;
+  if (p.nkind == 3) {
+    const double M = (double)C * hw;
+    const double mean = p.coef[(long long)n * C].z;
+    double g1 = 0, g2 = 0;
+    for (int c = tid; c < C; c += 256) {
+      double S1 = 0, S2 = 0;
+      for (int k = 0; k < splits; ++k) {
+        const float2 v = p.nstats[((long long)n * splits + k) * C + c];
+        S1 += v.x; S2 += v.y;
+      }
+      const double g = p.nweight[c];
+      g1 += g * S1;
+      g2 += g * (S2 - mean * S1);
+    }
+    g1 = block_sum_d(g1, dsm);
+    g2 = block_sum_d(g2, dsm);
+    const double inv = p.coef[(long long)n * C].w;
+    const double sd = 1.0 / inv - (double)p.neps;
+    const double K = sd > 0 ? g2 * inv * inv / ((M - 1.0) * sd) : 0.0;
+    const double b = -K;
+    const double cc = -g1 * inv / M + K * mean;
+    for (int c = tid; c < C; c += 256) sbco[c] = make_float4((float)(p.nweight[c] * inv), (float)b, (float)cc, 0.f);
+  } else {
+    for (int c = tid; c < C; c += 256) {
+      double S1 = 0, S2 = 0;
+      for (int k = 0; k < splits; ++k) {
+        const float2 v = p.nstats[((long long)n * splits + k) * C + c];
+        S1 += v.x; S2 += v.y;
+      }
+      const float4 q = p.coef[(long long)n * C + c];
+      const double mean = q.z, rstd = q.w;
+      const double w = p.nkind == 2 ? (double)p.nweight[(long long)n * C + c] : 1.0;
+      const double m1 = S1 / hw;
+      const double m2 = rstd * (S2 / hw - mean * m1);
+      if (p.nkind == 2 && write) {
+        p.dbias[(long long)n * C + c] = (float)S1;
+        p.dweight[(long long)n * C + c] = (float)(rstd * (S2 - mean * S1));
+      }
+      const double a = w * rstd;
+      const double b = -rstd * rstd * w * m2;
+      const double cc = -rstd * w * m1 - b * mean;
+      sbco[c] = make_float4((float)a, (float)b, (float)cc, 0.f);
+    }
+  }
+  __syncthreads();
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p) {
   extern __shared__ __align__(128) uint8_t rsm[];
@@ -142,14 +247,30 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
   for (int e = 0; e < 8; ++e) {
     sc[e] = 1.f; sh[e] = 0.f; ba[e] = 1.f; bb[e] = 0.f; bc[e] = 0.f;
   }
-  if (MODE != RM_STATS && p.coef) {
+  __shared__ float4 s_co[512];                          // in-kernel coefficients (C <= 512)
+  __shared__ double s_d[256];
+  if (MODE == RM_FWD && p.nstats) {
+    rp_fwd_coef(p, n, C, reinterpret_cast<float2*>(s_co), s_d, blockIdx.x == 0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float2 q = reinterpret_cast<const float2*>(s_co)[c0 + e];
+      sc[e] = q.x; sh[e] = q.y;
+    }
+  } else if (MODE != RM_STATS && p.coef) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float4 q = __ldg(p.coef + (long long)n * C + c0 + e);
       sc[e] = q.x; sh[e] = q.y;
     }
   }
-  if (MODE == RM_BAPPLY && p.bco) {
+  if (MODE == RM_BAPPLY && p.nstats) {
+    rp_bwd_coef(p, n, C, s_co, s_d, blockIdx.x == 0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float4 q = s_co[c0 + e];
+      ba[e] = q.x; bb[e] = q.y; bc[e] = q.z;
+    }
+  } else if (MODE == RM_BAPPLY && p.bco) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float4 q = __ldg(p.bco + (long long)n * C + c0 + e);
@@ -301,7 +422,7 @@ static int rowpipe_launch(RowP& p, int nb, int row_splits, int n, cudaStream_t s
     p.dbytes = p.d.wp * p.d.c * 2;
   }
   const int stage_bytes = p.segbytes + p.dbytes;
-  int stages = 98304 / stage_bytes;
+  int stages = 103000 / stage_bytes;                   // 2 CTAs per SM next to ~11 KB of static shared memory
   if (stages > 4) stages = 4;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -313,7 +434,7 @@ static int rowpipe_launch(RowP& p, int nb, int row_splits, int n, cudaStream_t s
     attr = smem;
   }
   if (row_splits <= 0) {
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    int per_sm = (int)((227 * 1024) / (smem + 12 * 1024));
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     row_splits = (per_sm * dwc_num_sms()) / n;

@@ -442,10 +442,12 @@ class PostFn(torch.autograd.Function):
                 stats = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
                 _call("dwc_nc_stats", C.byref(ys), splits, L.ptr(stats), L.stream())
                 coef = torch.empty(n * c * 4, dtype=torch.float32, device=dev)
-                _call("dwc_norm_finalize", kind, L.ptr(stats), splits, n, c, hw, L.f32(eps), L.ptr(nw), L.ptr(nb),
-                      L.ptr(coef), L.stream())
-            _call("dwc_post_fwd", C.byref(ys), L.ptr(coef), act, C.byref(rs) if rs is not None else None, C.byref(os_),
-                  L.stream())
+                # statistics -> coefficients inside the normalise kernel (or a separate finalize pass, see the C side)
+                _call("dwc_post_fwd_norm", C.byref(ys), kind, L.ptr(stats), splits, L.f32(eps), L.ptr(nw), L.ptr(nb),
+                      act, C.byref(rs) if rs is not None else None, C.byref(os_), L.ptr(coef), L.stream())
+            else:
+                _call("dwc_post_fwd", C.byref(ys), None, act, C.byref(rs) if rs is not None else None, C.byref(os_),
+                      L.stream())
         ctx.fused = fused
         ctx.meta = (y.n, y.h, y.w, y.c, y.halo, kind, act, out_halo, out_layout, eps, splits,
                     (res.n, res.h, res.w, res.c, res.halo, res.layout) if res is not None else None)
@@ -478,7 +480,6 @@ class PostFn(torch.autograd.Function):
         else:
             # fold the reflect-halo gradient once, in place: the streaming passes then read whole interior rows
             pre = _prefold(dout)
-            bco = None
             if kind != NORM_NONE:
                 red = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
                 _call("dwc_post_bwd_reduce", C.byref(ds), C.byref(ys), L.ptr(coef), act, splits, L.ptr(red), pre,
@@ -492,10 +493,13 @@ class PostFn(torch.autograd.Function):
                     gw, gb = ctx.ln_mod.grad_buffers()
                 else:
                     gw = gb = None
-                _call("dwc_norm_bwd_finalize", kind, L.ptr(red), splits, L.ptr(coef), n, c, h * w, L.f32(eps), L.ptr(nw),
-                      L.ptr(gw), L.ptr(gb), L.ptr(bco), L.stream())
-            _call("dwc_post_bwd_apply", C.byref(ds), C.byref(ys), L.ptr(coef), L.ptr(bco), act, C.byref(dys),
-                  C.byref(drs) if drs is not None else None, pre, L.stream())
+                # reductions -> coefficients (+ AdaIN / LayerNorm parameter gradients) -> apply
+                _call("dwc_post_bwd_apply_norm", C.byref(ds), C.byref(ys), L.ptr(coef), kind, L.ptr(red), splits,
+                      L.f32(eps), L.ptr(nw), L.ptr(gw), L.ptr(gb), L.ptr(bco), act, C.byref(dys),
+                      C.byref(drs) if drs is not None else None, pre, L.stream())
+            else:
+                _call("dwc_post_bwd_apply", C.byref(ds), C.byref(ys), None, None, act, C.byref(dys),
+                      C.byref(drs) if drs is not None else None, pre, L.stream())
         dres_t = dres.t if dres is not None else None
         if dres is not None and ctx.skip_box is not None:
             ctx.skip_box["dres"] = dres          # handed to ConvFn.backward of the block's first conv (see there)

@@ -164,6 +164,17 @@ int dwc_norm_bwd_finalize(int kind, const float* red, int splits, const float* c
 int dwc_post_bwd_apply(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, const float* bco,
                        int act, const dwc_hbuf_t* dy, const dwc_hbuf_t* dres, int prefolded, dwc_stream_t stream);
 
+/* dwc_norm_finalize + dwc_post_fwd in one call: on the row-streaming path (bf16, rows of >= 2 KB, C <= 512) the
+ * coefficients are computed inside the normalise kernel from the partial statistics (each CTA recomputes its sample's
+ * C coefficients from L2) and `coef` [N,C,4] is written for the backward pass; otherwise the two passes are launched. */
+int dwc_post_fwd_norm(const dwc_hbuf_t* y, int kind, const float* stats, int splits, float eps, const float* weight,
+                      const float* bias, int act, const dwc_hbuf_t* res, const dwc_hbuf_t* out, float* coef,
+                      dwc_stream_t stream);
+/* dwc_norm_bwd_finalize + dwc_post_bwd_apply in one call (same rule; `bco` [N,C,4] is scratch for the two-pass path). */
+int dwc_post_bwd_apply_norm(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, int kind, const float* red,
+                            int splits, float eps, const float* weight, float* dweight, float* dbias, float* bco,
+                            int act, const dwc_hbuf_t* dy, const dwc_hbuf_t* dres, int prefolded, dwc_stream_t stream);
+
 /* nn.Upsample(2, bilinear, align_corners=False) + reflect pad (networks_v2.py:154, networks.py:531). */
 int dwc_upsample_pad_fwd(const dwc_hbuf_t* x, const dwc_hbuf_t* out, dwc_stream_t stream);
 int dwc_upsample_pad_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* dx, int prefolded, dwc_stream_t stream);

@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
 (time timeout -k 10 600 python -m pytest tests -q -m gpu -x --tb=short 2>&1 | grep -v "Warning\|warnings.html\|detach()" | tail -12) > gpurun_out/t_all.log 2>&1
 tail -6 gpurun_out/t_all.log
-TAG=default timeout 200 python tests/diag_graph.py 2>&1 | grep -v Warn | tail -3
+timeout -k 10 300 python bench.py --steps 10 --warmup 4 --no-cpu-baseline 2>gpurun_out/bench27.err | tail -1 > gpurun_out/bench27.json
+cut -c1-200 gpurun_out/bench27.json
+timeout -k 10 900 python tools/timeline_step.py 16 2>&1 | grep -v Warn > gpurun_out/timeline.txt; head -8 gpurun_out/timeline.txt; grep "embed\|row_kernel\|finalize" gpurun_out/timeline.txt
