@@ -92,13 +92,21 @@ def one_step(s, cfg, b, it):
     s.update_attention_status(it)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at its in-step shape, from the
+# `ncu --set full` capture summarised in profiles/r01g_ncu_g7_b48.md (None until measured for another batch)
+G7_TRAFFIC_BYTES = {48: None}
+
+
 def conv_roofline(peaks, B):
-    """Dominant kernel: tcgen05 implicit-GEMM conv at the G7 geometry (3x3, 256->256 @32x32: 16 of the 27 generator
-    convs).  Timed alone with CUDA events, rotating over enough buffers to exceed the 126 MB L2."""
+    """Dominant kernel of the step: the tcgen05 implicit-GEMM conv at the G7 geometry (3x3, 256->256 @32x32: 16 of
+    the 27 generator convs) at the batch it runs with inside the step - the three gradient-carrying decodes / the three
+    re-encodes of gen_update are one 3B batch, which the persistent kernel variant serves (64 launches x ~50 us per
+    step against 67 x ~25 us for the single-batch launches of the same geometry).  Timed alone with CUDA events,
+    rotating over enough buffers to exceed the 126 MB L2."""
     from dwc_gan_b200 import _lib as L, plan as P
     from dwc_gan_b200.plan import HB
-    n, c, hw = B, 256, 32
-    nbuf = 16
+    n, c, hw = 3 * B, 256, 32
+    nbuf = 8
     xs = [HB(torch.randn(n, hw + 2, hw + 2, c, device="cuda").to(torch.bfloat16), n, hw, hw, c, 1, 0) for _ in range(nbuf)]
     ys = [HB.empty(n, hw, hw, c, 2, 0, torch.bfloat16, "cuda") for _ in range(nbuf)]
     w = (torch.randn(c, 9 * c, device="cuda") * 0.02).to(torch.bfloat16)
@@ -107,7 +115,7 @@ def conv_roofline(peaks, B):
     for p in plans[:4]:
         p.launch()
     torch.cuda.synchronize()
-    reps = 4
+    reps = 6
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
@@ -118,14 +126,11 @@ def conv_roofline(peaks, B):
     ms = e0.elapsed_time(e1) / (reps * nbuf)
     flops = 2.0 * n * hw * hw * c * 9 * c
     achieved = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "gconv_tc_kernel<256> (G7 3x3 256->256 @32x32, batch %d)" % n,
+    return {"bound": "tensor", "kernel": "gconv_tcp_kernel<256> (G7 3x3 256->256 @32x32, 3 x batch %d = %d images)" % (B, n),
             "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-            "frac": round(achieved / peaks["tflops"], 4),
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this kernel at
-            # this geometry (profiles/r01c_ncu_prof_g7_old.txt): input + weights are read once (10.7 MB vs 10.7 MB
-            # algorithmic), the 10.6 MB output was still in L2 when the capture ended
-            "traffic": 10705152 if n == 16 else None, "algorithmic_flops": flops, "peak_source": peaks["src"] + " burst",
-            "us_per_launch": round(ms * 1e3, 2)}
+            "frac": round(achieved / peaks["tflops"], 4), "traffic": G7_TRAFFIC_BYTES.get(n),
+            "algorithmic_flops": flops, "algorithmic_bytes": int(xs[0].t.numel() * 2 + ys[0].t.numel() * 2 + w.numel() * 2),
+            "peak_source": peaks["src"] + " burst", "us_per_launch": round(ms * 1e3, 2)}
 
 
 def cpu_baseline(sample_b=2):

@@ -1379,11 +1379,147 @@ __global__ void __launch_bounds__(256) upsample_pad_bwd_fast_kernel(HB dout, HB 
   }
 }
 
+// Row-streaming forward (bf16): input rows arrive by 1-D bulk copies in a shared-memory ring; a CTA owns a range of
+// input rows and produces the two output rows between each consecutive pair (plus the image's first / last row), one
+// thread per (pair of neighbouring input columns, 8 channels): 4 shared-memory reads give a 2 x 2 block of outputs.
+struct UpP {
+  HB x, out;
+  int stages, rowbytes;
+};
+
+__global__ void __launch_bounds__(256) row_up_fwd_kernel(const __grid_constant__ UpP p) {
+  extern __shared__ __align__(128) uint8_t usm[];
+  __shared__ uint64_t full[8];
+  const int tid = threadIdx.x, n = blockIdx.y;
+  const int H = p.x.h, W = p.x.w, C = p.x.c, cvs = C >> 3, S = p.stages;
+  const int r0 = (int)(((long long)blockIdx.x * H) / gridDim.x), r1 = (int)(((long long)(blockIdx.x + 1) * H) / gridDim.x);
+  if (r1 <= r0) return;
+  const int lo = max(r0 - 1, 0), hi = min(r1, H - 1), cnt = hi - lo + 1;
+  const bf16* xb = reinterpret_cast<const bf16*>(p.x.ptr);
+  bf16* ob = reinterpret_cast<bf16*>(p.out.ptr);
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  int issued = 0;                                       // thread 0 only
+  auto issue_upto = [&](int last) {
+    while (issued < cnt && issued <= last) {
+      const int s = issued % S;
+      mbar_expect_tx(&full[s], (uint32_t)p.rowbytes);
+      bulk_load_1d(usm + (size_t)s * p.rowbytes, xb + p.x.off(n, lo + issued, 0), (uint32_t)p.rowbytes, &full[s]);
+      ++issued;
+    }
+  };
+  if (tid == 0) issue_upto(S - 1);
+  const int halo = p.out.halo, HO = 2 * H, WO = 2 * W;
+  int waited = -1;                                      // highest unit whose barrier this thread has passed
+  for (int a = r0 - 1; a <= r1 - 1; ++a) {
+    const int ia = max(a, 0), ib = min(a + 1, H - 1);
+    __syncthreads();                                    // the previous pair is done: units below ia - lo are dead
+    if (tid == 0) issue_upto(ia - lo + S - 1);
+    for (int u = waited + 1; u <= ib - lo; ++u) mbar_wait(&full[u % S], (uint32_t)((u / S) & 1));
+    waited = max(waited, ib - lo);
+    const uint8_t* rowA = usm + (size_t)((ia - lo) % S) * p.rowbytes;
+    const uint8_t* rowB = usm + (size_t)((ib - lo) % S) * p.rowbytes;
+    // output rows 2a+1 (weights .75 / .25 on rows a, a+1) and 2a+2 (.25 / .75; the image's first row takes row 0 alone)
+    const int oyk[2] = {2 * a + 1, 2 * a + 2};
+    bool vk[2];
+    int Yk[2][3];                                       // primary padded row and up to two reflected copies (-1 = none)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int oy = oyk[k];
+      vk[k] = oy >= 2 * r0 && oy < 2 * r1 && oy >= 0 && oy < HO;
+      Yk[k][0] = oy + halo;
+      Yk[k][1] = (halo > 0 && oy >= 1 && oy <= halo) ? halo - oy : -1;
+      Yk[k][2] = (halo > 0 && oy >= HO - 1 - halo && oy <= HO - 2) ? halo + 2 * (HO - 1) - oy : -1;
+    }
+    const float wyk[2][2] = {{0.75f, 0.25f}, {a < 0 ? 1.f : 0.25f, a < 0 ? 0.f : 0.75f}};
+    for (int t = tid; t < (W + 1) * cvs; t += 256) {
+      const int jj = t / cvs - 1, cv = t - (jj + 1) * cvs;
+      const int ja = max(jj, 0), jb = min(jj + 1, W - 1);
+      float va[8], vb[8], vc[8], vd[8];
+      rp_unpack8(*reinterpret_cast<const uint4*>(rowA + ((size_t)ja * cvs + cv) * 16), va);
+      rp_unpack8(*reinterpret_cast<const uint4*>(rowA + ((size_t)jb * cvs + cv) * 16), vb);
+      rp_unpack8(*reinterpret_cast<const uint4*>(rowB + ((size_t)ja * cvs + cv) * 16), vc);
+      rp_unpack8(*reinterpret_cast<const uint4*>(rowB + ((size_t)jb * cvs + cv) * 16), vd);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        // output columns 2jj+1 (.75 / .25 on columns jj, jj+1) and 2jj+2 (.25 / .75; column 0 takes column 0 alone)
+        const int ox = 2 * jj + 1 + m;
+        if (ox < 0 || ox >= WO) continue;
+        const float wx0 = m == 0 ? 0.75f : (jj < 0 ? 1.f : 0.25f), wx1 = m == 0 ? 0.25f : (jj < 0 ? 0.f : 0.75f);
+        float top[8], bot[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          top[e] = wx0 * va[e] + wx1 * vb[e];
+          bot[e] = wx0 * vc[e] + wx1 * vd[e];
+        }
+        const int X0 = ox + halo;
+        const int X1 = (halo > 0 && ox >= 1 && ox <= halo) ? halo - ox : -1;
+        const int X2 = (halo > 0 && ox >= WO - 1 - halo && ox <= WO - 2) ? halo + 2 * (WO - 1) - ox : -1;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (!vk[k]) continue;
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = wyk[k][0] * top[e] + wyk[k][1] * bot[e];
+          const uint4 ov = rp_pack8(o);
+#pragma unroll
+          for (int yi = 0; yi < 3; ++yi) {
+            const int Y = Yk[k][yi];
+            if (Y < 0) continue;
+            bf16* rowp = ob + p.out.off_padded(n, Y, 0) + cv * 8;
+            *reinterpret_cast<uint4*>(rowp + (long long)X0 * C) = ov;
+            if (X1 >= 0) *reinterpret_cast<uint4*>(rowp + (long long)X1 * C) = ov;
+            if (X2 >= 0) *reinterpret_cast<uint4*>(rowp + (long long)X2 * C) = ov;
+          }
+        }
+      }
+    }
+  }
+}
+
+static bool row_up_ok(const dwc_hbuf_t* x, const dwc_hbuf_t* out) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DWC_ROWUP");
+    on = e ? atoi(e) : 1;
+  }
+  const long long rowbytes = (long long)x->w * x->c * 2;
+  return on && rowpipe_enabled() && x->dtype == DWC_BF16 && out->dtype == DWC_BF16 && x->layout == 0 && out->layout == 0 &&
+         x->c % 8 == 0 && rowbytes >= 2048 && rowbytes <= 32768 && out->halo <= 2 * x->h - 1 && out->halo <= 2 * x->w - 1;
+}
+
 extern "C" int dwc_upsample_pad_fwd(const dwc_hbuf_t* x, const dwc_hbuf_t* out, dwc_stream_t stream) {
   DWC_CHECK(x->c % 8 == 0 && out->h == 2 * x->h && out->w == 2 * x->w && out->c == x->c && out->n == x->n,
             "dwc_upsample_pad_fwd: geometry mismatch");
   HB hx(*x), ho(*out);
   long long total = ho.padded_pixels() * (out->c / 8);
+  if (row_up_ok(x, out)) {
+    UpP up;
+    up.x = hx; up.out = ho;
+    up.rowbytes = x->w * x->c * 2;
+    up.stages = 65536 / up.rowbytes;
+    if (up.stages > 4) up.stages = 4;
+    if (up.stages < 3) up.stages = 3;
+    const size_t smem = (size_t)up.stages * up.rowbytes;
+    static size_t attr = 0;
+    if (smem > attr) {
+      DWC_CUDA(cudaFuncSetAttribute(row_up_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = smem;
+    }
+    int per_sm = 1;                                    // resident CTAs per SM (registers and shared memory): one wave
+    DWC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, row_up_fwd_kernel, 256, smem));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    int splits = (per_sm * dwc_num_sms()) / x->n;
+    if (splits > x->h) splits = x->h;
+    if (splits < 1) splits = 1;
+    row_up_fwd_kernel<<<dim3(splits, x->n), 256, smem, as_stream(stream)>>>(up);
+    DWC_LAUNCH_CHECK();
+    return 0;
+  }
   if (x->dtype == DWC_BF16 && ps_ok(out->c) && x->layout == 0 && out->layout == 0) {
     upsample_pad_fwd_fast_kernel<<<ps_grid(ho.hp * ho.wp, out->c / 8, out->n), 256, 0, as_stream(stream)>>>(hx, ho);
     DWC_LAUNCH_CHECK();

@@ -434,7 +434,8 @@ static int rowpipe_launch(RowP& p, int nb, int row_splits, int n, cudaStream_t s
     attr = smem;
   }
   if (row_splits <= 0) {
-    int per_sm = (int)((227 * 1024) / (smem + 12 * 1024));
+    int per_sm = 1;                                    // resident CTAs per SM (registers and shared memory)
+    DWC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, row_kernel<MODE>, 256, smem));
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     row_splits = (per_sm * dwc_num_sms()) / n;

@@ -54,6 +54,13 @@ def test_conv_plans_match_torch(n, h, w, cin, cout, k, s, p):
         emu.emu_gconv(q)
     got = dxp.padded_nhwc().permute(0, 3, 1, 2)
     assert torch.allclose(got, xpad.grad, atol=1e-10)
+    if s == 1:
+        # accumulate mode (ResBlock skip gradient already in the buffer): out += result
+        skip = torch.randn_like(dxp.t)
+        dxa = HB(skip.clone(), n, h, w, cin, p, layout)
+        for q in P.plan_conv_dgrad(dyz, wd, dxa, k, s, 0, accumulate=True):
+            emu.emu_gconv(q)
+        assert torch.allclose(dxa.t, skip + dxp.t, atol=1e-10)
 
     # ---- wgrad (+bias)
     dw = torch.zeros(cout, k, k, cin, dtype=torch.double)

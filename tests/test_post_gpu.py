@@ -130,7 +130,10 @@ def test_post_three_pass(n, c, h, w, kind, act, use_res, oh, ol, yh):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-@pytest.mark.parametrize("n,c,h,w,oh", [(2, 64, 8, 8, 2), (1, 128, 16, 32, 2), (2, 8, 4, 4, 0)])
+@pytest.mark.parametrize("n,c,h,w,oh", [(2, 64, 8, 8, 2), (1, 128, 16, 32, 2), (2, 8, 4, 4, 0),
+                                       # row-streaming forward at the in-network shapes, odd heights, one row
+                                       (2, 256, 32, 32, 2), (1, 128, 64, 64, 2), (3, 64, 5, 16, 1), (2, 64, 1, 16, 0),
+                                       (1, 64, 7, 256, 3)])
 def test_upsample_pad(mode, n, c, h, w, oh):
     dwc_gan_b200.set_mode(mode)
     dtype = torch.float32 if mode == "fp32" else torch.bfloat16
