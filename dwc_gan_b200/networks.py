@@ -679,6 +679,18 @@ class AdaINGen_v2(_FlatOwner):
         return self.dec(content)
 
     def assign_adain_params(self, adain_params, model):
+        """networks_v2.py:89-95 / networks.py:463-472.  All AdaIN layers of the decoder have the same width, so the
+        [N, L*2*F] MLP output is split by ONE transposing copy into L x (mean, std) contiguous [N*F] vectors (and one
+        gather in backward) instead of 2L slice copies, 2L zero-fills and 2L gradient accumulations per decode."""
+        mods = [m for m in model.modules() if m.__class__.__name__ == "AdaptiveInstanceNorm2d"]
+        feats = {m.num_features for m in mods}
+        if mods and len(feats) == 1 and adain_params.is_cuda and adain_params.dim() == 2 and \
+                adain_params.size(1) == 2 * len(mods) * mods[0].num_features:
+            parts = ops.AdainSplitFn.apply(adain_params, len(mods), mods[0].num_features)
+            for i, m in enumerate(mods):
+                m.bias = parts[2 * i]
+                m.weight = parts[2 * i + 1]
+            return
         for m in model.modules():
             if m.__class__.__name__ == "AdaptiveInstanceNorm2d":
                 mean = adain_params[:, :m.num_features]

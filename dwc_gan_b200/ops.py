@@ -405,6 +405,58 @@ def _prefold(d: HB) -> int:
     return 0
 
 
+class AdainSplitFn(torch.autograd.Function):
+    """[N, L*2*F] AdaIN parameters -> 2L contiguous [N*F] vectors (mean_0, std_0, mean_1, ...) with one copy each way."""
+
+    @staticmethod
+    def forward(ctx, params, nl, f):
+        n = params.shape[0]
+        ctx.meta = (n, nl, f, params.dtype)
+        ctx.set_materialize_grads(False)
+        buf = params.detach().float().view(n, nl, 2, f).permute(1, 2, 0, 3).contiguous()      # [L, 2, N, F]
+        return tuple(buf[l, j].reshape(-1) for l in range(nl) for j in range(2))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        n, nl, f, dtype = ctx.meta
+        ref = next((g for g in grads if g is not None), None)
+        if ref is None:
+            return None, None, None
+        gs = [g.reshape(n, f).float() if g is not None else torch.zeros(n, f, dtype=torch.float32, device=ref.device)
+              for g in grads]
+        g = torch.stack(gs, 0).view(nl, 2, n, f).permute(2, 0, 1, 3).reshape(n, nl * 2 * f)
+        return g.to(dtype), None, None
+
+
+class WeightedSumFn(torch.autograd.Function):
+    """sum_i w_i * term_i over scalar loss terms with constant weights: one stack + one dot product (and one scaling in
+    backward) instead of a multiply and an add kernel per term in each direction."""
+    _wcache = {}
+
+    @staticmethod
+    def forward(ctx, wkey, *terms):
+        dev = terms[0].device
+        w = WeightedSumFn._wcache.get((wkey, dev))
+        if w is None:                                     # built in the eager warm-up steps, before any graph capture
+            w = WeightedSumFn._wcache[(wkey, dev)] = torch.tensor(list(wkey), dtype=torch.float32, device=dev)
+        ctx.save_for_backward(w)
+        ctx.k = len(terms)
+        st = torch.stack([t.reshape(()).float() for t in terms])
+        return torch.dot(st, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        gv = g * w
+        return (None,) + tuple(gv.unbind(0))
+
+
+def weighted_sum(pairs):
+    """pairs: [(scalar tensor, python float weight), ...] -> scalar tensor."""
+    wkey = tuple(float(w) for _, w in pairs)
+    return WeightedSumFn.apply(wkey, *[t for t, _ in pairs])
+
+
 NORM_NONE, NORM_IN, NORM_ADAIN, NORM_LN = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 

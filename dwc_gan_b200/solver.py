@@ -288,12 +288,12 @@ class Solver(nn.Module):
 
         with _frozen(dis):                                      # D weight gradients are never used here
             # D(x_fake) and D(x_fake1) (two calc_gen_loss calls, solver.py:206-207) as one 2B pass over x3[B:]
-            adv = 0
+            adv = []
             for src, cls in dis.forward(x3[B:]):
                 for i in range(2):
-                    adv = adv + ops.mse_const(src[i * B:(i + 1) * B], 1.0) * configs['gan_w']
-                    adv = adv + ops.bce_logits(cls[i * B:(i + 1) * B], label_trg) * configs['cls_w']
-            self.loss_gen_adv = adv
+                    adv.append((ops.mse_const(src[i * B:(i + 1) * B], 1.0), configs['gan_w']))
+                    adv.append((ops.bce_logits(cls[i * B:(i + 1) * B], label_trg), configs['cls_w']))
+            self.loss_gen_adv = ops.weighted_sum(adv)
 
             self.loss_kl_x, self.loss_kl_trg = 0.0, 0.0
             if self.dist_mode == 'kls':
@@ -304,18 +304,20 @@ class Solver(nn.Module):
                 self.loss_kl_trg = gmm_earth_mover_distance_sp(mu_txt, c_trg)
             self.loss_gen_vgg = 0
 
-            self.loss_gen_total = self.loss_gen_adv + \
-                configs['recon_x_w'] * self.loss_gen_recon_x + \
-                configs['recon_c_w'] * self.loss_gen_recon_c_real + \
-                configs['recon_c_w'] * self.loss_gen_recon_c_fake + \
-                configs['recon_c_w'] * self.loss_gen_recon_c_rand + \
-                configs['recon_s_w'] * self.loss_gen_recon_s_real + \
-                configs['recon_s_w'] * self.loss_gen_recon_s_fake + \
-                configs['recon_s_w'] * self.loss_gen_recon_s_rand + \
-                configs['recon_x_cyc_w'] * self.loss_gen_cycrecon_x + \
-                configs['kl_w'] * self.loss_kl_x + \
-                configs['kl_w'] * self.loss_kl_trg - \
-                self._ds_w_dev * self.loss_ds
+            # one stacked dot product instead of a multiply and an add kernel per term (same sum, solver.py:225-237)
+            terms = [(self.loss_gen_adv, 1.0),
+                     (self.loss_gen_recon_x, configs['recon_x_w']),
+                     (self.loss_gen_recon_c_real, configs['recon_c_w']),
+                     (self.loss_gen_recon_c_fake, configs['recon_c_w']),
+                     (self.loss_gen_recon_c_rand, configs['recon_c_w']),
+                     (self.loss_gen_recon_s_real, configs['recon_s_w']),
+                     (self.loss_gen_recon_s_fake, configs['recon_s_w']),
+                     (self.loss_gen_recon_s_rand, configs['recon_s_w']),
+                     (self.loss_gen_cycrecon_x, configs['recon_x_cyc_w']),
+                     (self.loss_kl_x, configs['kl_w']),
+                     (self.loss_kl_trg, configs['kl_w'])]
+            terms = [(t, w) for t, w in terms if isinstance(t, torch.Tensor)]
+            self.loss_gen_total = ops.weighted_sum(terms) - self._ds_w_dev * self.loss_ds
             self.loss_gen_total.backward()
         ops.side_join()
         if self.grad_sync is not None:
@@ -342,12 +344,12 @@ class Solver(nn.Module):
 
         gw, cw = configs['gan_w'], configs['cls_w']
         # D(x_real), D(x_fake), D(x_fake1) as one 3B pass; rows [0,B) real, [B,2B) x_fake, [2B,3B) x_fake1
-        loss = 0.0
+        terms = []
         for src, cls in dis.forward(torch.cat([x_real, fakes], dim=0)):
-            loss = loss + ops.mse_const(src[B:2 * B], 0.0) * gw + ops.mse_const(src[2 * B:], 0.0) * gw
+            terms += [(ops.mse_const(src[B:2 * B], 0.0), gw), (ops.mse_const(src[2 * B:], 0.0), gw)]
             # real-branch terms appear once per calc_dis_loss call, i.e. twice (solver.py:333-334)
-            loss = loss + 2.0 * (ops.mse_const(src[:B], 1.0) * gw + ops.bce_logits(cls[:B], label_src) * cw)
-        self.loss_dis = loss
+            terms += [(ops.mse_const(src[:B], 1.0), 2.0 * gw), (ops.bce_logits(cls[:B], label_src), 2.0 * cw)]
+        self.loss_dis = ops.weighted_sum(terms)
         self.loss_dis_all = self.loss_dis
         self.loss_dis_all.backward()
         ops.side_join()

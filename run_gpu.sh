@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 120 python tools/bench_upsample.py 2>&1 | grep -v Warn | tee gpurun_out/bench_up_row3.log
-timeout -k 10 300 python bench.py --steps 10 --warmup 4 --no-cpu-baseline 2>gpurun_out/bench29.err | tail -1 > gpurun_out/bench29.json
-DWC_ROWUP=0 timeout -k 10 300 python bench.py --steps 10 --warmup 4 --no-cpu-baseline 2>gpurun_out/bench30.err | tail -1 > gpurun_out/bench30.json
-cut -c1-200 gpurun_out/bench29.json gpurun_out/bench30.json; grep -o '"roofline.*' gpurun_out/bench29.json | cut -c1-400
+(time timeout -k 10 600 python -m pytest tests -q -m gpu -x --tb=short 2>&1 | grep -v "Warning\|warnings.html\|detach()" | tail -12) > gpurun_out/t_all.log 2>&1
+tail -6 gpurun_out/t_all.log
+timeout -k 10 300 python bench.py --steps 10 --warmup 4 --no-cpu-baseline 2>gpurun_out/bench31.err | tail -1 > gpurun_out/bench31.json
+cut -c1-200 gpurun_out/bench31.json; grep -o '"gpu_launches": [0-9]*' gpurun_out/bench31.json; tail -2 gpurun_out/bench31.err
