@@ -94,7 +94,9 @@ def one_step(s, cfg, b, it):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at its in-step shape, from the
 # `ncu --set full` capture summarised in profiles/r01g_ncu_g7_b48.md (None until measured for another batch)
-G7_TRAFFIC_BYTES = {48: None}
+# n = 48: 29.71 MB read + 0.08 MB written (input 28.4 MB + weights 1.2 MB read exactly once; the 31.8 MB output was
+# still in the 126 MB L2 when the capture ended)
+G7_TRAFFIC_BYTES = {48: 29794560}
 
 
 def conv_roofline(peaks, B):
