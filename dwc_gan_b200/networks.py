@@ -655,12 +655,16 @@ class AdaINGen_v2(_FlatOwner):
         content, mus, logvar = self.encode(images)
         return self.decode(content, torch.cat(mus, 1) if isinstance(mus, (list, tuple)) else mus)
 
-    def encode_fused(self, images):
-        """(content tensor, mu [B, S], logvar [B, S]) with one shared padded copy of the image."""
+    def encode_fused(self, images, after_style=None):
+        """(content tensor, mu [B, S], logvar [B, S]) with one shared padded copy of the image.  `after_style(mu)` is
+        called between the two encoders: the Solver forks the text encoder (which only needs mu) onto its own stream
+        there, so that its latency-bound LSTM / small-GEMM kernels run under the content encoder's convolutions."""
         self.ensure_flat()
         images = images.contiguous().float()
         rows = ops.image_rows(images, 1, self.enc_style.model[0])     # shared by both 7x7 first layers
         mu, lv = self.enc_style.run(images, rows)
+        if after_style is not None:
+            after_style(mu)
         content = _hb_to_tensor(self.enc_content.run(images, rows))
         return content, mu, lv
 

@@ -41,6 +41,8 @@ class Runtime:
         self.fuse_skip_grad = os.environ.get("DWC_FUSE_SKIP_GRAD", "1") != "0"
         self.batch_pack = os.environ.get("DWC_BATCH_PACK", "1") != "0"
         self.use_conv7 = os.environ.get("DWC_CONV7", "1") != "0"
+        self.use_txt_stream = os.environ.get("DWC_TXT_STREAM", "1") != "0"
+        self.aux_streams = {}
         self.conv7_which = os.environ.get("DWC_CONV7", "1")          # diagnostics: "h" heads only, "d" dgrad only
         self.use_fused_norm = os.environ.get("DWC_FUSED_NORM", "0") != "0"   # opt-in: the row-streaming passes are faster
 
@@ -56,6 +58,13 @@ class Runtime:
 
     def tc_ok(self, *channels):
         return self.use_tc and self.dtype == torch.bfloat16 and all(c % 64 == 0 for c in channels)
+
+    def aux_stream(self, device, name):
+        key = (device.index if device.index is not None else torch.cuda.current_device(), name)
+        st = self.aux_streams.get(key)
+        if st is None:
+            st = self.aux_streams[key] = torch.cuda.Stream(device=key[0])
+        return st
 
     def workspace(self, nbytes, device=None):
         device = device or torch.device("cuda", torch.cuda.current_device())

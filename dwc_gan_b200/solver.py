@@ -153,6 +153,37 @@ class Solver(nn.Module):
     def _blend(self, img, att, x_real):
         return ops.blend(img, att, x_real) if self.use_attention else img
 
+    def _fork_txt(self, box, txt, lens, before=None):
+        """after_style hook of encode_fused: run the text encoder on the device's text stream, ordered after everything
+        enqueued so far (autograd replays its backward on the same stream).  Values and RNG consumption are those of
+        the in-line call; only the kernels' placement changes."""
+        gen = self.gen
+
+        def hook(mu):
+            if before is not None:                        # keeps the reference's order of random draws (solver.py:323)
+                box['pre'] = before()
+            if not (ops.RT.use_txt_stream and mu.is_cuda):
+                box['out'] = gen.encode_txt(mu, txt, lens)
+                return
+            main = torch.cuda.current_stream()
+            ts = ops.RT.aux_stream(mu.device, 'txt')
+            ts.wait_stream(main)
+            with torch.cuda.stream(ts):
+                box['out'] = gen.encode_txt(mu, txt, lens)
+            box['stream'] = ts
+        return hook
+
+    @staticmethod
+    def _join_txt(box):
+        mt, lvt = box['out']
+        ts = box.get('stream')
+        if ts is not None:
+            main = torch.cuda.current_stream()
+            main.wait_stream(ts)
+            for t in list(mt) + list(lvt):
+                t.record_stream(main)
+        return mt, lvt
+
     def _decode(self, content, style):
         img, att = self.gen.decode(content, style)
         return img, att
@@ -250,11 +281,15 @@ class Solver(nn.Module):
         self.gen_opt.zero_grad()
         x_real = x_real.float()
         B = x_real.shape[0]
-        content_real, mu_real, lv_real = gen.encode_fused(x_real)
-        mt, lvt = gen.encode_txt(mu_real, txt_src2trg, txt_lens)
-        mu_txt, lv_txt = torch.cat(mt, dim=1), torch.cat(lvt, dim=1)
+        tbox = {}
+        content_real, mu_real, lv_real = gen.encode_fused(x_real, after_style=self._fork_txt(tbox, txt_src2trg, txt_lens))
         style1 = self._sample_style(c_trg, 'gen1')
         style2 = self._sample_style(c_trg, 'gen2')
+        with torch.no_grad():                                   # solver.py:181 detaches this branch; it does not need
+            x_fake2, att2 = self._decode(content_real, style2)  # the text code, so it runs while the text stream works
+            x_fake2 = self._blend(x_fake2, att2, x_real)
+        mt, lvt = self._join_txt(tbox)
+        mu_txt, lv_txt = torch.cat(mt, dim=1), torch.cat(lvt, dim=1)
 
         # The three decodes that carry gradient (reconstruction, text-driven, sampled: solver.py:157-177) run as ONE
         # 3B batch: no operator of the decoder couples samples (AdaIN / LayerNorm are per sample), so the result is
@@ -262,9 +297,6 @@ class Solver(nn.Module):
         imgs, atts = self._decode(torch.cat([content_real] * 3, dim=0), torch.cat([mu_real, mu_txt, style1], dim=0))
         x3 = self._blend(imgs, atts, x_real.repeat(3, 1, 1, 1) if self.use_attention else None)
         x_real_rec, x_fake, x_fake1 = x3.view(3, B, *x3.shape[1:]).unbind(0)
-        with torch.no_grad():                                   # solver.py:181 detaches this branch
-            x_fake2, att2 = self._decode(content_real, style2)
-            x_fake2 = self._blend(x_fake2, att2, x_real)
         self.loss_ds = ops.l1_loss(x_fake1, x_fake2)
 
         # re-encode the three generated batches together (solver.py:162,182,186)
@@ -335,9 +367,12 @@ class Solver(nn.Module):
         x_real = x_real.float()
         B = x_real.shape[0]
         with torch.no_grad():                                   # G gradients of this phase are discarded anyway
-            content_real, mu_real, _ = gen.encode_fused(x_real)
-            style1 = self._sample_style(c_trg, 'dis1')
-            mt, _ = gen.encode_txt(mu_real, txt_src2trg, txt_lens)
+            tbox = {}
+            content_real, mu_real, _ = gen.encode_fused(
+                x_real, after_style=self._fork_txt(tbox, txt_src2trg, txt_lens,
+                                                   before=lambda: self._sample_style(c_trg, 'dis1')))
+            style1 = tbox['pre']
+            mt, _ = self._join_txt(tbox)
             # both decodes (solver.py:327-328) as one 2B batch
             imgs, atts = self._decode(torch.cat([content_real] * 2, dim=0), torch.cat([torch.cat(mt, dim=1), style1], dim=0))
             fakes = self._blend(imgs, atts, x_real.repeat(2, 1, 1, 1) if self.use_attention else None)

@@ -1,3 +1,6 @@
 mkdir -p gpurun_out
-timeout -k 10 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 10 --warmup 4 --no-cpu-baseline > gpurun_out/bench_8gpu.log 2>&1
-grep '"metric"' gpurun_out/bench_8gpu.log | cut -c1-330; tail -2 gpurun_out/bench_8gpu.log | cut -c1-200
+(time timeout -k 10 600 python -m pytest tests -q -m gpu -x --tb=short 2>&1 | grep -v "Warning\|warnings.html\|detach()" | tail -12) > gpurun_out/t_all.log 2>&1
+tail -6 gpurun_out/t_all.log
+timeout -k 10 300 python bench.py --steps 10 --warmup 4 --no-cpu-baseline 2>gpurun_out/bench32.err | tail -1 > gpurun_out/bench32.json
+DWC_TXT_STREAM=0 timeout -k 10 300 python bench.py --steps 10 --warmup 4 --no-cpu-baseline 2>gpurun_out/bench33.err | tail -1 > gpurun_out/bench33.json
+cut -c1-200 gpurun_out/bench32.json gpurun_out/bench33.json; tail -2 gpurun_out/bench32.err
