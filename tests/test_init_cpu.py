@@ -64,3 +64,41 @@ def test_hot_path_refuses_cpu():
     import pytest
     with pytest.raises(RuntimeError):
         s.gen.encode(torch.zeros(1, 3, 128, 128))
+
+
+def test_adain_split_matches_slicing():
+    """ops.AdainSplitFn (one transposing copy) = the reference's slice-by-slice split (networks.py:463-472), values and
+    gradients, including parts that receive no gradient."""
+    import torch
+    from dwc_gan_b200 import ops
+    torch.manual_seed(0)
+    n, nl, f = 3, 4, 8
+    p1 = torch.randn(n, nl * 2 * f, requires_grad=True)
+    p2 = p1.detach().clone().requires_grad_(True)
+    parts = ops.AdainSplitFn.apply(p1, nl, f)
+    ref, rest = [], p2
+    for _ in range(nl):
+        ref += [rest[:, :f].contiguous().view(-1), rest[:, f:2 * f].contiguous().view(-1)]
+        rest = rest[:, 2 * f:]
+    assert len(parts) == 2 * nl
+    for a, b in zip(parts, ref):
+        assert torch.equal(a, b)
+    w = [torch.randn(n * f) for _ in range(2 * nl)]
+    used = [0, 1, 3, 6]                                   # the other parts get no gradient at all
+    sum((parts[i] * w[i]).sum() for i in used).backward()
+    sum((ref[i] * w[i]).sum() for i in used).backward()
+    assert torch.allclose(p1.grad, p2.grad)
+
+
+def test_weighted_sum_matches_python_sum():
+    import torch
+    from dwc_gan_b200 import ops
+    torch.manual_seed(1)
+    ts = [torch.randn((), requires_grad=True) for _ in range(5)]
+    ws = [1.0, 0.5, 10.0, 0.0, 2.5]
+    out = ops.weighted_sum(list(zip(ts, ws)))
+    ref = sum(t.detach() * w for t, w in zip(ts, ws))
+    assert torch.allclose(out.detach(), ref)
+    out.backward()
+    for t, w in zip(ts, ws):
+        assert abs(float(t.grad) - w) < 1e-6
