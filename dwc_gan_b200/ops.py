@@ -42,6 +42,7 @@ class Runtime:
         self.batch_pack = os.environ.get("DWC_BATCH_PACK", "1") != "0"
         self.use_conv7 = os.environ.get("DWC_CONV7", "1") != "0"
         self.use_txt_stream = os.environ.get("DWC_TXT_STREAM", "1") != "0"
+        self.use_dis_stream = os.environ.get("DWC_DIS_STREAM", "1") != "0"
         self.aux_streams = {}
         self.conv7_which = os.environ.get("DWC_CONV7", "1")          # diagnostics: "h" heads only, "d" dgrad only
         self.use_fused_norm = os.environ.get("DWC_FUSED_NORM", "0") != "0"   # opt-in: the row-streaming passes are faster

@@ -298,6 +298,37 @@ class Solver(nn.Module):
         x3 = self._blend(imgs, atts, x_real.repeat(3, 1, 1, 1) if self.use_attention else None)
         x_real_rec, x_fake, x_fake1 = x3.view(3, B, *x3.shape[1:]).unbind(0)
         self.loss_ds = ops.l1_loss(x_fake1, x_fake2)
+        with _frozen(dis):                                      # D weight gradients are never used in this phase
+            self._gen_update_tail(x_real, x3, x_real_rec, c_src, c_trg, label_trg, content_real, mu_real, lv_real,
+                                  mu_txt, lv_txt, style1, configs, B)
+        ops.side_join()
+        if self.grad_sync is not None:
+            self.grad_sync(self.gen)
+        self.gen_opt.step()
+
+    def _adv_terms(self, x_gen, label_trg, configs, B):
+        """D(x_fake) and D(x_fake1) (two calc_gen_loss calls, solver.py:206-207) as one 2B pass."""
+        adv = []
+        for src, cls in self.dis.forward(x_gen):
+            for i in range(2):
+                adv.append((ops.mse_const(src[i * B:(i + 1) * B], 1.0), configs['gan_w']))
+                adv.append((ops.bce_logits(cls[i * B:(i + 1) * B], label_trg), configs['cls_w']))
+        return ops.weighted_sum(adv)
+
+    def _gen_update_tail(self, x_real, x3, x_real_rec, c_src, c_trg, label_trg, content_real, mu_real, lv_real, mu_txt,
+                         lv_txt, style1, configs, B):
+        gen = self.gen
+        # The adversarial branch (frozen D on the two translated batches) depends on x3 only: it is forked onto its own
+        # stream here and joined when the loss is assembled, so that the discriminator's small, low-occupancy kernels -
+        # forward now, data gradients in backward (autograd replays them on the same stream) - run next to the
+        # re-encode and the cycle decode instead of after them.  D has no random draws; values are unchanged.
+        ds = None
+        if ops.RT.use_dis_stream and x3.is_cuda:
+            main = torch.cuda.current_stream()
+            ds = ops.RT.aux_stream(x3.device, 'dis')
+            ds.wait_stream(main)
+            with torch.cuda.stream(ds):
+                self.loss_gen_adv = self._adv_terms(x3[B:], label_trg, configs, B)
 
         # re-encode the three generated batches together (solver.py:162,182,186)
         contents, mus, _ = gen.encode_fused(x3)
@@ -318,43 +349,37 @@ class Solver(nn.Module):
         if configs['recon_x_cyc_w'] > 0:
             self.loss_gen_cycrecon_x = self.recon_criterion(x_cycle, x_real)
 
-        with _frozen(dis):                                      # D weight gradients are never used here
-            # D(x_fake) and D(x_fake1) (two calc_gen_loss calls, solver.py:206-207) as one 2B pass over x3[B:]
-            adv = []
-            for src, cls in dis.forward(x3[B:]):
-                for i in range(2):
-                    adv.append((ops.mse_const(src[i * B:(i + 1) * B], 1.0), configs['gan_w']))
-                    adv.append((ops.bce_logits(cls[i * B:(i + 1) * B], label_trg), configs['cls_w']))
-            self.loss_gen_adv = ops.weighted_sum(adv)
+        if ds is None:
+            self.loss_gen_adv = self._adv_terms(x3[B:], label_trg, configs, B)
+        else:
+            main = torch.cuda.current_stream()
+            main.wait_stream(ds)
+            self.loss_gen_adv.record_stream(main)
 
-            self.loss_kl_x, self.loss_kl_trg = 0.0, 0.0
-            if self.dist_mode == 'kls':
-                self.loss_kl_x = gmm_kl_distance_sp(mu_real, lv_real, c_src, self.sigma)
-                self.loss_kl_trg = gmm_kl_distance_sp(mu_txt, lv_txt, c_trg, self.sigma)
-            else:
-                self.loss_kl_x = gmm_earth_mover_distance_sp(mu_real, c_src)
-                self.loss_kl_trg = gmm_earth_mover_distance_sp(mu_txt, c_trg)
-            self.loss_gen_vgg = 0
+        self.loss_kl_x, self.loss_kl_trg = 0.0, 0.0
+        if self.dist_mode == 'kls':
+            self.loss_kl_x = gmm_kl_distance_sp(mu_real, lv_real, c_src, self.sigma)
+            self.loss_kl_trg = gmm_kl_distance_sp(mu_txt, lv_txt, c_trg, self.sigma)
+        else:
+            self.loss_kl_x = gmm_earth_mover_distance_sp(mu_real, c_src)
+            self.loss_kl_trg = gmm_earth_mover_distance_sp(mu_txt, c_trg)
+        self.loss_gen_vgg = 0
 
-            # one stacked dot product instead of a multiply and an add kernel per term (same sum, solver.py:225-237)
-            terms = [(self.loss_gen_adv, 1.0),
-                     (self.loss_gen_recon_x, configs['recon_x_w']),
-                     (self.loss_gen_recon_c_real, configs['recon_c_w']),
-                     (self.loss_gen_recon_c_fake, configs['recon_c_w']),
-                     (self.loss_gen_recon_c_rand, configs['recon_c_w']),
-                     (self.loss_gen_recon_s_real, configs['recon_s_w']),
-                     (self.loss_gen_recon_s_fake, configs['recon_s_w']),
-                     (self.loss_gen_recon_s_rand, configs['recon_s_w']),
-                     (self.loss_gen_cycrecon_x, configs['recon_x_cyc_w']),
-                     (self.loss_kl_x, configs['kl_w']),
-                     (self.loss_kl_trg, configs['kl_w'])]
-            terms = [(t, w) for t, w in terms if isinstance(t, torch.Tensor)]
-            self.loss_gen_total = ops.weighted_sum(terms) - self._ds_w_dev * self.loss_ds
-            self.loss_gen_total.backward()
-        ops.side_join()
-        if self.grad_sync is not None:
-            self.grad_sync(self.gen)
-        self.gen_opt.step()
+        # one stacked dot product instead of a multiply and an add kernel per term (same sum, solver.py:225-237)
+        terms = [(self.loss_gen_adv, 1.0),
+                 (self.loss_gen_recon_x, configs['recon_x_w']),
+                 (self.loss_gen_recon_c_real, configs['recon_c_w']),
+                 (self.loss_gen_recon_c_fake, configs['recon_c_w']),
+                 (self.loss_gen_recon_c_rand, configs['recon_c_w']),
+                 (self.loss_gen_recon_s_real, configs['recon_s_w']),
+                 (self.loss_gen_recon_s_fake, configs['recon_s_w']),
+                 (self.loss_gen_recon_s_rand, configs['recon_s_w']),
+                 (self.loss_gen_cycrecon_x, configs['recon_x_cyc_w']),
+                 (self.loss_kl_x, configs['kl_w']),
+                 (self.loss_kl_trg, configs['kl_w'])]
+        terms = [(t, w) for t, w in terms if isinstance(t, torch.Tensor)]
+        self.loss_gen_total = ops.weighted_sum(terms) - self._ds_w_dev * self.loss_ds
+        self.loss_gen_total.backward()
 
     # ------------------------------------------------------------------ D step
     def dis_update(self, x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg, configs, iters):

@@ -1,3 +1,6 @@
 mkdir -p gpurun_out
-timeout -k 10 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --steps 10 --warmup 4 --no-cpu-baseline > gpurun_out/bench_2gpu.log 2>&1
-grep '"metric"' gpurun_out/bench_2gpu.log | head -1 | cut -c1-330; tail -2 gpurun_out/bench_2gpu.log | cut -c1-200
+(time timeout -k 10 600 python -m pytest tests -q -m gpu -x --tb=short 2>&1 | grep -v "Warning\|warnings.html\|detach()" | tail -12) > gpurun_out/t_all.log 2>&1
+tail -6 gpurun_out/t_all.log
+timeout -k 10 300 python bench.py --steps 10 --warmup 4 --no-cpu-baseline 2>gpurun_out/bench35.err | tail -1 > gpurun_out/bench35.json
+DWC_DIS_STREAM=0 timeout -k 10 300 python bench.py --steps 10 --warmup 4 --no-cpu-baseline 2>gpurun_out/bench36.err | tail -1 > gpurun_out/bench36.json
+cut -c1-200 gpurun_out/bench35.json gpurun_out/bench36.json; tail -2 gpurun_out/bench35.err
