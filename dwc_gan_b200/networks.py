@@ -668,6 +668,30 @@ class AdaINGen_v2(_FlatOwner):
         content = _hb_to_tensor(self.enc_content.run(images, rows))
         return content, mu, lv
 
+    def encode_forked(self, images):
+        """encode_fused with the style encoder on its own stream: returns (content, mu, lv, join) where join() makes the
+        current stream wait for mu / lv.  The caller keeps working on the content code (e.g. the cycle decode) while the
+        style encoder's small feature maps are processed; autograd replays both backward passes the same way."""
+        self.ensure_flat()
+        images = images.contiguous().float()
+        rows = ops.image_rows(images, 1, self.enc_style.model[0])
+        if not (ops.RT.use_sty_stream and images.is_cuda):
+            mu, lv = self.enc_style.run(images, rows)
+            return _hb_to_tensor(self.enc_content.run(images, rows)), mu, lv, (lambda: None)
+        main = torch.cuda.current_stream()
+        ss = ops.RT.aux_stream(images.device, 'sty')
+        ss.wait_stream(main)
+        with torch.cuda.stream(ss):
+            mu, lv = self.enc_style.run(images, rows)
+        content = _hb_to_tensor(self.enc_content.run(images, rows))
+
+        def join():
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(ss)
+            mu.record_stream(cur)
+            lv.record_stream(cur)
+        return content, mu, lv, join
+
     def encode(self, images):
         content, mu, lv = self.encode_fused(images)
         return content, list(mu.split(self.c_dim, 1)), list(lv.split(self.c_dim, 1))

@@ -44,6 +44,8 @@ class Runtime:
         self.use_txt_stream = os.environ.get("DWC_TXT_STREAM", "1") != "0"
         self.use_dis_stream = os.environ.get("DWC_DIS_STREAM", "1") != "0"
         self.aux_streams = {}
+        self.home_stream = None                            # stream that called backward() (set by the Solver)
+        self.use_sty_stream = os.environ.get("DWC_STY_STREAM", "1") != "0"
         self.conv7_which = os.environ.get("DWC_CONV7", "1")          # diagnostics: "h" heads only, "d" dgrad only
         self.use_fused_norm = os.environ.get("DWC_FUSED_NORM", "0") != "0"   # opt-in: the row-streaming passes are faster
 
@@ -96,8 +98,9 @@ def side_launch(fn, keep):
         fn()
     if not RT.side_keep:
         # first side launch of this backward pass: join the streams when the pass ends, so that whoever called
-        # .backward() sees complete parameter gradients on its own stream
-        RT.side_main = main
+        # .backward() sees complete parameter gradients on its own stream.  `main` may be an auxiliary stream (a
+        # forked encoder replays its backward there); the Solver names the stream that called backward() as home.
+        RT.side_main = RT.home_stream if RT.home_stream is not None else main
         torch.autograd.Variable._execution_engine.queue_callback(side_join)
     RT.side_keep.append(keep)
 

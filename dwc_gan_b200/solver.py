@@ -331,12 +331,14 @@ class Solver(nn.Module):
                 self.loss_gen_adv = self._adv_terms(x3[B:], label_trg, configs, B)
 
         # re-encode the three generated batches together (solver.py:162,182,186)
-        contents, mus, _ = gen.encode_fused(x3)
+        # (the style half of it runs on its own stream next to the content half and the cycle decode)
+        contents, mus, _, join_style = gen.encode_forked(x3)
         content_real_rec, content_fake_rec, content_rand = contents.view(3, B, *contents.shape[1:]).unbind(0)
-        mu_real_rec, mu_fake_rec, mu_rand = mus.view(3, B, mus.shape[1]).unbind(0)
         if configs['recon_x_cyc_w'] > 0:
             x_cycle, att_c = self._decode(content_fake_rec, mu_real)
             x_cycle = self._blend(x_cycle, att_c, x_real)
+        join_style()
+        mu_real_rec, mu_fake_rec, mu_rand = mus.view(3, B, mus.shape[1]).unbind(0)
 
         self.loss_gen_recon_x = self.recon_criterion(x_real_rec, x_real)
         self.loss_gen_recon_c_real = self.recon_criterion(content_real_rec, content_real)
@@ -379,7 +381,11 @@ class Solver(nn.Module):
                  (self.loss_kl_trg, configs['kl_w'])]
         terms = [(t, w) for t, w in terms if isinstance(t, torch.Tensor)]
         self.loss_gen_total = ops.weighted_sum(terms) - self._ds_w_dev * self.loss_ds
-        self.loss_gen_total.backward()
+        ops.RT.home_stream = torch.cuda.current_stream() if x3.is_cuda else None
+        try:
+            self.loss_gen_total.backward()
+        finally:
+            ops.RT.home_stream = None
 
     # ------------------------------------------------------------------ D step
     def dis_update(self, x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg, configs, iters):
