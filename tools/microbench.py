@@ -212,6 +212,17 @@ def main():
             for r in bench_post(args.batch, c, hw, kind, peaks):
                 lines.append("| %s | %s | %.1f | %.1f | %.3f |" % (r["layer"], r["op"], r["us"], r["gbs"], r["frac_of_hbm"]))
                 print(lines[-1], flush=True)
+    if not args.only:
+        # the dedicated few-channel 7x7 kernel and the upsample passes (same measurements as tools/bench_conv7.py and
+        # tools/bench_upsample.py, which print more detail)
+        import subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        for tool in ("bench_conv7.py", "bench_upsample.py"):
+            r = subprocess.run([sys.executable, os.path.join(here, tool)], capture_output=True, text=True)
+            for ln in r.stdout.splitlines():
+                if ln.startswith("|"):
+                    lines.append(ln)
+                    print(ln, flush=True)
     if args.out:
         with open(args.out, "w") as f:
             f.write("\n".join(lines) + "\n")
