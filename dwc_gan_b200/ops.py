@@ -426,7 +426,7 @@ class AdainSplitFn(torch.autograd.Function):
         n = params.shape[0]
         ctx.meta = (n, nl, f, params.dtype)
         ctx.set_materialize_grads(False)
-        buf = params.detach().float().view(n, nl, 2, f).permute(1, 2, 0, 3).contiguous()      # [L, 2, N, F]
+        buf = params.detach().float().reshape(n, nl, 2, f).permute(1, 2, 0, 3).contiguous()   # [L, 2, N, F]
         return tuple(buf[l, j].reshape(-1) for l in range(nl) for j in range(2))
 
     @staticmethod
@@ -442,8 +442,8 @@ class AdainSplitFn(torch.autograd.Function):
 
 
 class WeightedSumFn(torch.autograd.Function):
-    """sum_i w_i * term_i over scalar loss terms with constant weights: one stack + one dot product (and one scaling in
-    backward) instead of a multiply and an add kernel per term in each direction."""
+    """sum_i w_i * term_i over scalar loss terms with constant weights: one stack + one multiply + one sum (and one
+    scaling in backward) instead of a multiply and an add kernel per term in each direction."""
     _wcache = {}
 
     @staticmethod
@@ -455,7 +455,7 @@ class WeightedSumFn(torch.autograd.Function):
         ctx.save_for_backward(w)
         ctx.k = len(terms)
         st = torch.stack([t.reshape(()).float() for t in terms])
-        return torch.dot(st, w)
+        return (st * w).sum()                             # (not torch.dot: that would be a cuBLAS call)
 
     @staticmethod
     def backward(ctx, g):
