@@ -31,7 +31,9 @@ __global__ void gmm_sample_kernel(const float* __restrict__ mu, const float* __r
   int k = i % cdim;
   int j = (i / cdim) % ncls;
   int b = i / (cdim * ncls);
-  z[i] = mu[b * ncls + j] + stddev * eps[((long long)k * B + b) * ncls + j];
+  // two roundings (product, then sum) like torch.normal(mean, std) = randn().mul_(std).add_(mean): bit-identical to
+  // tdist.Normal(mu, stddev).sample() of the reference for any stddev, not only powers of two (no FMA contraction)
+  z[i] = __fadd_rn(mu[b * ncls + j], __fmul_rn(stddev, eps[((long long)k * B + b) * ncls + j]));
 }
 extern "C" int dwc_gmm_sample(const float* mu, const float* eps, float stddev, float* z, int b, int ncls, int cdim,
                               dwc_stream_t stream) {

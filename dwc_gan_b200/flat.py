@@ -273,33 +273,41 @@ class FusedAdam(torch.optim.Optimizer):
             self.steps[n] += 1
         self.flat.bump()
 
+    def _param_order(self):
+        """Names of the trainable parameters in ``module.parameters()`` order - the order torch.optim.Adam (the
+        reference's optimizer, solver.py:63-68) numbers its state entries in.  The flat buffer's own order differs
+        (fusion groups are contiguous), so checkpoints are emitted / consumed through this map."""
+        return [n for n, p in self.flat.module.named_parameters() if p.requires_grad]
+
     def state_dict(self):
-        """torch.optim.Adam-shaped state (what Solver.save writes, solver.py:413)."""
+        """torch.optim.Adam-shaped state (what Solver.save writes, solver.py:413): entry i belongs to the i-th
+        trainable parameter of ``module.parameters()``."""
         named = dict(self.flat.module.named_parameters())
+        order = self._param_order()
         state = {}
         if self.m is not None:
-            for i, n in enumerate(self._names):
+            for i, n in enumerate(order):
                 if self.steps[n] == 0:
                     continue
                 shape = named[n].shape
                 state[i] = dict(step=torch.tensor(float(self.steps[n])),
-                                exp_avg=self.flat._view(self.m, n, shape).clone(),
-                                exp_avg_sq=self.flat._view(self.v, n, shape).clone())
-        groups = [dict(self.param_groups[0], params=list(range(len(self._names))))]
-        groups[0].pop("params", None)
-        groups[0]["params"] = list(range(len(self._names)))
-        return dict(state=state, param_groups=groups)
+                                exp_avg=self.flat._view(self.m, n, shape).clone().contiguous(),
+                                exp_avg_sq=self.flat._view(self.v, n, shape).clone().contiguous())
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(order)))
+        return dict(state=state, param_groups=[group])
 
     def load_state_dict(self, sd):
         self._ensure_state()
         named = dict(self.flat.module.named_parameters())
+        order = self._param_order()
         for i, st in sd.get("state", {}).items():
-            n = self._names[int(i)]
+            n = order[int(i)]
             self.steps[n] = int(st["step"])
             self.flat._view(self.m, n, named[n].shape).copy_(st["exp_avg"])
             self.flat._view(self.v, n, named[n].shape).copy_(st["exp_avg_sq"])
         if sd.get("param_groups"):
-            for k in ("lr", "betas", "eps", "weight_decay"):
+            for k in ("lr", "betas", "eps", "weight_decay", "initial_lr"):
                 if k in sd["param_groups"][0]:
                     self.param_groups[0][k] = sd["param_groups"][0][k]
 

@@ -81,6 +81,6 @@ def attach(solver, group=None):
     """Turn a Solver into a data-parallel replica: broadcast weights once, average gradients every phase."""
     broadcast_parameters(solver.gen, group=group)
     broadcast_parameters(solver.dis, group=group)
-    solver.grad_sync = GradSync(group)
-    solver.gen_opt.grad_scale = solver.dis_opt.grad_scale = 1.0 / solver.grad_sync.world
+    solver._dp_sync = GradSync(group)
+    solver.gen_opt.grad_scale = solver.dis_opt.grad_scale = 1.0 / solver._dp_sync.world
     return solver

@@ -87,8 +87,10 @@ class Solver(nn.Module):
         self.dis_scheduler = get_scheduler(self.dis_opt, configs)
         self.gen_scheduler = get_scheduler(self.gen_opt, configs)
         self.criterionL1 = torch.nn.L1Loss()
-        self.grad_sync = None        # set by parallel.DataParallelSync
-        self.noise_hook = None       # tests: callable(name) -> eps tensor for dist_sampling_split
+        self._dp_sync = None        # set by parallel.attach (name avoids the reference write_loss filter: loss|grad|nwd)
+        self.noise_hook = None       # tests: callable(name) -> eps tensor for dist_sampling_split (forces eager steps)
+        self.noise_buffers = None    # tests: {name: persistent device tensor (1, c_dim, B, num_cls)} read at every
+        #                              call, also by a replayed CUDA graph (refill them in place between steps)
         # CUDA graphs: after `graph_warmup` eager calls per (phase, batch shape, attention status) the whole
         # phase (forward, backward, gradient all-reduce, Adam) is captured once and replayed afterwards.
         self.use_cuda_graphs = os.environ.get("DWC_CUDA_GRAPHS", "1") != "0"
@@ -103,9 +105,18 @@ class Solver(nn.Module):
         for net, opt_name in ((self.gen, 'gen_opt'), (self.dis, 'dis_opt')):
             net.ensure_flat()
         # optimizers keep pointing at the (possibly rebuilt) flat buffers
+        # and carry their moments along (same layout: a rebuild keeps the parameter order); if that is impossible the
+        # step counters are reset together with the moments, so that the bias corrections stay consistent
         for opt in (getattr(self, 'gen_opt', None), getattr(self, 'dis_opt', None)):
-            if opt is not None:
+            if opt is None or opt.m is None:
+                continue
+            f = opt.flat
+            if opt.m.numel() == f.total:
+                opt.m = opt.m.to(f.data.device)
+                opt.v = opt.v.to(f.data.device)
+            else:
                 opt.m = opt.v = None
+                opt.steps = {n: 0 for n in opt.steps}
         p = next(self.gen.parameters(), None)
         if p is not None:
             self.device = p.device
@@ -148,6 +159,8 @@ class Solver(nn.Module):
 
     def _sample_style(self, c_trg, tag):
         eps = self.noise_hook(tag) if self.noise_hook is not None else None
+        if eps is None and self.noise_buffers is not None:
+            eps = self.noise_buffers[tag]
         return dist_sampling_split(c_trg, self.c_dim, self.stddev, self.device, eps=eps)
 
     def _blend(self, img, att, x_real):
@@ -302,8 +315,8 @@ class Solver(nn.Module):
             self._gen_update_tail(x_real, x3, x_real_rec, c_src, c_trg, label_trg, content_real, mu_real, lv_real,
                                   mu_txt, lv_txt, style1, configs, B)
         ops.side_join()
-        if self.grad_sync is not None:
-            self.grad_sync(self.gen)
+        if self._dp_sync is not None:
+            self._dp_sync(self.gen)
         self.gen_opt.step()
 
     def _adv_terms(self, x_gen, label_trg, configs, B):
@@ -419,8 +432,8 @@ class Solver(nn.Module):
         self.loss_dis_all = self.loss_dis
         self.loss_dis_all.backward()
         ops.side_join()
-        if self.grad_sync is not None:
-            self.grad_sync(self.dis)
+        if self._dp_sync is not None:
+            self._dp_sync(self.dis)
         self.dis_opt.step()
 
     def smooth_moving(self):
@@ -467,6 +480,15 @@ class Solver(nn.Module):
         self.dis.load_state_dict(torch.load(last, map_location='cpu')['b'])
         self.dis_scheduler = get_scheduler(self.dis_opt, configs, iterations)
         self.gen_scheduler = get_scheduler(self.gen_opt, configs, iterations)
+        # The reference re-steps both schedulers `iterations` more times on torch != 0.4.1 (solver.py:376-379), so the
+        # learning rate after a resume is the one of epoch 2*iterations+1 counted from the CURRENT lr (e.g. 2.5e-5
+        # instead of 5e-5 when resuming at 150000 under StepLR(100000, 0.5)).  Mirrored as is: a drop-in must train the
+        # way the reference does (pinned by tests/golden/ref_extra.json "resume_lr").  Optimizer moments are not
+        # restored either (solver.py:370-372 is commented out in the reference).
+        if self.gen_scheduler is not None and self.dis_scheduler is not None:
+            for _ in range(iterations):
+                self.gen_scheduler.step()
+                self.dis_scheduler.step()
         print('Resume from iteration %d' % iterations)
         return iterations
 

@@ -23,6 +23,25 @@ def _lstm_groups(num_layers):
     return groups
 
 
+def final_state_rows(finals_h, finals_c):
+    """[B, 4*L*H] feature from the per-layer final states (lists of L tensors [B, 2H], directions concatenated).
+
+    The reference concatenates final_h and final_c along dim=1 - the BATCH dimension of [L, B, 2H] - and then views
+    the (L, 2B, 2H) result as (B, -1) (networks_v2.py:248-249).  For B > 1 row r therefore holds 4 consecutive
+    2H-vectors of the flat sequence (layer 0: h_0..h_{B-1}, c_0..c_{B-1}; layer 1: ...), mixing samples (SURVEY
+    8a-3 #1).  Pure data movement: reproduced bit for bit."""
+    B = finals_h[0].shape[0]
+    final_h = torch.stack(list(finals_h), 0)                           # [L, B, 2H]
+    final_c = torch.stack(list(finals_c), 0)
+    return torch.cat([final_h, final_c], dim=1).reshape(B, -1)
+
+
+def final_state_rows_bwd(dres, num_layers, B, H):
+    """Adjoint of final_state_rows: ([L, B, 2H] gradient of final_h, [L, B, 2H] gradient of final_c)."""
+    d = dres.contiguous().float().reshape(num_layers, 2 * B, 2 * H)
+    return d[:, :B], d[:, B:]
+
+
 class TxtBodyFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, style, anchor, enc, tokens, lens, mask_in, mask_mid, need_grad):
@@ -71,9 +90,7 @@ class TxtBodyFn(torch.autograd.Function):
                 _call("dwc_mul", L.ptr(out), L.ptr(mask_mid), L.ptr(nxt), L.i64(out.numel()), L.stream())
             saved.append((inp, out, gates, csave))
             inp = nxt
-        final_h = torch.stack(finals_h, 0)                             # [L, B, 2H]
-        final_c = torch.stack(finals_c, 0)
-        res = torch.cat([final_h, final_c], dim=1).reshape(B, -1)      # the reference's (L, 2B, 2H) -> (B, -1) quirk
+        res = final_state_rows(finals_h, finals_c)                     # the reference's (L, 2B, 2H) -> (B, -1) quirk
         ctx.enc, ctx.dims = enc, (B, T, E, S, H, NL)
         ctx.saved = saved
         ctx.aux = (tokens, lens, mask_in, mask_mid, pre, emb_name)
@@ -87,8 +104,7 @@ class TxtBodyFn(torch.autograd.Function):
         B, T, E, S, H, NL = ctx.dims
         tokens, lens, mask_in, mask_mid, pre, emb_name = ctx.aux
         dev = dres.device
-        d = dres.contiguous().float().reshape(NL, 2 * B, 2 * H)
-        dfh, dfc = d[:, :B], d[:, B:]                                   # [L, B, 2H]
+        dfh, dfc = final_state_rows_bwd(dres, NL, B, H)                 # [L, B, 2H] each
         dseq = None
         for l in range(NL - 1, -1, -1):
             inp, out, gates, csave = ctx.saved[l]

@@ -45,6 +45,70 @@ DEFAULT_CFG = dict(
 
 
 # --------------------------------------------------------------------------
+# storage-rounding mode (bf16 product-mode emulation)
+# --------------------------------------------------------------------------
+# The CUDA path keeps activations and activation gradients in bf16 HBM buffers and
+# feeds the tensor cores bf16 weights (fp32 accumulation, fp32 statistics, fp32
+# master weights / weight gradients / dense layers).  ``storage_rounding("bf16")``
+# makes this oracle round to bf16 at exactly those storage points - forward values
+# AND the gradients flowing back through them - while all arithmetic stays fp32.
+# It answers "how far from the fp32 reference can a bf16-storage implementation be
+# before anything is wrong with it": tests compare the CUDA path against both.
+
+class _RoundBf16(torch.autograd.Function):
+    """y = bf16(x) in forward, dx = bf16(dy) in backward (an activation buffer and its gradient buffer)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundBf16Fwd(torch.autograd.Function):
+    """bf16 copy of an fp32 master weight: rounded operand, fp32 gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+_STORAGE = {"mode": "fp32"}
+
+
+class storage_rounding:
+    """Context manager: ``with storage_rounding("bf16"): ...`` (default "fp32" = no rounding)."""
+
+    def __init__(self, mode: str):
+        assert mode in ("fp32", "bf16"), mode
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = _STORAGE["mode"]
+        _STORAGE["mode"] = self.mode
+        return self
+
+    def __exit__(self, *a):
+        _STORAGE["mode"] = self.prev
+
+
+def _q(x: Tensor) -> Tensor:
+    """An activation the CUDA path stores in HBM (and whose gradient it stores too)."""
+    return _RoundBf16.apply(x) if _STORAGE["mode"] == "bf16" else x
+
+
+def _qw(w: Tensor) -> Tensor:
+    """A convolution weight as the tensor cores see it."""
+    return _RoundBf16Fwd.apply(w) if _STORAGE["mode"] == "bf16" else w
+
+
+# --------------------------------------------------------------------------
 # building blocks
 # --------------------------------------------------------------------------
 
@@ -66,7 +130,7 @@ def conv_reflect(P: Params, key: str, x: Tensor, k: int, s: int, p: int) -> Tens
     """reflect-pad + conv + bias: networks/networks.py:531,577-580."""
     if p > 0:
         x = F.pad(x, (p, p, p, p), mode="reflect")
-    return F.conv2d(x, P[key + ".weight"], P[key + ".bias"], stride=s)
+    return _q(F.conv2d(x, _qw(P[key + ".weight"]), P[key + ".bias"], stride=s))
 
 
 def inst_norm(x: Tensor, eps: float = 1e-5) -> Tensor:
@@ -108,9 +172,11 @@ def linear(P: Params, key: str, x: Tensor) -> Tensor:
 def style_encoder(P: Params, x: Tensor, cfg=DEFAULT_CFG, pre="enc_style.",
                   drop_mask: Optional[Tensor] = None) -> Tuple[List[Tensor], List[Tensor]]:
     """StyleEncoder (v2): networks/networks_v2.py:98-141."""
-    h = _act(conv_reflect(P, pre + "model.0.conv", x, 7, 1, 3), "relu")
+    h = _q(_act(conv_reflect(P, pre + "model.0.conv", _q(x), 7, 1, 3), "relu"))
     for i in range(1, 1 + cfg["style_downsample"]):
         h = _act(conv_reflect(P, pre + f"model.{i}.conv", h, 4, 2, 1), "relu")
+        if i < cfg["style_downsample"]:
+            h = _q(h)                                        # the last layer's ReLU is fused into the pooling
     h = h.mean(dim=(2, 3))                                   # AdaptiveAvgPool2d(1)
     h = torch.relu(linear(P, pre + "mapping.0", h))
     if drop_mask is not None:                                # Dropout(0.1), :119
@@ -123,16 +189,16 @@ def style_encoder(P: Params, x: Tensor, cfg=DEFAULT_CFG, pre="enc_style.",
 
 def content_encoder(P: Params, x: Tensor, cfg=DEFAULT_CFG, pre="enc_content.") -> Tensor:
     """ContentEncoder + ResBlocks: networks/networks.py:428-446, 480-489, 509-522."""
-    h = torch.relu(inst_norm(conv_reflect(P, pre + "model.0.conv", x, 7, 1, 3)))
+    h = _q(torch.relu(inst_norm(conv_reflect(P, pre + "model.0.conv", _q(x), 7, 1, 3))))
     nd = cfg["content_downsample"]
     for i in range(1, 1 + nd):
-        h = torch.relu(inst_norm(conv_reflect(P, pre + f"model.{i}.conv", h, 4, 2, 1)))
+        h = _q(torch.relu(inst_norm(conv_reflect(P, pre + f"model.{i}.conv", h, 4, 2, 1))))
     rb = pre + f"model.{nd + 1}.model."
     for j in range(cfg["n_res"]):
         r = h
-        h = torch.relu(inst_norm(conv_reflect(P, rb + f"{j}.model.0.conv", h, 3, 1, 1)))
+        h = _q(torch.relu(inst_norm(conv_reflect(P, rb + f"{j}.model.0.conv", h, 3, 1, 1))))
         h = inst_norm(conv_reflect(P, rb + f"{j}.model.1.conv", h, 3, 1, 1))
-        h = h + r                                            # second block: norm, no act, += residual
+        h = _q(h + r)                                        # second block: norm, no act, += residual
     return h
 
 
@@ -153,7 +219,7 @@ def decoder(P: Params, content: Tensor, adain_params: Tensor, cfg=DEFAULT_CFG,
     """Decoder (v2): networks/networks_v2.py:144-169 with AdaIN parameters consumed
     in module order, 2*C per layer, bias("mean") first then weight("std"):
     networks/networks_v2.py:78-87.  The attention head is always evaluated."""
-    h = content
+    h = _q(content)
     c = content.shape[1]
     off = 0
     rb = pre + "model.0.model."
@@ -165,13 +231,15 @@ def decoder(P: Params, content: Tensor, adain_params: Tensor, cfg=DEFAULT_CFG,
             off += 2 * c
             h = conv_reflect(P, rb + f"{j}.model.{t}.conv", h, 3, 1, 1)
             h = _act(adain(h, weight, bias), act)
-        h = h + r
+            if t == 0:
+                h = _q(h)
+        h = _q(h + r)
     idx = 2
     for _ in range(cfg["content_downsample"]):
-        h = upsample2x(h)
+        h = _q(upsample2x(h))
         h = conv_reflect(P, pre + f"model.{idx}.conv", h, 5, 1, 2)
-        h = torch.relu(layer_norm_munit(h, P[pre + f"model.{idx}.norm.gamma"],
-                                        P[pre + f"model.{idx}.norm.beta"]))
+        h = _q(torch.relu(layer_norm_munit(h, P[pre + f"model.{idx}.norm.gamma"],
+                                           P[pre + f"model.{idx}.norm.beta"])))
         idx += 2
     img = torch.tanh(conv_reflect(P, pre + "image_content.conv", h, 7, 1, 3))
     att = torch.sigmoid(conv_reflect(P, pre + "image_attention.conv", h, 7, 1, 3))
@@ -253,9 +321,9 @@ def dis_forward(D: Params, x: Tensor, cfg=DEFAULT_CFG):
     """MsImageDis.forward: networks/networks.py:102-114."""
     outs = []
     for s in range(cfg["dis_num_scales"]):
-        h = x
+        h = _q(x)
         for i in range(cfg["dis_n_layer"]):
-            h = _act(conv_reflect(D, f"cnns_feat.{s}.{i}.conv", h, 4, 2, 1), "lrelu")
+            h = _q(_act(conv_reflect(D, f"cnns_feat.{s}.{i}.conv", h, 4, 2, 1), "lrelu"))
         src = F.conv2d(h, D[f"cnns_src.{s}.weight"], D[f"cnns_src.{s}.bias"])
         cls = F.conv2d(h, D[f"cnns_cls.{s}.weight"]).reshape(x.shape[0], -1)
         outs.append((src, cls))

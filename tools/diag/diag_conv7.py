@@ -1,6 +1,6 @@
 """Diagnostic: is dwc_conv7_few bit-reproducible launch to launch (alone and under a concurrent stream)?"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import dwc_gan_b200
 from dwc_gan_b200 import ops

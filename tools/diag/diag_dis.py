@@ -1,6 +1,6 @@
 """Diagnostics (not a pytest): discriminator forward/backward vs the fp64 oracle, with spatial error structure."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import dwc_oracle as O
 from tests.util_gpu import build_solver, cpu_state, to_cuda, rel, grads_of

@@ -1,6 +1,6 @@
 """Diagnostics: discriminator scale-0 chain, every intermediate gradient vs a torch fp64 graph."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.nn.functional as F
 from dwc_gan_b200 import ops

@@ -1,6 +1,6 @@
 """Diagnostic: max parameter difference eager vs graph (and eager vs eager) after 7 steps."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from tests.test_graph_gpu import _run
 

@@ -1,7 +1,7 @@
 """Diagnostic for the halo-tile conv kernel: identity weights on a single tap reveal which input pixel / channel
 each output element was read from."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from dwc_gan_b200 import _lib as L, plan as P
 from dwc_gan_b200.plan import HB

@@ -1,7 +1,7 @@
 """Diagnostic: every torch.empty buffer is pre-filled with NaN; any kernel that reads memory it (or a producer) never
 wrote turns losses / gradients into NaN."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 
 _empty = torch.empty

@@ -1,6 +1,6 @@
 """Diagnostics for the tcgen05 kernels (not a pytest): prints error structure for simple cases."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.nn.functional as F
 from dwc_gan_b200 import _lib as L, plan as P
