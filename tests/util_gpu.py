@@ -50,14 +50,21 @@ def grads_of(net):
             for k, p in net.named_parameters()}
 
 
+def cancelled_bias(k):
+    """Conv biases that feed InstanceNorm / AdaIN: the mean subtraction cancels them, so their gradient is exactly
+    zero in exact arithmetic.  The CUDA path writes that zero; the reference / oracle compute round-off noise there
+    (fp32: ~1e-8; with bf16 storage rounding: rounding noise of the summed gradient) - not comparable."""
+    return k.endswith("conv.bias") and (k.startswith("enc_content.") or k.startswith("dec.model.0."))
+
+
 def compare_grads(mine, ref, skip_rel=1e-5):
     """(worst per-tensor rel err, its key, global rel err).  Tensors whose reference gradient is pure round-off
-    (biases in front of InstanceNorm/AdaIN: exactly zero in exact arithmetic) are left out of the per-tensor figure."""
+    (biases in front of InstanceNorm/AdaIN: exactly zero in exact arithmetic) are left out."""
     worst, wk, num, den = 0.0, None, 0.0, 0.0
     gmax = max(float(g.double().norm()) for g in ref.values() if g is not None)
     skip_tiny = skip_rel * gmax
     for k, g in ref.items():
-        if g is None:
+        if g is None or cancelled_bias(k):
             continue
         m = mine[k]
         assert m is not None, k
@@ -70,3 +77,42 @@ def compare_grads(mine, ref, skip_rel=1e-5):
         if e > worst:
             worst, wk = e, k
     return worst, wk, (num ** 0.5) / (den ** 0.5 + 1e-30)
+
+
+def per_tensor_errs(mine, ref, skip_rel=1e-5):
+    """{key: relative L2 error} over tensors whose reference gradient is not pure round-off."""
+    gmax = max(float(g.double().norm()) for g in ref.values() if g is not None)
+    out = {}
+    for k, g in ref.items():
+        if g is None or cancelled_bias(k):
+            continue
+        gn = float(g.double().norm())
+        if gn < skip_rel * gmax:
+            continue
+        out[k] = float((mine[k].double() - g.double()).norm()) / gn
+    return out
+
+
+def params_of(net):
+    return {k: p.detach().float().cpu().contiguous().clone() for k, p in net.named_parameters()}
+
+
+def update_errs(p0, p1_mine, p1_ref):
+    """Per tensor: ||dp_mine - dp_ref|| / ||dp_ref|| for the parameter update dp = p1 - p0 of one optimizer step, and
+    the largest absolute parameter difference."""
+    out = {}
+    for k, ref in p1_ref.items():
+        d_ref = ref.double() - p0[k].double()
+        d_mine = p1_mine[k].double() - p0[k].double()
+        dn = float(d_ref.norm())
+        if dn == 0.0:
+            assert float(d_mine.norm()) == 0.0, ("parameter moved that the reference left alone", k)
+            continue
+        out[k] = (float((d_mine - d_ref).norm()) / dn, float((p1_mine[k].double() - ref.double()).abs().max()))
+    return out
+
+
+def top_errs(mine, ref, n=6):
+    """The n worst tensors as 'key:err' strings (diagnostics printed by the parity tests)."""
+    e = sorted(per_tensor_errs(mine, ref).items(), key=lambda kv: -kv[1])[:n]
+    return ", ".join("%s:%.2e" % kv for kv in e)
