@@ -1,12 +1,20 @@
 #!/usr/bin/env python
-"""Headline benchmark: full G+D training step of DWC-GAN at 128x128, bf16, batch 16 per GPU (BASELINE.json
-configs[2]), data-parallel over N GPUs of one node.
+"""Benchmarks of the DWC-GAN hot path on B200 (BASELINE.json configs), one JSON line on stdout (rank 0).
 
-  python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K ...  # reference's CPU path (oracle port) on the host cores
+  python bench.py [--config train128|infer64|train256] --gpus N --steps K --warmup W     # our arm (torchrun for N > 1)
+  python bench.py --impl reference [--config ...] --gpus N --steps K --warmup W         # the reference's own CPU path
 
-One JSON line on stdout (rank 0).  A "step" = dis_update + gen_update + smooth_moving + update_learning_rate +
-update_attention_status (train.py:102-111) on one synthetic batch.
+  train128 (default, BASELINE configs[2], the config the metric is quoted on): full G+D training step, bf16, 128x128,
+           batch 16 per GPU, data parallel.  A "step" = dis_update + gen_update + smooth_moving + update_learning_rate +
+           update_attention_status (train.py:102-111) on one synthetic batch.
+  train256 (configs[3]): the scaled 256x256 variant (image_size 256, dis.image_size 256, gen.content_downsample 3),
+           batch 8 per GPU.
+  infer64  (configs[1]): generator-only inference (content encode + text-conditioned AdaIN decode + attention blend,
+           Solver.forward), batch 64, bf16, eval mode.
+
+The reference arm times the UNMODIFIED reference (oracle/_ref snapshot, cpu_baseline.kind "reference"; the oracle port
+if the snapshot is absent) on the box's host cores: BASELINE configs[0] = the same architecture, fp32, batch 8 (a
+bounded sample of the workload; the batch is lowered if K+W steps would not fit a few minutes, and said so).
 """
 import argparse
 import json
@@ -21,8 +29,22 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-GFLOP_PER_IMAGE_STEP = 569.7          # required algorithmic conv+linear work of one G+D step
-METRIC = "G+D train images/sec @128^2"
+# required algorithmic conv+linear work (2*MAC) per image
+CONFIGS = {
+    "train128": dict(size=128, batch=16, gflop=569.7, overrides=None, train=True,
+                     metric="G+D train images/sec @128^2",
+                     workload="full G+D training step, 128x128, configs/celeba_faces.yaml, vgg_w=0 (BASELINE configs[2])"),
+    "train256": dict(size=256, batch=8, gflop=979.1, train=True,
+                     overrides={"image_size": 256, "dis": {"image_size": 256}, "gen": {"content_downsample": 3}},
+                     metric="G+D train images/sec @256^2",
+                     workload="full G+D training step, scaled 256x256 variant (extra down/up-sampling stage), vgg_w=0 "
+                              "(BASELINE configs[3])"),
+    "infer64": dict(size=128, batch=64, gflop=38.78, overrides=None, train=False,
+                    metric="generator inference images/sec @128^2",
+                    workload="generator-only inference: encode + text encode + AdaIN decode + blend, 128x128, eval "
+                             "(BASELINE configs[1])"),
+}
+REF_BUDGET_S = 240.0          # wall-clock target of a whole --impl reference run
 
 
 def load_peaks():
@@ -71,20 +93,29 @@ def make_host_batch(B, size, seed):
     return O.synthetic_batch(B, size, seed=seed)
 
 
-def build_solver(device, mode="bf16"):
+def _apply_overrides(cfg, overrides):
+    for k, v in (overrides or {}).items():
+        if isinstance(v, dict):
+            cfg[k].update(v)
+        else:
+            cfg[k] = v
+
+
+def build_solver(device, mode="bf16", overrides=None):
     import dwc_gan_b200
     from dwc_gan_b200.solver import Solver
     from dwc_gan_b200.utils import get_config
     dwc_gan_b200.set_mode(mode)
     cfg = get_config(os.path.join(ROOT, "tests", "golden", "celeba_faces.yaml"))
     cfg["vgg_w"] = 0
+    _apply_overrides(cfg, overrides)
     torch.manual_seed(1234)                      # train.py:23
     s = Solver(cfg, device, None).to(device)
     s.copy_nets()
     return s, cfg
 
 
-def one_step(s, cfg, b, it):
+def train_step(s, cfg, b, it):
     s.dis_update(b["x_real"], b["c_src"], b["c_trg"], b["txt"], b["txt_lens"], b["label_src"], b["label_trg"], cfg, it)
     s.gen_update(b["x_real"], b["c_src"], b["c_trg"], b["txt"], b["txt_lens"], b["label_src"], b["label_trg"], cfg, it)
     s.smooth_moving()
@@ -92,22 +123,24 @@ def one_step(s, cfg, b, it):
     s.update_attention_status(it)
 
 
+one_step = train_step          # name used by tools/timeline_step.py, tools/profile_step.py
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at its in-step shape, from the
-# `ncu --set full` capture summarised in profiles/r01g_ncu_g7_b48.md (None until measured for another batch)
+# `ncu --set full` captures summarised under profiles/ (None where no capture exists for that batch).
 # n = 48: 29.71 MB read + 0.08 MB written (input 28.4 MB + weights 1.2 MB read exactly once; the 31.8 MB output was
-# still in the 126 MB L2 when the capture ended)
+# still in the 126 MB L2 when the capture ended), profiles/r01g_ncu_g7_b48.md
 G7_TRAFFIC_BYTES = {48: 29794560}
 
 
-def conv_roofline(peaks, B):
-    """Dominant kernel of the step: the tcgen05 implicit-GEMM conv at the G7 geometry (3x3, 256->256 @32x32: 16 of
-    the 27 generator convs) at the batch it runs with inside the step - the three gradient-carrying decodes / the three
-    re-encodes of gen_update are one 3B batch, which the persistent kernel variant serves (64 launches x ~50 us per
-    step against 67 x ~25 us for the single-batch launches of the same geometry).  Timed alone with CUDA events,
-    rotating over enough buffers to exceed the 126 MB L2."""
+def conv_roofline(peaks, n):
+    """Dominant kernel of every config: the tcgen05 implicit-GEMM conv at the G7 geometry (3x3, 256->256 @32x32: 16 of
+    the 27 generator convs) at the batch `n` it runs with inside the step (training: the three gradient-carrying decodes /
+    the three re-encodes of gen_update are one 3B batch; inference: B).  Timed alone with CUDA events on the launching
+    stream, rotating over enough buffers to exceed the 126 MB L2."""
     from dwc_gan_b200 import _lib as L, plan as P
     from dwc_gan_b200.plan import HB
-    n, c, hw = 3 * B, 256, 32
+    c, hw = 256, 32
     nbuf = 8
     xs = [HB(torch.randn(n, hw + 2, hw + 2, c, device="cuda").to(torch.bfloat16), n, hw, hw, c, 1, 0) for _ in range(nbuf)]
     ys = [HB.empty(n, hw, hw, c, 2, 0, torch.bfloat16, "cuda") for _ in range(nbuf)]
@@ -128,62 +161,168 @@ def conv_roofline(peaks, B):
     ms = e0.elapsed_time(e1) / (reps * nbuf)
     flops = 2.0 * n * hw * hw * c * 9 * c
     achieved = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "gconv_tcp_kernel<256> (G7 3x3 256->256 @32x32, 3 x batch %d = %d images)" % (B, n),
+    return {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv, G7 3x3 256->256 @32x32, %d images per launch" % n,
             "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
             "frac": round(achieved / peaks["tflops"], 4), "traffic": G7_TRAFFIC_BYTES.get(n),
             "algorithmic_flops": flops, "algorithmic_bytes": int(xs[0].t.numel() * 2 + ys[0].t.numel() * 2 + w.numel() * 2),
             "peak_source": peaks["src"] + " burst", "us_per_launch": round(ms * 1e3, 2)}
 
 
-def cpu_baseline(sample_b=2):
-    """Oracle port (the reference's algorithm on torch CPU fp32) timed on this box's host cores: 1 G+D step."""
-    from oracle import dwc_oracle as O
-    import dwc_gan_b200  # noqa: F401
-    from dwc_gan_b200.solver import Solver
-    from dwc_gan_b200.utils import get_config
-    cfg = get_config(os.path.join(ROOT, "tests", "golden", "celeba_faces.yaml"))
-    cfg["vgg_w"] = 0
-    torch.manual_seed(1234)
-    s = Solver(cfg, torch.device("cpu"), None)            # parameter container only (init parity with the reference)
-    orc = O.OracleSolver({k: v.contiguous() for k, v in s.gen.state_dict().items()},
-                         {k: v.contiguous() for k, v in s.dis.state_dict().items()})
-    batch = O.synthetic_batch(sample_b, 128, seed=0)
-    return orc, batch
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the unmodified reference on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+
+class _RefRunner:
+    """One 'step' of the reference's own implementation (oracle/_ref snapshot of /root/reference, through the two import
+    stubs of SURVEY.md 8c) or, if the snapshot is absent, of the oracle port."""
+
+    def __init__(self, conf):
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):          # the reference prints parameter counts while it builds
+            self._build(conf)
+
+    def _build(self, conf):
+        self.conf = conf
+        self.kind = "reference"
+        try:
+            from oracle.make_ref import import_reference
+            Solver, ref_utils, cfg_path = import_reference()
+            cfg = ref_utils.get_config(cfg_path)
+            cfg["vgg_w"] = 0
+            _apply_overrides(cfg, conf["overrides"])
+            torch.manual_seed(1234)
+            self.solver = Solver(cfg, torch.device("cpu"), None)
+            self.solver.copy_nets()
+            self.cfg = cfg
+            if not conf["train"]:
+                self.solver.eval()
+        except Exception as e:  # noqa: BLE001  (no snapshot on this box: fall back to the port, and say so)
+            self.kind = "port"
+            self.why = "%s: %s" % (type(e).__name__, e)
+            from oracle import dwc_oracle as O
+            from dwc_gan_b200.solver import Solver as Mine
+            from dwc_gan_b200.utils import get_config
+            cfg = get_config(os.path.join(ROOT, "tests", "golden", "celeba_faces.yaml"))
+            cfg["vgg_w"] = 0
+            _apply_overrides(cfg, conf["overrides"])
+            torch.manual_seed(1234)
+            s = Mine(cfg, torch.device("cpu"), None)            # parameter container only (init parity with the reference)
+            ocfg = dict(O.DEFAULT_CFG)
+            if conf["overrides"]:
+                ocfg.update(image_size=conf["size"], content_downsample=cfg["gen"]["content_downsample"])
+            self.orc = O.OracleSolver({k: v.contiguous() for k, v in s.gen.state_dict().items()},
+                                      {k: v.contiguous() for k, v in s.dis.state_dict().items()}, cfg=ocfg)
+            self.ocfg = ocfg
+
+    def set_batch(self, B):
+        self.B = B
+        self.batch = make_host_batch(B, self.conf["size"], seed=0)
+
+    def step(self, it):
+        b, B = self.batch, self.B
+        if self.kind == "reference":
+            s = self.solver
+            if self.conf["train"]:
+                args = (b["x_real"], b["c_src"], b["c_trg"], b["txt"], b["txt_lens"], b["label_src"], b["label_trg"],
+                        self.cfg, it)
+                s.dis_update(*args)
+                s.gen_update(*args)
+                s.smooth_moving()
+                s.update_learning_rate()
+                s.update_attention_status(it)
+            else:
+                with torch.no_grad():            # Solver.sample's semantics (solver.py:142-149 has a latent bug, SURVEY 3.4)
+                    c, mus, _ = s.gen.encode(b["x_real"])
+                    st, _ = s.gen.encode_txt(torch.cat(mus, 1), b["txt"], b["txt_lens"])
+                    img, att = s.gen.decode(c, torch.cat(st, 1))
+                    _ = img * att + b["x_real"] * (1 - att)
+        else:
+            from oracle import dwc_oracle as O
+            if self.conf["train"]:
+                torch.manual_seed(it)
+                self.orc.dis_update(b, torch.randn(1, 8, B, 8))
+                self.orc.gen_update(b, torch.randn(1, 8, B, 8), torch.randn(1, 8, B, 8))
+                self.orc.smooth_moving()
+                self.orc.update_attention_status(it)
+            else:
+                with torch.no_grad():
+                    O.translate(self.orc.G, b["x_real"], b["txt"], b["txt_lens"], True, self.ocfg)
+
+    def describe(self, steps):
+        what = "G+D training steps" if self.conf["train"] else "translations"
+        src = "the unmodified reference (oracle/_ref snapshot), torch CPU fp32" if self.kind == "reference" \
+            else "the oracle port (no oracle/_ref snapshot on this box), torch CPU fp32"
+        return "%d %s of batch %d at %dx%d by %s" % (steps, what, self.B, self.conf["size"], self.conf["size"], src)
 
 
-def run_reference(args):
+def run_reference(args, conf, our_config):
+    """`--impl reference`: K timed + W warm-up steps of the reference on all host cores, within ~REF_BUDGET_S."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import dwc_oracle as O
     torch.set_num_threads(os.cpu_count())
-    sample_b = 2 if args.steps <= 12 else 1
-    orc, batch = cpu_baseline(sample_b)
-    B = sample_b
-
-    def step(it):
-        torch.manual_seed(it)
-        orc.dis_update(batch, torch.randn(1, 8, B, 8))
-        orc.gen_update(batch, torch.randn(1, 8, B, 8), torch.randn(1, 8, B, 8))
-        orc.smooth_moving()
-        orc.update_attention_status(it)
-    for it in range(args.warmup):
-        step(it)
+    r = _RefRunner(conf)
+    # BASELINE configs[0] is batch 8 for training; inference uses the config's own batch.  One probe step decides
+    # whether K + W steps of that batch fit the budget; otherwise the batch is halved (stated in `sample`).
+    B = 8 if conf["train"] else conf["batch"]
+    total = args.steps + args.warmup
+    r.set_batch(B)
     t0 = time.perf_counter()
-    for it in range(args.steps):
-        step(args.warmup + it)
+    r.step(0)
+    probe = time.perf_counter() - t0
+    while B > 1 and probe * total * (B / r.B) > REF_BUDGET_S:
+        B //= 2
+    if B != r.B:
+        r.set_batch(B)
+    it = 1
+    for _ in range(max(0, args.warmup - 1)):
+        r.step(it)
+        it += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r.step(it)
+        it += 1
     dt = time.perf_counter() - t0
     v = B * args.steps / dt
-    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "images/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": conf["metric"], "value": round(v, 4), "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "full G+D training step, 128x128, configs/celeba_faces.yaml, vgg_w=0",
-                       "per_gpu_batch": 16, "sample_batch": B},
-            "cpu_baseline": {"value": round(v, 4), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "%d G+D steps of batch %d (reference algorithm, oracle port, torch CPU fp32)" % (
-                                 args.steps, B)},
+            "config": our_config, "sample_batch": B,
+            "cpu_baseline": {"value": round(v, 4), "unit": "images/s", "cores": torch.get_num_threads(), "kind": r.kind,
+                             "sample": r.describe(args.steps)},
             "e2e": {"value": round(v, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(conf, budget_s=25.0):
+    """cpu_baseline of our own line (rank 0, N = 1): a bounded sample of the same workload on the host cores."""
+    torch.set_num_threads(os.cpu_count())
+    r = _RefRunner(conf)
+    B = 8 if conf["train"] else min(conf["batch"], 16)
+    r.set_batch(B)
+    t0 = time.perf_counter()
+    r.step(0)
+    probe = time.perf_counter() - t0
+    if probe > budget_s and B > 2:               # the probe step itself was the sample
+        return {"value": round(B / probe, 4), "unit": "images/s", "cores": torch.get_num_threads(), "kind": r.kind,
+                "sample": r.describe(1) + " (first call, includes allocator warm-up), %.1f s" % probe}
+    t0 = time.perf_counter()
+    r.step(1)
+    dt = time.perf_counter() - t0
+    return {"value": round(B / dt, 4), "unit": "images/s", "cores": torch.get_num_threads(), "kind": r.kind,
+            "sample": r.describe(1) + " after one warm-up call, %.1f s" % dt}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+
+def our_config_dict(name, conf, B, world, mode):
+    return {"workload": conf["workload"], "name": name, "per_gpu_batch": B, "global_batch": B * world,
+            "parallelism": "dp%d" % world if conf["train"] else "replicas%d" % world,
+            "l2": "inputs larger than L2: one step streams > 2 GB of activations per GPU" if conf["train"] else
+                  "one call streams ~1.7 GB of activations (> 126 MB L2); weights (41 MB bf16) stay L2-resident as in serving",
+            "mode": mode}
 
 
 def main():
@@ -192,12 +331,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--config", default="train128", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--mode", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    conf = CONFIGS[args.config]
+    B = args.batch or conf["batch"]
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, conf, our_config_dict(args.config, conf, B, world_env, "bf16"))
     if args.warmup < 3:
         args.warmup = 3
 
@@ -210,13 +353,27 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     peaks = load_peaks()
-    s, cfg = build_solver(dev, args.mode)
-    if world > 1:
-        parallel.attach(s)
-    B = args.batch
-    host = make_host_batch(B, 128, seed=rank)
+    s, cfg = build_solver(dev, args.mode, conf["overrides"])
+    if world > 1 and conf["train"]:
+        parallel.attach(s)                       # inference: N independent replicas, no collective
+    host = make_host_batch(B, conf["size"], seed=rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
+    if conf["train"]:
+        keys = list(pinned)
+
+        def step(b, it):
+            train_step(s, cfg, b, it)
+            return None
+    else:
+        s.eval()
+        keys = ["x_real", "txt", "txt_lens"]
+        pinned = {k: pinned[k] for k in keys}
+        out_host = torch.empty(B, 3, conf["size"], conf["size"], dtype=torch.float32).pin_memory()
+
+        def step(b, it):
+            with torch.no_grad():
+                return s(b["x_real"], b["txt"], b["txt_lens"])
 
     def barrier():
         if world > 1:
@@ -226,7 +383,7 @@ def main():
     # ---- device-resident timing
     it = 0
     for _ in range(args.warmup):
-        one_step(s, cfg, resident, it)
+        step(resident, it)
         it += 1
     barrier()
     sampler = ClockSampler(local)
@@ -235,29 +392,34 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        one_step(s, cfg, resident, it)
+        step(resident, it)
         it += 1
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = dwc_gan_b200.RT.launches - l0
     sampler.stop_flag = True
-    # ---- end to end: pinned host batch -> device every step, losses read back every step
-    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    # ---- end to end through the public API: pinned host batch -> device every step, result read back every step
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     d2h = 0
     for _ in range(args.steps):
-        b = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        one_step(s, cfg, b, it)
+        b = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
+        out = step(b, it)
         it += 1
-        losses = torch.stack([s.loss_gen_total.detach().float(), s.loss_dis_all.detach().float()]).cpu()
-        d2h = losses.numel() * 4
+        if conf["train"]:
+            result = torch.stack([s.loss_gen_total.detach().float(), s.loss_dis_all.detach().float()]).cpu()
+        else:
+            out_host.copy_(out.float(), non_blocking=True)            # the translated images are the result
+            torch.cuda.current_stream().synchronize()
+            result = out_host
+        d2h = result.numel() * 4
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
-    assert torch.isfinite(losses).all(), losses
+    assert torch.isfinite(result).all()
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -267,28 +429,18 @@ def main():
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     sampler.join(timeout=2)
-    roof = conv_roofline(peaks, B)
-    roof["step_tensor_frac_sustained"] = round(value / world * GFLOP_PER_IMAGE_STEP * 1e9 / (peaks["tflops_sustained"] * 1e12), 4)
-    line = {"metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+    roof = conv_roofline(peaks, 3 * B if conf["train"] else B)
+    roof["step_tensor_frac_sustained"] = round(value / world * conf["gflop"] * 1e9 / (peaks["tflops_sustained"] * 1e12), 4)
+    roof["step_tensor_frac_burst"] = round(value / world * conf["gflop"] * 1e9 / (peaks["tflops"] * 1e12), 4)
+    roof["step_algorithmic_gflop_per_image"] = conf["gflop"]
+    line = {"metric": conf["metric"], "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode.startswith("bf16") else "f32",
-            "data": "synthetic",
-            "config": {"workload": "full G+D training step, 128x128, configs/celeba_faces.yaml, vgg_w=0 (BASELINE configs[2])",
-                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                       "l2": "inputs larger than L2: one step streams > 2 GB of activations per GPU",
-                       "mode": args.mode},
+            "data": "synthetic", "config": our_config_dict(args.config, conf, B, world, args.mode),
             "e2e": {"value": round(e2e, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof}
-    if not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count())
-        orc, cb = cpu_baseline(2)
-        t0 = time.perf_counter()
-        orc.dis_update(cb, torch.randn(1, 8, 2, 8))
-        orc.gen_update(cb, torch.randn(1, 8, 2, 8), torch.randn(1, 8, 2, 8))
-        orc.smooth_moving()
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": round(2 / dt, 4), "unit": "images/s", "cores": torch.get_num_threads(),
-                                "kind": "port", "sample": "1 G+D step of batch 2 (oracle port, torch CPU fp32), %.1f s" % dt}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_leg(conf)
     print(json.dumps(line), flush=True)
     _leave(world)
 

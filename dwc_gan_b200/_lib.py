@@ -37,6 +37,7 @@ class GConv(C.Structure):
         ("o_str", C.c_int64 * 3),
         ("out_dtype", C.c_int32), ("accumulate", C.c_int32),
         ("nphase", C.c_int32), ("reserved0", C.c_int32), ("phase_w_off", C.c_int64), ("phase_out_off", C.c_int64),
+        ("stats", C.c_void_p),
     ]
 
 

@@ -232,14 +232,17 @@ __global__ void __launch_bounds__(TC_THREADS)
       const int half = (warp - 2) >> 2;
       const int cw0 = half * HB_;                          // first column of this warp inside the tile
       uint8_t* stg = smem + (warp - 2) * (32 * ROWB);      // all MMAs have retired: the stage buffers are free
+      // fused statistics: per-warp column sums go to shared memory behind the staging area, [8 warps][HB_] float2
+      float2* sst = reinterpret_cast<float2*>(smem + 8 * 32 * ROWB);
 #pragma unroll 1
       for (int cc = 0; cc < HB_; cc += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cw0 + cc), v);
         tmem_ld_wait();
+        float fa[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          float f[8];
+          float* f = fa + j;
           if (p.bias) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cw0 + cc + j));
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cw0 + cc + j + 4));
@@ -253,6 +256,22 @@ __global__ void __launch_bounds__(TC_THREADS)
           }
           const int piece = (cc + j) >> 3;
           Vec8<bf16>::store(reinterpret_cast<bf16*>(stg + lane * ROWB + ((piece ^ (lane & (PIECES - 1))) << 4)), f);
+        }
+        if (p.stats) sst[(warp - 2) * HB_ + cc + lane] = warp_col_stats32(fa, lane, valid);
+      }
+      if (p.stats) {
+        // add the four row quadrants of each column half and write this tile's partial sums
+        epi_bar_sync();
+        const int tpi = p.tiles_x * p.tiles_y, n_img = tile / tpi, t_img = tile - n_img * tpi;
+        for (int c = threadIdx.x - 64; c < BN; c += 256) {
+          const int h2 = c / HB_, ccol = c - h2 * HB_;
+          float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) {
+            const float2 u = sst[(h2 * 4 + w4) * HB_ + ccol];
+            t.x += u.x; t.y += u.y;
+          }
+          p.stats[((long long)n_img * tpi + t_img) * p.ncols + col0 + c] = t;
         }
       }
       __syncwarp();
@@ -348,13 +367,14 @@ template <int BN> struct TcpCfg {
   // producer / MMA-issuer threads per SM as in the non-persistent kernel
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
   static constexpr int CTAS_PER_SM = BN >= 256 ? 1 : 2;
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES_AL) + 1024 + 512;
+  static constexpr int STAT_BYTES = BN >= 64 ? 2 * 8 * (BN / 2) * 8 : 0;     // 2 buffers x 8 warps x BN/2 columns x float2
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES_AL) + 1024 + 512 + STAT_BYTES;
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, (BN >= 256 ? 1 : 2))     // narrow tiles: two CTAs per SM (<= 102 registers)
     gconv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ GConvDev p) {
   using Cfg = TcpCfg<BN>;
@@ -475,6 +495,9 @@ __global__ void __launch_bounds__(TC_THREADS)
       off += ph * p.phase_out_off;
       mbar_wait(&tmem_full[acc], (li >> 1) & 1);
       tc_fence_after();
+      // fused statistics (BN >= 64): per-warp column sums in shared memory, double-buffered over items
+      float2* sst = reinterpret_cast<float2*>(smem + Cfg::STAGES * (Cfg::A_BYTES + Cfg::B_BYTES_AL) + 512) +
+                    (li & 1) * 8 * HCOLS;
 #pragma unroll 1
       for (int cc = 0; cc < HCOLS; cc += CHUNK) {
         uint32_t v[32];
@@ -490,6 +513,20 @@ __global__ void __launch_bounds__(TC_THREADS)
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (BN >= 64 && CHUNK == 32 && p.stats) {
+          // the bias is added here once (the store path below then sees biased values): v <- v + bias, in place
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + ccol + j));
+              v[j] = __float_as_uint(__uint_as_float(v[j]) + b.x);
+              v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b.y);
+              v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b.z);
+              v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b.w);
+            }
+          }
+          sst[(warp - 2) * HCOLS + cc + lane] = warp_col_stats32(reinterpret_cast<const float*>(v), lane, valid);
+        }
         if (!valid) continue;
         const int cbase = col0 + ccol;
         if (p.out_dtype == DWC_BF16) {
@@ -500,7 +537,7 @@ __global__ void __launch_bounds__(TC_THREADS)
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
-              if (p.bias) {
+              if (p.bias && !(BN >= 64 && p.stats)) {
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
                 const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j + 4));
                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
@@ -532,6 +569,23 @@ __global__ void __launch_bounds__(TC_THREADS)
               o[j] = f;
             }
           }
+        }
+      }
+      if (BN >= 64 && p.stats) {
+        // add the four row quadrants of each column half and write this tile's partial sums (one barrier per item:
+        // the buffer of item li is next written at item li + 2, after every warp has passed the barrier of li + 1)
+        __syncwarp();
+        epi_bar_sync();
+        const int tpi = p.tiles_x * p.tiles_y, n_img = tile / tpi, t_img = tile - n_img * tpi;
+        for (int c = threadIdx.x - 64; c < BN; c += 256) {
+          const int h2 = c / HCOLS, cq = c - h2 * HCOLS;
+          float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) {
+            const float2 u = sst[(h2 * 4 + w4) * HCOLS + cq];
+            t.x += u.x; t.y += u.y;
+          }
+          p.stats[((long long)n_img * tpi + t_img) * p.ncols + col0 + c] = t;
         }
       }
     }
@@ -618,6 +672,12 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
   d.ncols = g->ncols; d.ncols_padded = g->ncols_padded;
   d.out_dtype = g->out_dtype; d.accumulate = g->accumulate;
   d.nphase = nphase; d.phase_out_off = g->phase_out_off;
+  d.stats = reinterpret_cast<float2*>(g->stats);
+  if (g->stats) {
+    DWC_CHECK(g->backend == DWC_TC && g->dtype == DWC_BF16 && g->out_dtype == DWC_BF16 && !g->flat && nphase == 1 &&
+                  g->box[2] == 1 && g->ncols % 64 == 0 && g->ncols == g->ncols_padded && !g->accumulate,
+              "dwc_gconv: fused statistics need the tcgen05 backend, bf16 output, one image per tile and ncols %% 64 == 0");
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -646,7 +706,7 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
       const char* e = getenv("DWC_CG2");
       cg2 = e ? atoi(e) : 0;
     }
-    if (cg2 && ntiles >= 2) {
+    if (cg2 && ntiles >= 2 && !g->stats) {
       const int rc = dwc_launch_gconv_tc2(g, d, st);
       if (rc >= 0) return rc;
     }

@@ -18,6 +18,7 @@ struct GConvDev {
   int out_dtype, accumulate;
   int nphase;            // >= 1
   long long phase_out_off;   // element offset of a phase's output; its weights start ncols_padded rows further down
+  float2* stats;         // fused per-(n, tile, column) {sum, sum of squares} of the stored outputs, or null
   int debug;             // diagnostics only (DWC_GCONV_DEBUG): 1 no stores, 2 no epilogue, 3 no mainloop
   int taps[DWC_MAX_TAPS][3];
 };
@@ -55,6 +56,43 @@ __device__ __forceinline__ bool out_offset(const GConvDev& p, const RowCoord& rc
   return true;
 }
 
+
+// ---- fused statistics in the tcgen05 epilogues -------------------------------------------------------------------
+// Column sums over the 32 lanes of a warp for 32 per-lane values (lane = accumulator row, index = column): after the
+// five exchange stages lane j holds sum_l v_l[j] in v[0] - 31 shuffles instead of 5 per column.
+template <int N> __device__ __forceinline__ void colsum_stage(float* v, int lane) {
+  const bool up = (lane & N) != 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float keep = up ? v[i + N] : v[i];
+    const float send = up ? v[i] : v[i + N];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, N);
+  }
+}
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+  colsum_stage<16>(v, lane);
+  colsum_stage<8>(v, lane);
+  colsum_stage<4>(v, lane);
+  colsum_stage<2>(v, lane);
+  colsum_stage<1>(v, lane);
+  return v[0];
+}
+// {sum, sum of squares} over the warp's 32 rows of the 32 columns f[0..32) of this lane's row, as they are STORED
+// (rounded to bf16): lane j returns column j.  Rows outside the valid region contribute nothing.  The two reductions
+// run one after the other so that only one 32-register scratch array is live next to f.
+__device__ __forceinline__ float2 warp_col_stats32(const float* f, int lane, bool valid) {
+  float t[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) t[j] = valid ? __bfloat162float(__float2bfloat16_rn(f[j])) : 0.f;
+  const float s = warp_colsum32(t, lane);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float r = valid ? __bfloat162float(__float2bfloat16_rn(f[j])) : 0.f;
+    t[j] = r * r;
+  }
+  return make_float2(s, warp_colsum32(t, lane));
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 
 // CTA-pair (cta_group::2) variant of the tap-by-tap kernel, gconv2.cu; -1 = geometry not handled
 int dwc_launch_gconv_tc2(const dwc_gconv_t* g, const GConvDev& d, cudaStream_t st);

@@ -48,6 +48,8 @@ class Runtime:
         self.use_sty_stream = os.environ.get("DWC_STY_STREAM", "1") != "0"
         self.conv7_which = os.environ.get("DWC_CONV7", "1")          # diagnostics: "h" heads only, "d" dgrad only
         self.use_fused_norm = os.environ.get("DWC_FUSED_NORM", "0") != "0"   # opt-in: the row-streaming passes are faster
+        self.epi_stats = os.environ.get("DWC_EPI_STATS", "1") != "0"        # norm statistics from the conv epilogue
+        self.wgrad_hook = None       # data parallel: callable(weight name) after a layer's weight gradient is enqueued
 
     def set_mode(self, mode: str):
         if mode == "bf16":
@@ -82,10 +84,19 @@ class Runtime:
 RT = Runtime()
 
 
-def side_launch(fn, keep):
+def side_launch(fn, keep, name=None):
     """Run `fn` (weight-gradient kernels: off the critical path of backward) on the device's side stream, ordered
     after everything already enqueued on the current stream.  `keep` are the tensors the kernels read: they are held
-    until side_join() so that their memory is not reused while the side stream still needs it."""
+    until side_join() so that their memory is not reused while the side stream still needs it.  `name`: the weight
+    whose gradient `fn` produces - reported to RT.wgrad_hook (bucketed gradient all-reduce, parallel.GradSync)."""
+    try:
+        return _side_launch(fn, keep)
+    finally:
+        if name is not None and RT.wgrad_hook is not None:
+            RT.wgrad_hook(name)
+
+
+def _side_launch(fn, keep):
     if not RT.use_side_stream:
         return fn()
     dev = torch.cuda.current_device()
@@ -185,14 +196,18 @@ class ConvFn(torch.autograd.Function):
         tc = RT.tc_ok(xp.c) and (rows_p % 64 == 0 or rows_p == 16)
         pl = P.plan_conv_fwd(HB(xp_t, xp.n, xp.h, xp.w, xp.c, xp.halo, xp.layout), wf, cout, rows_p, layer.bias_f32(),
                              y, k, s, L.TC if tc else L.SIMT)
+        stats = _attach_stats(pl, layer, xp.n, cout, xp_t.device)
         RT.launches += 1
         pl.launch()
         ctx.layer, ctx.xp_meta, ctx.y_meta = layer, (xp.n, xp.h, xp.w, xp.c, xp.halo, xp.layout), (ho, wo, hy)
         ctx.save_for_backward(xp_t)
-        return y.t
+        if stats is None:
+            return y.t
+        ctx.mark_non_differentiable(stats)
+        return y.t, stats
 
     @staticmethod
-    def backward(ctx, dy_t):
+    def backward(ctx, dy_t, dstats=None):
         layer = ctx.layer
         (xp_t,) = ctx.saved_tensors
         n, h, w, c, halo, layout = ctx.xp_meta
@@ -222,15 +237,35 @@ class ConvFn(torch.autograd.Function):
             tc = RT.tc_ok(c, cout)
             wp = P.plan_conv_wgrad(dy, xp, gw, gb, k, s, L.TC if tc else L.SIMT, accumulate=True)
             RT.launches += 3
-            side_launch(lambda: wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device)), (dy.t, xp_t))
+            side_launch(lambda: wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device)), (dy.t, xp_t),
+                        name=layer._names()[1])
         return dxp_t, None, None, None, None
+
+
+def _attach_stats(pl, layer, n, cout, device):
+    """Ask the convolution's epilogue for the per-(n, tile, column) partial sums its norm layer needs (InstanceNorm /
+    AdaIN / LayerNorm statistics without re-reading y); None when the layer has no norm or the launch cannot do it."""
+    if not RT.epi_stats or getattr(layer, "norm_kind", NORM_NONE) == NORM_NONE:
+        return None
+    splits = P.stats_splits(pl)
+    if splits == 0 or splits > 256:
+        return None
+    pl.stats = torch.empty(n * splits * cout * 2, dtype=torch.float32, device=device)
+    return pl.stats
+
+
+def _hb_with_stats(out, n, ho, wo, cout, halo):
+    if isinstance(out, tuple):
+        t, stats = out
+        return HB(t, n, ho, wo, cout, halo, 0, stats=(stats, stats.numel() // (2 * n * cout)))
+    return HB(out, n, ho, wo, cout, halo, 0)
 
 
 def conv(xp: HB, layer, skip_box=None) -> HB:
     k, s = layer.k, layer.stride
     ho, wo = P.out_size(xp, k, s)
-    t = ConvFn.apply(xp.t, layer.weight_param, layer, xp, skip_box)
-    return HB(t, xp.n, ho, wo, layer.total_cout(), k - 1 if s == 1 else 1, 0)
+    out = ConvFn.apply(xp.t, layer.weight_param, layer, xp, skip_box)
+    return _hb_with_stats(out, xp.n, ho, wo, layer.total_cout(), k - 1 if s == 1 else 1)
 
 
 def image_rows(img, pool, layer):
@@ -262,14 +297,19 @@ class FirstConvFn(torch.autograd.Function):
         y = HB.empty(n, ho, wo, cout, hy, 0, rows_t.dtype, rows_t.device)
         be = L.TC if RT.tc_ok(64, cout) else L.SIMT
         RT.launches += 1
-        P.plan_first_conv_fwd(rows_t, n, hp, wo, ho, k, s, layer.packed_rows(rows_t.dtype, 3), cout, layer.bias_f32(), y,
-                              be).launch()
+        pl = P.plan_first_conv_fwd(rows_t, n, hp, wo, ho, k, s, layer.packed_rows(rows_t.dtype, 3), cout, layer.bias_f32(),
+                                   y, be)
+        stats = _attach_stats(pl, layer, n, cout, rows_t.device)
+        pl.launch()
         ctx.layer, ctx.meta = layer, (n, c, h, w, pool, hp, ho, wo, hy)
         ctx.save_for_backward(rows_t)
-        return y.t
+        if stats is None:
+            return y.t
+        ctx.mark_non_differentiable(stats)
+        return y.t, stats
 
     @staticmethod
-    def backward(ctx, dy_t):
+    def backward(ctx, dy_t, dstats=None):
         layer = ctx.layer
         (rows_t,) = ctx.saved_tensors
         n, c, h, w, pool, hp, ho, wo, hy = ctx.meta
@@ -302,7 +342,8 @@ class FirstConvFn(torch.autograd.Function):
             be = L.TC if RT.tc_ok(64, cout) else L.SIMT
             RT.launches += 3
             wp = P.plan_first_conv_wgrad(dy, rows_t, n, hp, wo, k, s, c, gw, gb, be)
-            side_launch(lambda: wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device)), (dy.t, rows_t))
+            side_launch(lambda: wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device)), (dy.t, rows_t),
+                        name=layer._names()[1])
         return dimg, None, None, None, None
 
 
@@ -310,8 +351,8 @@ def first_conv(img, rows_t, layer, pool) -> HB:
     n, c, h, w = img.shape
     k, s, p = layer.k, layer.stride, layer.padding
     ho, wo = (h // pool + 2 * p - k) // s + 1, (w // pool + 2 * p - k) // s + 1
-    t = FirstConvFn.apply(img.contiguous().float(), layer.weight_param, layer, rows_t, pool)
-    return HB(t, n, ho, wo, layer.cout, k - 1 if s == 1 else 1, 0)
+    out = FirstConvFn.apply(img.contiguous().float(), layer.weight_param, layer, rows_t, pool)
+    return _hb_with_stats(out, n, ho, wo, layer.cout, k - 1 if s == 1 else 1)
 
 
 def conv7_few(x_t, n, hin, win, w_master, w_base, s_o, s_ky, s_kx, s_i, bias, cout, out_t, out_str):
@@ -504,11 +545,14 @@ class PostFn(torch.autograd.Function):
                   C.byref(rs) if rs is not None else None, C.byref(os_), L.ptr(coef), L.stream())
         else:
             if kind != NORM_NONE:
-                stats = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
-                _call("dwc_nc_stats", C.byref(ys), splits, L.ptr(stats), L.stream())
+                if y.stats is not None:                   # partial sums written by the producing conv's epilogue
+                    stats, fsplits = y.stats
+                else:
+                    stats, fsplits = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev), splits
+                    _call("dwc_nc_stats", C.byref(ys), splits, L.ptr(stats), L.stream())
                 coef = torch.empty(n * c * 4, dtype=torch.float32, device=dev)
                 # statistics -> coefficients inside the normalise kernel (or a separate finalize pass, see the C side)
-                _call("dwc_post_fwd_norm", C.byref(ys), kind, L.ptr(stats), splits, L.f32(eps), L.ptr(nw), L.ptr(nb),
+                _call("dwc_post_fwd_norm", C.byref(ys), kind, L.ptr(stats), fsplits, L.f32(eps), L.ptr(nw), L.ptr(nb),
                       act, C.byref(rs) if rs is not None else None, C.byref(os_), L.ptr(coef), L.stream())
             else:
                 _call("dwc_post_fwd", C.byref(ys), None, act, C.byref(rs) if rs is not None else None, C.byref(os_),

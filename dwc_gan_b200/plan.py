@@ -39,10 +39,11 @@ class HB:
     """Haloed NHWC activation buffer.  layout 0: [N, H+2h, W+2h, C]; layout 1: four parity planes
     [N, 4, (H+2h)/2, (W+2h)/2, C] (input of a stride-2 conv)."""
 
-    __slots__ = ("t", "n", "h", "w", "c", "halo", "layout")
+    __slots__ = ("t", "n", "h", "w", "c", "halo", "layout", "stats")
 
-    def __init__(self, t, n, h, w, c, halo, layout=0):
+    def __init__(self, t, n, h, w, c, halo, layout=0, stats=None):
         self.t, self.n, self.h, self.w, self.c, self.halo, self.layout = t, n, h, w, c, halo, layout
+        self.stats = stats            # (partial sums tensor, splits) written by the producing convolution's epilogue
 
     @staticmethod
     def shape_of(n, h, w, c, halo, layout=0):
@@ -116,6 +117,7 @@ class GConvPlan:
     o_str: Tuple[int, int, int]
     accumulate: bool = False
     backend: int = L.SIMT
+    stats: Optional[torch.Tensor] = None   # fused per-(n, tile, column) {sum, sumsq} partials (see dwc_b200.h)
     nphase: int = 1                # independent problems sharing A / tiling / taps (stride-2 dgrad parity phases)
     phase_w_off: int = 0           # element offset of phase ph's weights: w_off + ph * phase_w_off
     phase_out_off: int = 0         # element offset of phase ph's output: out_off + ph * phase_out_off
@@ -144,6 +146,7 @@ class GConvPlan:
         g.out_dtype = L.dt(self.out)
         g.accumulate = int(self.accumulate)
         g.nphase, g.phase_w_off, g.phase_out_off = self.nphase, self.phase_w_off, self.phase_out_off
+        g.stats = self.stats.data_ptr() if self.stats is not None else None
         L.check(L.lib().dwc_gconv(C.byref(g), L.stream()), "gconv")
 
 
@@ -233,6 +236,18 @@ def input_view(xp: HB):
         return (c, xp.wp, xp.hp, 1, xp.n), (1, c, xp.wp * c, xp.hp * xp.wp * c, xp.hp * xp.wp * c)
     hq, wq = xp.hp // 2, xp.wp // 2
     return (c, wq, hq, 4, xp.n), (1, c, wq * c, hq * wq * c, 4 * hq * wq * c)
+
+
+def stats_splits(plan: "GConvPlan") -> int:
+    """Number of per-image partials the fused-statistics epilogue of `plan` writes, or 0 if it cannot (tiles that
+    span images, non-tensor-core backends, few-channel outputs, experimental kernels)."""
+    if plan.backend != L.TC or plan.box[2] != 1 or plan.flat[0] or plan.nphase != 1 or plan.accumulate:
+        return 0
+    if plan.ncols % 64 != 0 or plan.ncols != plan.ncols_padded or plan.out.dtype != torch.bfloat16:
+        return 0
+    if HALO_K or os.environ.get("DWC_CG2") or os.environ.get("DWC_GCONV_DEBUG"):
+        return 0
+    return plan.tiles[0] * plan.tiles[1]
 
 
 def out_size(xp: HB, k: int, stride: int):

@@ -329,6 +329,8 @@ class Solver(nn.Module):
     def _gen_update_impl(self, x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg, configs, iters):
         gen, dis = self.gen, self.dis
         self.gen_opt.zero_grad()
+        if self._dp_sync is not None:
+            self._dp_sync.begin(self.gen, key=bool(self.use_attention))
         x_real = x_real.float()
         B = x_real.shape[0]
         tbox = {}
@@ -445,6 +447,8 @@ class Solver(nn.Module):
     def _dis_update_impl(self, x_real, c_src, c_trg, txt_src2trg, txt_lens, label_src, label_trg, configs, iters):
         gen, dis = self.gen, self.dis
         self.dis_opt.zero_grad()
+        if self._dp_sync is not None:
+            self._dp_sync.begin(self.dis, key=bool(self.use_attention))
         x_real = x_real.float()
         B = x_real.shape[0]
         with torch.no_grad():                                   # G gradients of this phase are discarded anyway

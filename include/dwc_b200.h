@@ -84,6 +84,12 @@ typedef struct {
   int32_t reserved0;
   int64_t phase_w_off;
   int64_t phase_out_off;
+  /* Optional fused statistics (tcgen05 backend, bf16 output, box[2] == 1, no flat / phases, ncols % 64 == 0): the
+   * epilogue also writes per-(n, tile, column) partial sums of the stored (bf16-rounded) outputs,
+   * stats[((n * splits + t) * ncols + c) * 2 + {0, 1}] = {sum, sum of squares} with splits = tiles[0] * tiles[1] and
+   * t = ty * tiles[0] + tx - the first half of InstanceNorm / AdaIN / LayerNorm (networks.py:545,706-719,736-752)
+   * without re-reading the convolution's output (same layout as dwc_nc_stats).  NULL = off. */
+  float* stats;
 } dwc_gconv_t;
 
 int dwc_gconv(const dwc_gconv_t* p, dwc_stream_t stream);

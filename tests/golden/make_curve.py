@@ -3,7 +3,7 @@ test (tests/test_curve_gpu.py).  Build container only (needs /root/reference); d
 off), batch 1 of oracle.dwc_oracle.synthetic_batch(seed=7), GMM noise from torch.manual_seed(100+it) /
 (200+it) exactly as tests/golden/make_golden.py does.
 
-Usage:  python tests/golden/make_curve.py [steps]      -> tests/golden/ref_curve_b1.json
+Usage:  python tests/golden/make_curve.py [steps [batch]]      -> tests/golden/ref_curve_b<batch>.json
 """
 import json
 import os
@@ -23,7 +23,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     solver, cfg = MG.build_reference()
     solver.copy_nets()
-    B = 1
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     batch = O.synthetic_batch(B, 128, seed=7)
     names = ["loss_dis", "loss_gen_total", "loss_gen_adv", "loss_gen_recon_x", "loss_gen_recon_c_real",
              "loss_gen_recon_s_fake", "loss_gen_cycrecon_x", "loss_kl_x", "loss_kl_trg", "loss_ds"]
@@ -45,9 +45,10 @@ def main():
             print(it, "%.1fs" % (time.time() - t0), curve["loss_dis"][-1], curve["loss_gen_total"][-1], flush=True)
     out = {"B": B, "batch_seed": 7, "steps": steps, "curve": curve,
            "note": "reference run: torch %s CPU fp32, deterministic mode, vgg_w=0, seed 1234" % torch.__version__}
-    with open(os.path.join(HERE, "ref_curve_b1.json"), "w") as f:
+    name = "ref_curve_b%d.json" % B
+    with open(os.path.join(HERE, name), "w") as f:
         json.dump(out, f)
-    print("wrote ref_curve_b1.json")
+    print("wrote", name)
 
 
 if __name__ == "__main__":

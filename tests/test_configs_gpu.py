@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import dwc_oracle as O
-from tests.util_gpu import build_solver, compare_grads, cpu_state, grads_of, rel, to_cuda
+from tests.util_gpu import assert_grads, build_solver, cpu_state, grads_of, rel, to_cuda
 
 pytestmark = pytest.mark.gpu
 
@@ -36,15 +36,18 @@ def test_inference_batch64_bf16():
     assert float(out.abs().max()) <= 1.0 + 1e-3        # attention blend of tanh output and the input image
 
 
-@pytest.mark.parametrize("mode,ltol,gtol", [("fp32", 2e-4, 3e-2), ("bf16", 2e-2, 2.5e-1)])
-def test_256_variant_training_step(mode, ltol, gtol):
+@pytest.mark.parametrize("mode,ltol", [("fp32", 2e-4), ("bf16", 2e-2)])
+def test_256_variant_training_step(mode, ltol):
+    """BASELINE configs[3]: image_size 256, dis.image_size 256, gen.content_downsample 3, batch 2 (the
+    text encoder's row mixing is active), one full D+G step; gradient bounds as in tests/test_step_gpu.py."""
     over = {"image_size": 256, "dis": {"image_size": 256}, "gen": {"content_downsample": 3}}
     s, cfg = build_solver(mode, overrides=over)
     ocfg = dict(O.DEFAULT_CFG, image_size=256, content_downsample=3)
-    B = 1
+    B = 2
     batch = O.synthetic_batch(B, 256, seed=2)
     b = to_cuda(batch)
     orc = O.OracleSolver(cpu_state(s.gen), cpu_state(s.dis), cfg=ocfg)
+    orcq = O.OracleSolver(cpu_state(s.gen), cpu_state(s.dis), cfg=ocfg) if mode == "bf16" else None
     s.copy_nets()
     eps = {}
     s.noise_hook = lambda tag: eps[tag].cuda()
@@ -53,17 +56,20 @@ def test_256_variant_training_step(mode, ltol, gtol):
     eps["dis1"] = torch.randn(1, 8, B, 8)
     s.dis_update(*args)
     orc.dis_update(batch, eps["dis1"])
+    if orcq is not None:
+        with O.storage_rounding("bf16"):
+            orcq.dis_update(batch, eps["dis1"])
     ld = float(s.loss_dis)
     assert abs(ld - orc.losses["loss_dis"]) < ltol * abs(ld), (ld, orc.losses["loss_dis"])
-    worst, wk, glob = compare_grads(grads_of(s.dis), orc.last_dis_grads)
-    assert glob < gtol, ("dis grads", worst, wk, glob)
+    assert_grads("256 dis", grads_of(s.dis), orc.last_dis_grads, orcq.last_dis_grads if orcq else None, mode)
     torch.manual_seed(200)
     eps["gen1"], eps["gen2"] = torch.randn(1, 8, B, 8), torch.randn(1, 8, B, 8)
     s.gen_update(*args)
     orc.gen_update(batch, eps["gen1"], eps["gen2"])
+    if orcq is not None:
+        with O.storage_rounding("bf16"):
+            orcq.gen_update(batch, eps["gen1"], eps["gen2"])
     for name in ("loss_gen_total", "loss_gen_adv", "loss_gen_recon_x", "loss_kl_x", "loss_kl_trg", "loss_ds"):
         mine = float(getattr(s, name))
         assert abs(mine - orc.losses[name]) <= ltol * max(1.0, abs(orc.losses[name])), (name, mine, orc.losses[name])
-    worst, wk, glob = compare_grads(grads_of(s.gen), orc.last_gen_grads)
-    print("256 variant", mode, "gen grads worst/glob", worst, wk, glob)
-    assert glob < gtol, ("gen grads", worst, wk, glob)
+    assert_grads("256 gen", grads_of(s.gen), orc.last_gen_grads, orcq.last_gen_grads if orcq else None, mode)

@@ -153,3 +153,44 @@ def test_conv7_few(n, hin, win, cout, flip):
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w_oihw.to(torch.bfloat16).float(), bias).permute(0, 2, 3, 1)
     err = (out.float() - ref).abs().max().item()
     assert err <= 2e-2 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,s,p", [(2, 32, 32, 256, 256, 3, 1, 1),      # one-wave kernel, BN 256
+                                                  (40, 32, 32, 256, 256, 3, 1, 1),     # persistent kernel, BN 256
+                                                  (2, 64, 64, 256, 128, 5, 1, 2),      # BN 128
+                                                  (24, 64, 64, 64, 128, 4, 2, 1),      # persistent, BN 128, stride 2
+                                                  (3, 20, 12, 128, 64, 3, 1, 1),       # partial tiles, BN 64
+                                                  (12, 64, 64, 128, 64, 5, 1, 2)])     # persistent, BN 64
+def test_conv_fused_statistics(n, h, w, cin, cout, k, s, p):
+    """The tcgen05 epilogue's per-(image, tile, channel) {sum, sum of squares} of the STORED bf16 outputs
+    (dwc_gconv_t.stats): the statistics pass of InstanceNorm / AdaIN / LayerNorm without re-reading y."""
+    dtype = torch.bfloat16
+    torch.manual_seed(2)
+    x = torch.randn(n, cin, h, w).to(dtype).double()
+    wt = (torch.randn(cout, cin, k, k) * (1.0 / (cin * k * k) ** 0.5)).to(dtype).double()
+    bias = torch.randn(cout)
+    layout, hy = (0, k - 1) if s == 1 else (1, 1)
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    w_krsc = wt.permute(0, 2, 3, 1).contiguous().float().cuda()
+    xp = emu.make_padded(x, p, layout, dtype)
+    xp = xp.like(xp.t.cuda())
+    wf = pack(w_krsc, 0, dtype, cout, cout, k, cin)
+    y = HB.empty(n, ho, wo, cout, hy, 0, dtype, "cuda", zero=True)
+    pl = P.plan_conv_fwd(xp, wf, cout, cout, bias.cuda(), y, k, s, L.TC)
+    splits = P.stats_splits(pl)
+    assert splits == pl.tiles[0] * pl.tiles[1] > 0
+    pl.stats = torch.full((n * splits * cout * 2,), float("nan"), device="cuda")
+    pl.launch()
+    y2 = HB.empty(n, ho, wo, cout, hy, 0, dtype, "cuda", zero=True)
+    P.plan_conv_fwd(xp, wf, cout, cout, bias.cuda(), y2, k, s, L.TC).launch()
+    torch.cuda.synchronize()
+    assert torch.equal(y.t, y2.t)                                  # the output itself is unchanged by the option
+    st = pl.stats.view(n, splits, cout, 2).double().cpu()
+    yi = y.interior().double().cpu()                               # [n, ho, wo, cout], the stored values
+    bx, by, _ = pl.box
+    for ty in range(pl.tiles[1]):
+        for tx in range(pl.tiles[0]):
+            blk = yi[:, ty * by:(ty + 1) * by, tx * bx:(tx + 1) * bx, :]
+            ref = torch.stack([blk.sum((1, 2)), (blk * blk).sum((1, 2))], -1)
+            got = st[:, ty * pl.tiles[0] + tx]
+            assert float((got - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), (tx, ty)

@@ -5,34 +5,49 @@ import pytest
 import torch
 
 from oracle import dwc_oracle as O
-from tests.util_gpu import build_solver, compare_grads, cpu_state, grads_of, rel, to_cuda
+from tests.util_gpu import assert_grads, build_solver, compare_grads, cpu_state, grads_of, rel, to_cuda
 
 pytestmark = pytest.mark.gpu
 
-# (mode, forward tolerance, gradient tolerance).  Forward: 1e-4 relative in fp32 validation mode, 2e-2 in bf16
-# (BASELINE.json north_star).  Gradients are compared in L2 over a whole network: a single (Leaky)ReLU mask that
-# flips because a pre-activation sits within round-off of zero changes a gradient tensor by ~1e-3..1e-2 (measured:
-# the reference's own fp32 gradients move by 3e-3 when only its thread count changes, and deviate 2e-3 from an fp64
-# run in the decoder; tests/diag_dis2.py pins our 1.7e-3 discriminator deviation to one flipped element).  In bf16 the
-# forward round-off of ~5e-3 flips ~0.5 % of the masks, i.e. ~sqrt(5e-3) = 7 % L2 gradient error, as any bf16
-# autocast run of the reference itself would show.
-MODES = [("fp32", 1e-4, 3e-2), ("bf16", 2e-2, 2e-1)]
+# (mode, forward tolerance).  Forward: 1e-4 relative in fp32 validation mode, 2e-2 in bf16 (BASELINE.json north_star).
+# Gradients (tests.util_gpu.assert_grads): fp32 mode 2e-3 global / 2e-2 worst tensor against the fp32 oracle (a single
+# (Leaky)ReLU mask that flips on a pre-activation within round-off of zero moves a gradient tensor by ~1e-3..1e-2: the
+# reference's own fp32 gradients move by 3e-3 when only its thread count changes); bf16 mode: per tensor and globally no
+# worse than 1.5 x what bf16 storage costs the oracle itself (its storage_rounding("bf16") run, computed in the test).
+MODES = [("fp32", 1e-4), ("bf16", 2e-2)]
+
+
+def both(fn):
+    """fn(P) -> tensors with .grad populated; run it on the fp32 oracle and on the bf16-storage-rounding oracle."""
+    out = {}
+    for m in ("fp32", "bf16"):
+        with O.storage_rounding(m):
+            out[m] = fn()
+    return out["fp32"], out["bf16"]
 
 
 def leaf(P):
     return {k: v.clone().requires_grad_(True) for k, v in P.items()}
 
 
-@pytest.mark.parametrize("mode,tol,gtol", MODES)
-def test_encode(mode, tol, gtol):
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_encode(mode, tol):
     s, _ = build_solver(mode)
-    G = leaf(O.trainable(cpu_state(s.gen)))
+    state = O.trainable(cpu_state(s.gen))
     batch = O.synthetic_batch(2, 128, seed=3)
     x = batch["x_real"]
-    c_ref, mus, lvs = O.encode(G, x)
-    mu_ref, lv_ref = torch.cat(mus, 1), torch.cat(lvs, 1)
-    wc, wm, wl = torch.randn_like(c_ref), torch.randn_like(mu_ref), torch.randn_like(lv_ref)
-    ((c_ref * wc).sum() / 100 + (mu_ref * wm).sum() + (lv_ref * wl).sum()).backward()
+    w = {}
+
+    def run():
+        G = leaf(state)
+        c_ref, mus, lvs = O.encode(G, x)
+        mu_ref, lv_ref = torch.cat(mus, 1), torch.cat(lvs, 1)
+        if not w:
+            w.update(c=torch.randn_like(c_ref), m=torch.randn_like(mu_ref), l=torch.randn_like(lv_ref))
+        ((c_ref * w["c"]).sum() / 100 + (mu_ref * w["m"]).sum() + (lv_ref * w["l"]).sum()).backward()
+        return c_ref.detach(), mu_ref.detach(), lv_ref.detach(), {k: v.grad for k, v in G.items()}
+    (c_ref, mu_ref, lv_ref, g32), (_, _, _, gq) = both(run)
+    wc, wm, wl = w["c"], w["m"], w["l"]
 
     s.gen_opt.zero_grad()
     content, mu_l, lv_l = s.gen.encode(x.cuda())
@@ -41,22 +56,31 @@ def test_encode(mode, tol, gtol):
     assert rel(content.float(), c_ref) < tol * 3, rel(content.float(), c_ref)
     assert rel(mu, mu_ref) < tol * 3 and rel(lv, lv_ref) < tol * 3
     ((content.float() * wc.cuda()).sum() / 100 + (mu * wm.cuda()).sum() + (lv * wl.cuda()).sum()).backward()
-    worst, wk, glob = compare_grads(grads_of(s.gen), {k: v.grad for k, v in G.items()})
-    assert glob < gtol and worst < 5 * gtol, (worst, wk, glob)
+    assert_grads("encode", grads_of(s.gen), g32, gq, mode)
 
 
-@pytest.mark.parametrize("mode,tol,gtol", MODES)
-def test_decode(mode, tol, gtol):
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_decode(mode, tol):
     s, _ = build_solver(mode)
-    G = leaf(O.trainable(cpu_state(s.gen)))
+    state = O.trainable(cpu_state(s.gen))
     torch.manual_seed(5)
     content = torch.randn(2, 256, 32, 32).to(torch.bfloat16).float()
     style = torch.randn(2, 64)
-    c_leaf = content.clone().requires_grad_(True)
-    s_leaf = style.clone().requires_grad_(True)
-    img_ref, att_ref = O.decode(G, c_leaf, s_leaf)
-    wi, wa = torch.randn_like(img_ref), torch.randn_like(att_ref)
-    ((img_ref * wi).sum() + (att_ref * wa).sum()).backward()
+    w = {}
+
+    def run():
+        G = leaf(state)
+        c_leaf = content.clone().requires_grad_(True)
+        s_leaf = style.clone().requires_grad_(True)
+        img_ref, att_ref = O.decode(G, c_leaf, s_leaf)
+        if not w:
+            w.update(i=torch.randn_like(img_ref), a=torch.randn_like(att_ref))
+        ((img_ref * w["i"]).sum() + (att_ref * w["a"]).sum()).backward()
+        g = {k: v.grad for k, v in G.items()}
+        g["__content"], g["__style"] = c_leaf.grad, s_leaf.grad
+        return img_ref.detach(), att_ref.detach(), g
+    (img_ref, att_ref, g32), (_, _, gq) = both(run)
+    wi, wa = w["i"], w["a"]
 
     s.gen_opt.zero_grad()
     cc = content.cuda().to(dtype=torch.float32 if mode == "fp32" else torch.bfloat16)
@@ -65,19 +89,27 @@ def test_decode(mode, tol, gtol):
     img, att = s.gen.decode(cc, sc)
     assert rel(img, img_ref) < tol * 3 and rel(att, att_ref) < tol * 3, (rel(img, img_ref), rel(att, att_ref))
     ((img * wi.cuda()).sum() + (att * wa.cuda()).sum()).backward()
-    worst, wk, glob = compare_grads(grads_of(s.gen), {k: v.grad for k, v in G.items()})
-    assert glob < gtol and worst < 5 * gtol, (worst, wk, glob)
-    assert rel(cc.grad.float(), c_leaf.grad) < gtol and rel(sc.grad, s_leaf.grad) < gtol
+    mine = grads_of(s.gen)
+    mine["__content"], mine["__style"] = cc.grad.float().cpu(), sc.grad.cpu()     # input gradients, same bounds
+    assert_grads("decode", mine, g32, gq, mode)
 
 
-@pytest.mark.parametrize("mode,tol,gtol", MODES)
-def test_discriminator(mode, tol, gtol):
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_discriminator(mode, tol):
     s, cfg = build_solver(mode)
-    D = leaf(cpu_state(s.dis))
+    state = cpu_state(s.dis)
     batch = O.synthetic_batch(3, 128, seed=4)
-    x = batch["x_real"].clone().requires_grad_(True)
-    loss_ref = O.dis_loss(D, x, batch["x_real"].flip(0), batch["label_src"]) + O.gen_adv_loss(D, x, batch["label_trg"])
-    loss_ref.backward()
+
+    def run():
+        D = leaf(state)
+        x = batch["x_real"].clone().requires_grad_(True)
+        loss_ref = O.dis_loss(D, x, batch["x_real"].flip(0), batch["label_src"]) + \
+            O.gen_adv_loss(D, x, batch["label_trg"])
+        loss_ref.backward()
+        g = {k: v.grad for k, v in D.items()}
+        g["__x"] = x.grad
+        return loss_ref.detach(), g
+    (loss_ref, g32), (_, gq) = both(run)
 
     s.dis_opt.zero_grad()
     b = to_cuda(batch)
@@ -88,9 +120,9 @@ def test_discriminator(mode, tol, gtol):
         s.dis.calc_gen_loss(xc, b["label_trg"])
     assert abs(float(loss) - float(loss_ref)) < tol * abs(float(loss_ref)) * 3, (float(loss), float(loss_ref))
     loss.backward()
-    worst, wk, glob = compare_grads(grads_of(s.dis), {k: v.grad for k, v in D.items()})
-    assert glob < gtol and worst < 5 * gtol, (worst, wk, glob)
-    assert rel(xc.grad, x.grad) < gtol * 2
+    mine = grads_of(s.dis)
+    mine["__x"] = xc.grad.cpu()
+    assert_grads("discriminator", mine, g32, gq, mode)
 
 
 @pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 2e-3), ("bf16", 1e-4, 2e-3)])

@@ -106,6 +106,46 @@ def _worker(rank, world, port, ngpu, q):
             dist.broadcast(ref, src=0)
             assert torch.equal(flat, ref), phase
             res[phase] = (worst, glob, wu)
+        # ---- a second step with the same attention status runs the BUCKETED schedule learned in the first one: early
+        # buckets are reduced from inside backward, the rest at the end.  A range that missed its all-reduce would be
+        # off by the other rank's gradient (~70 % per tensor); the trajectories themselves have separated by ~1e-2.
+        sync = s._dp_sync
+        for phase in ("dis", "gen"):
+            c0 = sync.collectives
+            torch.manual_seed(300 * (rank + 1) + (0 if phase == "dis" else 1))
+            if phase == "dis":
+                eps["dis1"] = torch.randn(1, 8, B, 8)
+                s.dis_update(*args)
+                D = orc._leaf(orc.D)
+                with torch.no_grad():
+                    x = batch["x_real"]
+                    content, mus, _ = O.encode(orc.G, x)
+                    st1 = O.gmm_sample(batch["c_trg"], eps["dis1"], 0.5)
+                    mt, _ = O.text_encoder(orc.G, torch.cat(mus, 1), batch["txt"], batch["txt_lens"])
+                    f0, a0 = O.decode(orc.G, content, torch.cat(mt, 1))
+                    f1, a1 = O.decode(orc.G, content, st1)
+                    f0, f1 = O.blend(f0, a0, x, True), O.blend(f1, a1, x, True)
+                (O.dis_loss(D, f0, x, batch["label_src"]) + O.dis_loss(D, f1, x, batch["label_src"])).backward()
+                g_local, state, params, net = {k: v.grad for k, v in D.items()}, orc.d_state, orc.D, s.dis
+                want = 2 + 3                      # two early buckets + the pieces in front of, between and behind them
+            else:
+                eps["gen1"], eps["gen2"] = torch.randn(1, 8, B, 8), torch.randn(1, 8, B, 8)
+                s.gen_update(*args)
+                G = orc._leaf(orc.G)
+                O.gen_phase_losses(G, orc.D, batch, eps["gen1"], eps["gen2"], True, orc.ds_w)["loss_gen_total"].backward()
+                g_local, state, params, net = {k: v.grad for k, v in G.items()}, orc.g_state, orc.G, s.gen
+                want = 1 + 2                      # the decoder bucket + encoders in front, text encoder / MLP behind
+            assert sync.collectives - c0 == want, (phase, sync.collectives - c0, want)
+            mine = {k: (g / world if g is not None else None) for k, g in grads_of(net).items()}
+            g_avg = averaged(g_local)
+            worst, wk, glob = compare_grads(mine, g_avg)
+            assert glob < 5e-2 and worst < 0.3, ("bucketed", phase, worst, wk, glob)
+            O.adam_step(params, g_avg, state, orc.lr)
+            flat = net.flat.data.clone()
+            ref = flat.clone()
+            dist.broadcast(ref, src=0)
+            assert torch.equal(flat, ref), phase
+            res["bucketed_" + phase] = (worst, glob)
         q.put((rank, "ok", res, backend))
         dist.destroy_process_group()
     except Exception as e:  # noqa: BLE001

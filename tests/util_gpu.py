@@ -116,3 +116,21 @@ def top_errs(mine, ref, n=6):
     """The n worst tensors as 'key:err' strings (diagnostics printed by the parity tests)."""
     e = sorted(per_tensor_errs(mine, ref).items(), key=lambda kv: -kv[1])[:n]
     return ", ".join("%s:%.2e" % kv for kv in e)
+
+
+def assert_grads(tag, mine, ref32, refq, mode, glob_fp32=2e-3, worst_fp32=2e-2):
+    """Gradient check shared by the parity tests.  fp32 validation mode: absolute bounds (global / worst tensor)
+    against the fp32 oracle.  bf16: against the fp32 oracle, bounded per tensor and globally by 1.5 x the deviation of the
+    oracle's own bf16-storage-rounding run (`refq`), see tests/test_step_gpu.py."""
+    worst, wk, glob = compare_grads(mine, ref32)
+    if mode == "fp32":
+        print("%s [fp32]: grads vs fp32 oracle worst %.3e (%s) global %.3e" % (tag, worst, wk, glob))
+        assert glob < glob_fp32 and worst < worst_fp32, (tag, worst, wk, glob)
+        return
+    iworst, ik, iglob = compare_grads(refq, ref32)
+    print("%s [bf16]: grads vs fp32 oracle worst %.3e (%s) global %.3e | rounding oracle vs fp32 worst %.3e (%s) "
+          "global %.3e" % (tag, worst, wk, glob, iworst, ik, iglob))
+    assert glob < 1.5 * iglob + 1e-3, (tag, glob, iglob)
+    inh = per_tensor_errs(refq, ref32)
+    for k, e in per_tensor_errs(mine, ref32).items():
+        assert e < 1.5 * inh.get(k, 0.0) + 2e-2, (tag, k, e, inh.get(k))
