@@ -32,13 +32,18 @@ def build(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "dwc_b200.h"))
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("DWC_EXPERIMENTAL", "0") not in ("", "0"):        # parked kernels, see csrc/experimental/README.md
+        srcs += sorted(os.path.join("experimental", f) for f in os.listdir(os.path.join(CSRC, "experimental"))
+                       if f.endswith(".cu"))
+        flags.append("-DDWC_EXPERIMENTAL")
     nv = _nvcc()
 
     def compile_one(f):
         src = os.path.join(CSRC, f)
-        obj = os.path.join(OBJ, f[:-3] + ".o")
+        obj = os.path.join(OBJ, os.path.basename(f)[:-3] + ".o")
         if force or _stale(obj, [src] + headers):
-            r = subprocess.run([nv] + NVCC_FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
+            r = subprocess.run([nv] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
             with open(obj + ".log", "w") as lf:
                 lf.write(r.stdout + r.stderr)
             if r.returncode != 0:
@@ -50,7 +55,8 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     if force or _stale(LIB, objs):
-        r = subprocess.run([nv, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"],
+        r = subprocess.run([nv, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs +
+                           ["-lcudart_static", "-lpthread", "-ldl", "-lrt"],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -193,10 +193,19 @@ extern "C" int64_t dwc_sgemm_workspace_bytes(int m, int n, int k) {
   return s > 1 ? (int64_t)s * m * n * sizeof(float) : 0;
 }
 
+static int g_tf32 = 0;
+extern "C" void dwc_set_tf32(int on) { g_tf32 = on; }
+extern "C" int dwc_get_tf32(void) { return g_tf32; }
+
 extern "C" int dwc_sgemm_ws(int m, int n, int k, float alpha, const void* a, int a_dtype, int64_t a_sm, int64_t a_sk,
                             const float* b, int64_t b_sk, int64_t b_sn, float beta, float* c, int64_t c_sm, int64_t c_sn,
                             const float* bias, int act, float* workspace, int64_t workspace_bytes, dwc_stream_t stream) {
   DWC_CHECK(m > 0 && n > 0 && k > 0, "dwc_sgemm: empty problem (%d,%d,%d)", m, n, k);
+  // bf16 product mode: large fp32 GEMMs run on the tensor cores (tcgen05 kind::tf32, dense_tc.cu)
+  if (g_tf32 && a_dtype == DWC_F32 && (long long)m * n * k >= (1ll << 22) && act <= 1 &&
+      dwc_gemm_tf32_ok(m, n, k, a, a_sm, a_sk, b, b_sk, b_sn, c, c_sm, c_sn))
+    return dwc_gemm_tf32(m, n, k, alpha, reinterpret_cast<const float*>(a), a_sm, a_sk, b, b_sk, b_sn, beta, c, c_sm, bias,
+                         act, stream);
   cudaStream_t st0 = as_stream(stream);
   if (m >= 192 && n >= 192 && cdiv(m, 128) * cdiv(n, 128) >= dwc_num_sms() / 2) {
     dim3 g128(cdiv(m, 128), cdiv(n, 128));

@@ -10,7 +10,7 @@
 //             empty[s] and tmem_full live in both CTAs and are signalled by multicast tcgen05.commit;
 //  roles    : warp 0 TMA producer (both CTAs), warp 1 MMA issuer (leader only) + TMEM alloc/dealloc (both),
 //             warps 2-5 epilogue (both: TMEM lanes 0..127 of each CTA hold its own tile).
-#include "gconv.cuh"
+#include "../gconv.cuh"
 #include <stdlib.h>
 #include <string.h>
 

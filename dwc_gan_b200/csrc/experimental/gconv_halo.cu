@@ -12,7 +12,7 @@
 //              MT = 2 the weight bytes per MMA cycle halve, so the ring covers the TMA latency;
 //  roles     : warp 0 weight producer, warp 1 MMA issuer, warp 2 lane 0 input producer, warps 2-5 epilogue
 //              (tcgen05.ld -> +bias -> bf16/fp32 store).
-#include "gconv.cuh"
+#include "../gconv.cuh"
 
 namespace {
 

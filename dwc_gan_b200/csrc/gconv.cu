@@ -695,6 +695,7 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
   if (g->backend == DWC_TC || halo) {
     DWC_CHECK(g->dtype == DWC_BF16, "dwc_gconv: tcgen05 backend needs bf16 operands");
     DWC_CHECK(d.C % TC_BK == 0, "dwc_gconv: tcgen05 backend needs C %% 64 == 0 (C=%d)", d.C);
+#ifdef DWC_EXPERIMENTAL
     if (halo) {
       int ks = 1;
       while (ks * ks < g->ntaps) ++ks;
@@ -710,6 +711,10 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
       const int rc = dwc_launch_gconv_tc2(g, d, st);
       if (rc >= 0) return rc;
     }
+#else
+    DWC_CHECK(!halo && getenv("DWC_CG2") == nullptr,
+              "dwc_gconv: the halo-tile / CTA-pair kernels are parked (csrc/experimental); build with DWC_EXPERIMENTAL=1");
+#endif
     {
       static int persist = -1;
       if (persist < 0) {

@@ -60,6 +60,10 @@ class Runtime:
             self.dtype, self.use_tc = torch.float32, False
         else:
             raise ValueError("mode must be bf16, bf16_simt or fp32")
+        # product mode: the large fp32 GEMMs of the text encoder run as tf32 tensor-core GEMMs (csrc/dense_tc.cu);
+        # the validation modes keep exact fp32
+        if os.path.exists(L.LIB_PATH):
+            L.lib().dwc_set_tf32(1 if (mode == "bf16" and os.environ.get("DWC_TF32", "1") != "0") else 0)
 
     def tc_ok(self, *channels):
         return self.use_tc and self.dtype == torch.bfloat16 and all(c % 64 == 0 for c in channels)

@@ -311,8 +311,10 @@ class Solver(nn.Module):
         return ent["out"].clone()
 
     def _forward_impl(self, x_real, txt_src2trg, txt_lens):
-        content, mu, _ = self.gen.encode_fused(x_real)
-        mt, _ = self.gen.encode_txt(mu, txt_src2trg, txt_lens)
+        # the text encoder only needs the style code: it runs on its own stream next to the content encoder
+        tbox = {}
+        content, mu, _ = self.gen.encode_fused(x_real, after_style=self._fork_txt(tbox, txt_src2trg, txt_lens))
+        mt, _ = self._join_txt(tbox)
         img, att = self.gen.decode(content, torch.cat(mt, dim=1))
         return self._blend(img, att, x_real)
 

@@ -244,6 +244,19 @@ int dwc_relu_gap_bwd(const float* dout, const dwc_hbuf_t* y, const dwc_hbuf_t* d
 int dwc_sgemm(int m, int n, int k, float alpha, const void* a, int a_dtype, int64_t a_sm, int64_t a_sk,
               const float* b, int64_t b_sk, int64_t b_sn, float beta, float* c, int64_t c_sm, int64_t c_sn,
               const float* bias, int act, dwc_stream_t stream);
+
+/* The same GEMM on the tensor cores: tcgen05.mma kind::tf32 with fp32 operands fetched by TMA (no conversion pass),
+ * fp32 accumulation (csrc/dense_tc.cu).  A K-major (a_sk == 1) or M-major (a_sm == 1), B K-major (b_sk == 1) or
+ * N-major (b_sn == 1), C row-major; leading strides multiples of 4 elements, bases 16-byte aligned
+ * (dwc_gemm_tf32_ok).  dwc_set_tf32(1) makes dwc_sgemm / dwc_sgemm_ws route eligible problems here (bf16 product
+ * mode); with 0 (default, fp32 validation mode) they stay exact fp32. */
+int dwc_gemm_tf32_ok(int m, int n, int k, const void* a, int64_t a_sm, int64_t a_sk, const void* b, int64_t b_sk,
+                     int64_t b_sn, const void* c, int64_t c_sm, int64_t c_sn);
+int dwc_gemm_tf32(int m, int n, int k, float alpha, const float* a, int64_t a_sm, int64_t a_sk, const float* b,
+                  int64_t b_sk, int64_t b_sn, float beta, float* c, int64_t c_sm, const float* bias, int act,
+                  dwc_stream_t stream);
+void dwc_set_tf32(int on);
+int dwc_get_tf32(void);
 /* Same with a caller-provided float workspace of dwc_sgemm_workspace_bytes(m, n, k) bytes: problems with few
  * output tiles and a long K (head layers at small batch) are then split along K over many CTAs and summed in a
  * fixed order (deterministic). */

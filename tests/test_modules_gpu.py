@@ -125,7 +125,10 @@ def test_discriminator(mode, tol):
     assert_grads("discriminator", mine, g32, gq, mode)
 
 
-@pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 2e-3), ("bf16", 1e-4, 2e-3)])
+# fp32 validation mode: exact fp32 GEMMs.  bf16 product mode: the large GEMMs (LSTM input projections over all packed
+# tokens and their gradients) run as tf32 tensor-core GEMMs - 10 mantissa bits per operand, 7.7e-4 relative per GEMM
+# (tests/test_dense_gpu.py); the recurrence, the heads and everything element-wise stay fp32.
+@pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 2e-3), ("bf16", 1e-3, 1e-2)])
 def test_text_encoder(mode, tol, gtol):
     s, _ = build_solver(mode)
     G = leaf(O.trainable(cpu_state(s.gen)))

@@ -118,6 +118,50 @@ def bench_geom(g, n, peaks):
     return rows
 
 
+# first layers (3 input channels) through the 8-pixel x 8-channel row-im2col buffers: id, cout, k, stride, pad, H=W, pool
+FIRST = [("G1", 64, 7, 1, 3, 128, 1), ("D1", 64, 4, 2, 1, 128, 1), ("D1s", 64, 4, 2, 1, 128, 2)]
+
+
+def bench_first(g, n, peaks):
+    """3 -> 64 first convolution: forward and weight gradient on the tensor cores over the row-im2col operand, plus the
+    kernel that builds that operand from the fp32 NCHW image (HBM-bound: the layer's bound is AI x HBM)."""
+    from dwc_gan_b200 import ops
+    import ctypes as C
+    name, cout, k, s, p, hw, pool = g
+    bt = torch.bfloat16
+    hi = hw // pool
+    hp = hi + 2 * p
+    ho = (hp - k) // s + 1
+    hy = k - 1 if s == 1 else 1
+    nbuf = 6
+    imgs = [torch.rand(n, 3, hw, hw, device="cuda") * 2 - 1 for _ in range(nbuf)]
+    rows = [torch.empty(P.rows_shape(n, hp, ho, s), dtype=bt, device="cuda") for _ in range(nbuf)]
+    ys = [HB(torch.randn(HB.shape_of(n, ho, ho, cout, hy, 0), device="cuda").to(bt), n, ho, ho, cout, hy, 0) for _ in range(nbuf)]
+    w = torch.randn(cout, k, k, 3, device="cuda") * 0.1
+    wr = torch.empty(cout, k * 64, dtype=bt, device="cuda")
+    L.check(L.lib().dwc_pack_weights(L.ptr(w), cout, k, k, 3, 3, L.ptr(wr), L.BF16, cout, L.stream()), "pack")
+    bias = torch.zeros(cout, device="cuda")
+    dw, db = torch.zeros(cout, k, k, 3, device="cuda"), torch.zeros(cout, device="cuda")
+
+    def f_rows(i):
+        L.check(L.lib().dwc_image_rows_fwd(L.ptr(imgs[i]), n, 3, hw, hw, pool, p, s, s, ho, L.ptr(rows[i]), L.BF16, L.stream()))
+    for i in range(nbuf):
+        f_rows(i)
+    fw = [P.plan_first_conv_fwd(rows[i], n, hp, ho, ho, k, s, wr, cout, bias, ys[i], L.TC) for i in range(nbuf)]
+    wg = [P.plan_first_conv_wgrad(ys[i], rows[i], n, hp, ho, k, s, 3, dw, db, L.TC) for i in range(nbuf)]
+    res = {"rows (image -> im2col operand)": timeit([(lambda i=i: f_rows(i)) for i in range(nbuf)]),
+           "fprop": timeit([pl.launch for pl in fw]),
+           "wgrad": timeit([(lambda pl=pl: pl.launch(workspace)) for pl in wg])}
+    flops = 2.0 * n * ho * ho * cout * k * k * 3
+    in_bytes, out_bytes = n * 3 * hw * hw * 4, n * ho * ho * cout * 2
+    bound = min(peaks["tflops"] * 1e12, flops / (in_bytes + out_bytes) * peaks["hbm"] * 1e9)
+    out = []
+    for op, t in res.items():
+        out.append("| %s | %s | 3->%d k%d/s%d @%d | %.1f | %.1f | %.1f | %.3f | %.3f |" % (
+            name, op, cout, k, s, hi, t * 1e6, flops / t / 1e12, bound / 1e12, flops / t / bound, flops / t / 1e12 / peaks["tflops"]))
+    return out
+
+
 def bench_post(n, c, hw, kind, peaks, halo_out=1, halo_dy=2):
     """norm site through the C ABI: forward = stats + finalize + fused normalise/act/reflect-pad pass; backward =
     reduce + finalize + apply.  Each kernel is timed on its own (graph replay over rotating buffers)."""
@@ -206,6 +250,12 @@ def main():
                 r["layer"], r["op"], r["cin"], r["cout"], r["k"], r["stride"], r["hw_in"], r["us"], r["tflops"],
                 r["bound_tflops"], r["frac_of_bound"], r["frac_of_tensor_peak"]))
             print(lines[-1], flush=True)
+    for g in FIRST:
+        if args.only and g[0] not in args.only.split(","):
+            continue
+        for ln in bench_first(g, args.batch, peaks):
+            lines.append(ln)
+            print(ln, flush=True)
     lines += ["", "| norm site | op | us | GB/s (algorithmic) | frac of HBM peak |", "|---|---|---|---|---|"]
     if not args.only or args.only == "NONE":
         for (c, hw, kind) in ((64, 128, 1), (128, 64, 1), (256, 32, 1), (256, 32, 2), (128, 64, 3), (64, 128, 3)):

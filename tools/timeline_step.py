@@ -1,21 +1,30 @@
 """Kernel timeline of one replayed training step through torch.profiler (CUPTI): in-situ kernel durations (warm
 caches, real overlap between the main and the side stream), idle gaps, per-kernel totals.
-  python tools/timeline_step.py [batch] > profiles/xxx.txt"""
+  python tools/timeline_step.py [batch [config]] > profiles/xxx.txt        (config: train128 | train256 | infer64)"""
 import os, sys, json, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from torch.profiler import profile, ProfilerActivity
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+conf = bench.CONFIGS[sys.argv[2] if len(sys.argv) > 2 else "train128"]
+B = int(sys.argv[1]) if len(sys.argv) > 1 and int(sys.argv[1]) > 0 else conf["batch"]
 dev = torch.device("cuda", 0)
-s, cfg = bench.build_solver(dev, "bf16")
-b = {k: v.to(dev) for k, v in bench.make_host_batch(B, 128, 0).items()}
+s, cfg = bench.build_solver(dev, "bf16", conf["overrides"])
+b = {k: v.to(dev) for k, v in bench.make_host_batch(B, conf["size"], 0).items()}
+if conf["train"]:
+    step = lambda it: bench.one_step(s, cfg, b, it)
+else:
+    s.eval()
+
+    def step(it):
+        with torch.no_grad():
+            return s(b["x_real"], b["txt"], b["txt_lens"])
 for it in range(6):
-    bench.one_step(s, cfg, b, it)
+    step(it)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    bench.one_step(s, cfg, b, 6)
+    step(6)
     torch.cuda.synchronize()
 path = "/tmp/trace.json"
 prof.export_chrome_trace(path)
