@@ -23,6 +23,9 @@ struct WgradDev {
   int ngroup;          // taps per item on the N operand (1 = classic); > 1: N boxes are the SAME channels of `ngroup`
                        // taps, read at pixel - tap (the M operand is untapped and the tiles walk ITS pixel grid)
   int ntaps_total;     // real tap count (items cover ceil(ntaps_total / ngroup) groups)
+  int grp_plus;        // grouped mode, which side carries the taps: 0 = the N operand is read at pixel - tap (operands
+                       // swapped, M = untapped padded input); 1 = the N operand IS the tapped input, read at pixel + tap
+                       // (incl. its parity plane), M = untapped dY and the tiles walk dY's grid
   int taps[DWC_MAX_TAPS][3];
 };
 
@@ -201,9 +204,12 @@ __global__ void __launch_bounds__(WG_THREADS)
           for (int j = 0; j < BN / 64; ++j) {
             const int tj = t * p.ngroup + j / bpt;
             // taps beyond the real count read far outside the tensor (zero fill): their accumulator columns are unused
-            const int sx = tj < p.ntaps_total ? x0 - p.taps[tj][0] : -(1 << 20);
-            const int sy = tj < p.ntaps_total ? y0 - p.taps[tj][1] : 0;
-            tma_load_5d(s + Cfg::M_BYTES + j * WG_BOX_BYTES, &tmN, &full_bar[stage], (j % bpt) * 64, sx, sy, 0, n0);
+            const bool real = tj < p.ntaps_total;
+            const int sgn = p.grp_plus ? 1 : -1;
+            const int sx = real ? x0 + sgn * p.taps[tj][0] : -(1 << 20);
+            const int sy = real ? y0 + sgn * p.taps[tj][1] : 0;
+            const int sz = (real && p.grp_plus) ? p.taps[tj][2] : 0;
+            tma_load_5d(s + Cfg::M_BYTES + j * WG_BOX_BYTES, &tmN, &full_bar[stage], (j % bpt) * 64, sx, sy, sz, n0);
           }
         } else {
 #pragma unroll
@@ -428,6 +434,7 @@ struct WgPlan {
   bool swap;
   int cm, cn, bn, mr, splits, tiles_per_split, ntiles, items;
   int ngroup;                       // > 1: tap-grouped N operand (see WgradDev::ngroup)
+  int grp_plus;                     // see WgradDev::grp_plus
   int box[3], tiles[3];             // pixel boxes / tile counts actually used (grouped mode re-tiles the M grid)
 };
 
@@ -439,7 +446,10 @@ static int wg_plan(const dwc_wgrad_t* g, WgPlan* pl) {
     // accumulator rows need a multiple of 128 channels
     DWC_CHECK(g->ca % 64 == 0 && g->cb % 64 == 0, "dwc_wgrad: tcgen05 needs channel counts (%d,%d) %% 64 == 0", g->ca,
               g->cb);
-    pl->swap = (g->ca % 128 != 0) && (g->cb % 128 == 0);
+    // accumulator rows (M) come from one operand's channels, columns (N) from the other's: rows need a multiple of 128,
+    // and the widest tile (N = 256) has the best operand reuse - swap when that puts 256 channels on N
+    pl->swap = ((g->ca % 128 != 0) && (g->cb % 128 == 0)) ||
+               (g->ca % 256 == 0 && g->cb % 128 == 0 && g->cb % 256 != 0 && g->remap_axis == 0);
     pl->cm = pl->swap ? g->cb : g->ca;
     pl->cn = pl->swap ? g->ca : g->cb;
     pl->mr = pl->cm % 128 == 0 ? 128 : 64;
@@ -457,6 +467,16 @@ static int wg_plan(const dwc_wgrad_t* g, WgPlan* pl) {
     bool plain = g->remap_axis == 0 && g->ntaps >= 4;
     for (int t = 0; t < g->ntaps && plain; ++t)
       plain = g->taps[t * 3 + 2] == 0 && g->taps[t * 3] >= 0 && g->taps[t * 3 + 1] >= 0;
+    pl->grp_plus = 0;
+    if (grp_on && !pl->swap && g->remap_axis == 0 && pl->mr == 128 && (pl->cn == 64 || pl->cn == 128) &&
+        g->ntaps >= 256 / pl->cn) {
+      // N operand = the tapped input with few channels (64 -> 128, 64 -> 64 layers): 256 / cn taps side by side in N,
+      // each box read at its own tap offset / parity plane; M = dY untapped, tiles over dY's grid as in the classic mode
+      pl->ngroup = 256 / pl->cn;
+      pl->bn = 256;
+      pl->grp_plus = 1;
+      pl->items = (pl->cm / 128) * cdiv(g->ntaps, pl->ngroup);
+    } else
     if (grp_on && pl->swap && plain && pl->mr == 128 && (pl->cn == 64 || pl->cn == 128) && g->b_dim[3] == 1) {
       pl->ngroup = 256 / pl->cn;
       pl->bn = 256;
@@ -553,6 +573,7 @@ extern "C" int dwc_wgrad(const dwc_wgrad_t* g, dwc_stream_t stream) {
   d.ntiles = pl.ntiles; d.splits = pl.splits; d.tiles_per_split = pl.tiles_per_split;
   d.ntaps = pl.ngroup > 1 ? cdiv(g->ntaps, pl.ngroup) : g->ntaps;
   d.ngroup = pl.ngroup;
+  d.grp_plus = pl.grp_plus;
   d.ntaps_total = g->ntaps;
   d.ws = g->workspace;
   for (int t = 0; t < g->ntaps; ++t)
