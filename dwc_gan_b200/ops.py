@@ -220,6 +220,13 @@ class ConvFn(torch.autograd.Function):
         dy = HB(dy_t.contiguous(), n, ho, wo, cout, hy, 0)
         xp = HB(xp_t, n, h, w, c, halo, layout)
         dxp_t = None
+        # Output channels that are not a multiple of 64 (64 -> 32 stage of the 256x256 variant): the gradient is
+        # zero-extended to 64 channels once, so that both gradients run on the tcgen05 kernels (zero weights / zero
+        # gradient rows for the padding), instead of falling back to the CUDA-core kernels
+        padc = RT.tc_ok(c) and not RT.tc_ok(cout) and cout >= 16 and s == 1 and layer.extra_cols is None
+        if padc:
+            cp = _pad64(cout)
+            dy = _pad_channels(dy, cp)
         if ctx.needs_input_grad[0]:
             # ResBlock: the skip-connection gradient (PostFn.backward of the block's second conv left it in the box,
             # same geometry as this conv's input, zero halo) is the buffer the data gradient is added to, instead of
@@ -227,8 +234,15 @@ class ConvFn(torch.autograd.Function):
             skip = ctx.skip_box.pop("dres", None) if ctx.skip_box is not None else None
             dxp = skip if skip is not None else HB.empty(n, h, w, c, halo, layout, dy_t.dtype, dy_t.device)
             assert (dxp.n, dxp.h, dxp.w, dxp.c, dxp.halo, dxp.layout) == (n, h, w, c, halo, layout)
-            tc = RT.tc_ok(c, cout)
-            wd, rows_p = layer.packed_dgrad(dy_t.dtype)
+            tc = RT.tc_ok(c, cout) or padc
+            if padc:
+                _, wm, _ = layer._raw_weight()
+                wpad = torch.zeros(cp, k * k * c, dtype=torch.float32, device=dy_t.device)
+                wpad[:cout] = wm.view(cout, -1)
+                wd, rows_p = _pack(wpad, cp, k, c, 1, c, (c, k * k * cp), dy_t.dtype), c
+                RT.launches += 1
+            else:
+                wd, rows_p = layer.packed_dgrad(dy_t.dtype)
             for q in P.plan_conv_dgrad(dy, wd, dxp, k, s, L.TC if tc else L.SIMT, cin_padded=rows_p,
                                        accumulate=skip is not None):
                 RT.launches += 1
@@ -238,12 +252,44 @@ class ConvFn(torch.autograd.Function):
             gw, gb = layer.grad_buffers()
             if not layer.bias_grad_needed():
                 gb = None          # bias in front of InstanceNorm / AdaIN: its gradient is exactly zero
-            tc = RT.tc_ok(c, cout)
-            wp = P.plan_conv_wgrad(dy, xp, gw, gb, k, s, L.TC if tc else L.SIMT, accumulate=True)
+            tc = RT.tc_ok(c, cout) or padc
             RT.launches += 3
-            side_launch(lambda: wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device)), (dy.t, xp_t),
-                        name=layer._names()[1])
+            if padc:
+                def run(dy=dy):
+                    gwp = torch.empty(cp, k * k * c, dtype=torch.float32, device=dy_t.device)
+                    gbp = torch.empty(cp, dtype=torch.float32, device=dy_t.device) if gb is not None else None
+                    P.plan_conv_wgrad(dy, xp, gwp, gbp, k, s, L.TC, accumulate=False).launch(
+                        lambda nbytes: RT.workspace(nbytes, dy_t.device))
+                    gw.view(cout, -1).add_(gwp[:cout])
+                    if gb is not None:
+                        gb.add_(gbp[:cout])
+                side_launch(run, (dy.t, xp_t), name=layer._names()[1])
+            else:
+                wp = P.plan_conv_wgrad(dy, xp, gw, gb, k, s, L.TC if tc else L.SIMT, accumulate=True)
+                side_launch(lambda: wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device)), (dy.t, xp_t),
+                            name=layer._names()[1])
         return dxp_t, None, None, None, None
+
+
+def _pad_channels(hb: HB, c_new: int) -> HB:
+    """Zero-extend (or cut back) the channel dimension of a haloed buffer: a plain copy that lets layers whose channel
+    count is not a multiple of 64 (the 32-channel last decoder stage of the 256x256 variant) run on the
+    tcgen05 kernels, which stage 64-channel (128-byte) slabs."""
+    if c_new > hb.c:
+        t = torch.nn.functional.pad(hb.t, (0, c_new - hb.c))
+    else:
+        t = hb.t[..., :c_new].contiguous()
+    return HB(t, hb.n, hb.h, hb.w, c_new, hb.halo, hb.layout)
+
+
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
+def _pack(w, cout, k, cin, mode, rows, out_shape, dtype):
+    out = torch.empty(out_shape, dtype=dtype, device=w.device)
+    _call("dwc_pack_weights", L.ptr(w), cout, k, k, cin, mode, L.ptr(out), L.dt(out), rows, L.stream())
+    return out
 
 
 def _attach_stats(pl, layer, n, cout, device):
@@ -393,8 +439,15 @@ class HeadsConvFn(torch.autograd.Function):
         k, cout = layer.k, layer.total_cout()
         n, h, w = xp.n, xp.h, xp.w
         y = HB.empty(n, h, w, cout, 0, 0, xp_t.dtype, xp_t.device)
+        cin_real = xp.c
+        if RT.use_tc and xp_t.dtype == torch.bfloat16 and xp.c % 64 != 0 and xp.c % 8 == 0 and xp.layout == 0:
+            # 32 input channels (256x256 variant): zero-extend input and weights to 64 channels, see _pad_channels
+            xp = _pad_channels(HB(xp_t, n, h, w, xp.c, xp.halo, 0), _pad64(xp.c))
+            xp_t = xp.t
         if conv7_few_ok(xp_t.dtype, k, 1, xp.c, cout) and xp.layout == 0 and xp.halo == 3 and RT.conv7_which != "d":
-            _, wm, bm = layer._raw_weight()                    # fp32 master [cout][7][7][64]
+            _, wm, bm = layer._raw_weight()                    # fp32 master [cout][7][7][cin]
+            if cin_real != xp.c:
+                wm = torch.nn.functional.pad(wm.view(cout * k * k, cin_real), (0, xp.c - cin_real)).reshape(-1)
             conv7_few(xp_t, n, xp.hp, xp.wp, wm, 0, 49 * 64, 7 * 64, 64, 1, bm, cout, y.t, (cout, w * cout, h * w * cout))
         else:
             wf, rows_p = layer.packed_fwd(xp_t.dtype)
@@ -406,7 +459,7 @@ class HeadsConvFn(torch.autograd.Function):
         att = torch.empty(n, 1, h, w, dtype=torch.float32, device=xp_t.device)
         ys = y.struct()
         _call("dwc_heads_fwd", C.byref(ys), L.ptr(img), L.ptr(att), L.stream())
-        ctx.layer, ctx.meta, ctx.on_att_grad = layer, (n, h, w, xp.c, xp.halo), on_att_grad
+        ctx.layer, ctx.meta, ctx.on_att_grad = layer, (n, h, w, xp.c, xp.halo, cin_real), on_att_grad
         ctx.save_for_backward(xp_t, img, att)
         return img, att
 
@@ -414,7 +467,7 @@ class HeadsConvFn(torch.autograd.Function):
     def backward(ctx, dimg, datt):
         layer = ctx.layer
         xp_t, img, att = ctx.saved_tensors
-        n, h, w, cin, halo_in = ctx.meta
+        n, h, w, cin, halo_in, cin_real = ctx.meta              # cin: channels of the (possibly zero-extended) saved input
         k, cout = layer.k, layer.total_cout()
         dev, dtype = xp_t.device, xp_t.dtype
         if datt is not None and ctx.on_att_grad is not None:
@@ -435,13 +488,24 @@ class HeadsConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dxp = HB.empty(n, h, w, cin, halo_in, 0, dtype, dev)
             RT.launches += 1
-            P.plan_heads_dgrad(rows_d, n, hh, wh, layer.packed_rows(dtype, 4), dxp, k, be).launch()
-            dxp_t = dxp.t
+            if cin_real != cin:                               # zero rows for the padding channels
+                _, wm, _ = layer._raw_weight()
+                wr = _pack(wm, cout, k, cin_real, 4, cin, (cin, k * 64), dtype)
+            else:
+                wr = layer.packed_rows(dtype, 4)
+            P.plan_heads_dgrad(rows_d, n, hh, wh, wr, dxp, k, be).launch()
+            dxp_t = dxp.t if cin_real == cin else _pad_channels(dxp, cin_real).t
         if ctx.needs_input_grad[1]:
             gw, gb = layer.grad_buffers()
             RT.launches += 2
-            P.plan_heads_wgrad(win, HB(xp_t, n, h, w, cin, halo_in, 0), gw, k, cout, be).launch(
-                lambda nbytes: RT.workspace(nbytes, dev))
+            if cin_real != cin:
+                gwp = torch.zeros(cout * k * k * cin, dtype=torch.float32, device=dev)
+                P.plan_heads_wgrad(win, HB(xp_t, n, h, w, cin, halo_in, 0), gwp, k, cout, be).launch(
+                    lambda nbytes: RT.workspace(nbytes, dev))
+                gw.view(cout * k * k, cin_real).add_(gwp.view(cout * k * k, cin)[:, :cin_real])
+            else:
+                P.plan_heads_wgrad(win, HB(xp_t, n, h, w, cin, halo_in, 0), gw, k, cout, be).launch(
+                    lambda nbytes: RT.workspace(nbytes, dev))
             _call("dwc_colsum", nblk.value, cout, L.ptr(part), cout, 1, L.ptr(gb), 1, L.stream())
         return dxp_t, None, None, None, None
 
