@@ -354,8 +354,10 @@ def main():
     dev = torch.device("cuda", local)
     peaks = load_peaks()
     s, cfg = build_solver(dev, args.mode, conf["overrides"])
-    if world > 1 and conf["train"]:
+    if world > 1 and conf["train"] and os.environ.get("DWC_DP_NOSYNC", "0") == "0":
         parallel.attach(s)                       # inference: N independent replicas, no collective
+        # (DWC_DP_NOSYNC=1 is a diagnostic: N independent training replicas, to separate the cost of the gradient
+        #  exchange from the spread between the GPUs of a box; not a valid data-parallel run)
     host = make_host_batch(B, conf["size"], seed=rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
@@ -421,7 +423,11 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     assert torch.isfinite(result).all()
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [round(float(x[0]) / args.steps, 3) for x in allt]     # diagnostics: device time per step of every rank
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
     if rank != 0:
@@ -439,6 +445,8 @@ def main():
             "data": "synthetic", "config": our_config_dict(args.config, conf, B, world, args.mode),
             "e2e": {"value": round(e2e, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof}
+    if per_rank is not None:
+        line["ms_per_step_by_rank"] = per_rank
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_leg(conf)
     print(json.dumps(line), flush=True)

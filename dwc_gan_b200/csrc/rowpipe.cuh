@@ -319,8 +319,17 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
         if (row >= 1 && row <= halo) Ys[ny++] = halo - row;
         if (row >= H - 1 - halo && row <= H - 2) Ys[ny++] = halo + 2 * (H - 1) - row;
       }
-      for (int q = tid; q < nchunks; q += 256) {
-        const int px = x0 + q / cvs;
+      // Output addressing hoisted out of the chunk loop: per destination row Y the element offset of padded column
+      // X is ybase[Y][X & pmask] + (X >> pshift) * C (plain layout: pmask = pshift = 0; parity planes: 1 / 1)
+      const int pmask = p.o1.layout ? 1 : 0;
+      long long ybase[3][2];
+      for (int a = 0; a < ny; ++a) {
+        ybase[a][0] = p.o1.off_padded(n, Ys[a], 0) + c0;
+        ybase[a][1] = p.o1.layout ? p.o1.off_padded(n, Ys[a], 1) + c0 : ybase[a][0];
+      }
+      const int pstep = 256 / cvs;                     // pixels between two chunks of this thread (cvs divides 256)
+      int px = x0 + tid / cvs;
+      for (int q = tid; q < nchunks; q += 256, px += pstep) {
         float v[8];
         rp_unpack8(*reinterpret_cast<const uint4*>(sy + (size_t)q * 16), v);
 #pragma unroll
@@ -338,15 +347,18 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
           if (px >= 1 && px <= halo) Xs[nx++] = halo - px;
           if (px >= W - 1 - halo && px <= W - 2) Xs[nx++] = halo + 2 * (W - 1) - px;
         }
-        for (int a = 0; a < ny; ++a)
-          for (int b = 0; b < nx; ++b)
-            *reinterpret_cast<uint4*>(ob + p.o1.off_padded(n, Ys[a], Xs[b]) + c0) = o;
+        for (int b = 0; b < nx; ++b) {
+          const int X = Xs[b];
+          const long long xo = (long long)(X >> pmask) * C;
+          for (int a = 0; a < ny; ++a) *reinterpret_cast<uint4*>(ob + ybase[a][X & pmask] + xo) = o;
+        }
       }
     } else {
-      bf16* dyb = reinterpret_cast<bf16*>(p.o1.ptr);
-      bf16* drb = reinterpret_cast<bf16*>(p.o2.ptr);
-      for (int q = tid; q < nchunks; q += 256) {
-        const int px = x0 + q / cvs;
+      bf16* dyb = reinterpret_cast<bf16*>(p.o1.ptr) + p.o1.off(n, row, x0) + c0;      // plain layouts: + pixel * C
+      bf16* drb = p.has_o2 ? reinterpret_cast<bf16*>(p.o2.ptr) + p.o2.off(n, row, x0) + c0 : nullptr;
+      const int pstep = 256 / cvs;
+      int pl = tid / cvs;                               // pixel inside the segment
+      for (int q = tid; q < nchunks; q += 256, pl += pstep) {
         float v[8], g[8], o[8];
         const uint4 gu = *reinterpret_cast<const uint4*>(sd + d_off(q));
         rp_unpack8(*reinterpret_cast<const uint4*>(sy + (size_t)q * 16), v);
@@ -356,8 +368,8 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
           const float dz = g[e] * rp_act_grad(sc[e] * v[e] + sh[e], act);
           o[e] = ba[e] * dz + bb[e] * v[e] + bc[e];
         }
-        *reinterpret_cast<uint4*>(dyb + p.o1.off(n, row, px) + c0) = rp_pack8(o);
-        if (p.has_o2) *reinterpret_cast<uint4*>(drb + p.o2.off(n, row, px) + c0) = gu;
+        *reinterpret_cast<uint4*>(dyb + (long long)pl * C) = rp_pack8(o);
+        if (p.has_o2) *reinterpret_cast<uint4*>(drb + (long long)pl * C) = gu;
       }
       if (x0 == 0) {
         rp_zero_halo(p.o1, n, row, cvs, tid);

@@ -60,6 +60,7 @@ class GradSync:
         self.async_stream = async_stream
         self.bytes_reduced = 0
         self.bucket_prefixes = buckets or {}        # {id(net): [(prefix, ...), ...]}
+        self.use_buckets = os.environ.get("DWC_DP_BUCKETS", "1") != "0"
         self.plans = {}                             # (id(net), key) -> {"need": {name: count}, "buckets": [...]}
         self.cur = None
         self.collectives = 0
@@ -136,7 +137,7 @@ class GradSync:
             self._reduce(g)
             # learn the schedule for the next call of this phase
             buckets = []
-            for prefixes in self.bucket_prefixes.get(id(net), []):
+            for prefixes in (self.bucket_prefixes.get(id(net), []) if self.use_buckets else []):
                 r = self._ranges(flat, prefixes)
                 need = {n: c for n, c in cur["counts"].items() if n.startswith(tuple(prefixes))}
                 if r is not None and need:
