@@ -269,10 +269,73 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int K
     out[i] = from_f<T>(pack_elem(w, Cout, KH, KW, Cin, mode, rows_padded, i));
 }
 
-// every packed operand of a network in ONE launch: blockIdx.y = table entry (the table lives in device memory)
+// every packed operand of a network in ONE launch: blockIdx.y = table entry (the table lives in device memory), the
+// blocks of a row stride over the entry's work units.  bf16 outputs take coalesced paths: mode 0 is a cast (8 elements
+// per thread, 16-byte stores); the data-gradient operands (modes 1 / 2) are per-tap [Cout x Cin] -> [Cin x Cout]
+// transposes done through a 32 x 33 shared-memory tile, so that both the fp32 reads (along Cin) and the bf16 writes
+// (along Cout) are contiguous; the small row-im2col modes and fp32 outputs keep the element-wise path.
 __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const dwc_pack_entry_t* __restrict__ table) {
+  __shared__ float tile[32][33];
   const dwc_pack_entry_t e = table[blockIdx.y];
   const float* __restrict__ w = e.w;
+  const int taps = e.kh * e.kw;
+  if (e.out_dtype == DWC_BF16 && e.mode == 0 && (e.total & 7) == 0 && ((long long)taps * e.cin) % 8 == 0) {
+    bf16* out = reinterpret_cast<bf16*>(e.out);
+    const long long valid = (long long)e.cout * taps * e.cin;          // rows beyond cout are zero padding
+    for (long long i = (blockIdx.x * 256LL + threadIdx.x) * 8; i < e.total; i += gridDim.x * 2048LL) {
+      float f[8];
+      if (i < valid) {
+        const float4 a = *reinterpret_cast<const float4*>(w + i), b = *reinterpret_cast<const float4*>(w + i + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+      Vec8<bf16>::store(out + i, f);
+    }
+    return;
+  }
+  if (e.out_dtype == DWC_BF16 && (e.mode == 1 || (e.mode == 2 && e.kh == 4 && e.kw == 4)) && (e.cout & 1) == 0) {
+    bf16* out = reinterpret_cast<bf16*>(e.out);
+    const int rows = e.rows_padded, Cout = e.cout, Cin = e.cin;
+    const int ct = (rows + 31) / 32, ot = (Cout + 31) / 32;              // tiles along ci (incl. padding rows) and co
+    const int units = taps * ct * ot;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;              // 32 x 8 threads
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int t = u / (ct * ot), r = u - t * (ct * ot);
+      const int ci0 = (r / ot) * 32, co0 = (r % ot) * 32;
+      // read w[co][t][ci]: ci contiguous
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int co = co0 + ty + 8 * j, ci = ci0 + tx;
+        tile[ty + 8 * j][tx] = (co < Cout && ci < Cin) ? w[((long long)co * taps + t) * Cin + ci] : 0.f;
+      }
+      __syncthreads();
+      // where tap t of the forward filter lands in the data-gradient operand
+      long long base;
+      long long K;
+      if (e.mode == 1) {
+        K = (long long)taps * Cout;
+        base = (long long)(taps - 1 - t) * Cout;                         // flipped tap
+      } else {
+        const int kh = t >> 2, kw = t & 3;
+        const int py = kh & 1, ip = 1 - (kh >> 1), px = kw & 1, jp = 1 - (kw >> 1);
+        K = 4LL * Cout;
+        base = (long long)(py * 2 + px) * rows * K + (long long)(ip * 2 + jp) * Cout;
+      }
+      // write out[ci][...][co]: co contiguous, two bf16 per thread
+      const int cw = (threadIdx.x & 15) * 2, rw = threadIdx.x >> 4;       // 16 column pairs x 16 rows per pass
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int ci = ci0 + rw + 16 * j, co = co0 + cw;
+        if (ci < rows && co < Cout)
+          *reinterpret_cast<__nv_bfloat162*>(out + base + (long long)ci * K + co) =
+              __floats2bfloat162_rn(tile[cw][rw + 16 * j], tile[cw + 1][rw + 16 * j]);
+      }
+      __syncthreads();
+    }
+    return;
+  }
   if (e.out_dtype == DWC_F32) {
     float* out = reinterpret_cast<float*>(e.out);
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < e.total; i += gridDim.x * 256LL)
@@ -285,7 +348,7 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const dwc_pack_
 }
 extern "C" int dwc_pack_weights_batch(const dwc_pack_entry_t* table_dev, int count, dwc_stream_t stream) {
   DWC_CHECK(table_dev != nullptr && count > 0 && count <= 65535, "dwc_pack_weights_batch: bad table");
-  pack_weights_batch_kernel<<<dim3(48, count), 256, 0, as_stream(stream)>>>(table_dev);
+  pack_weights_batch_kernel<<<dim3(128, count), 256, 0, as_stream(stream)>>>(table_dev);
   DWC_LAUNCH_CHECK();
   return 0;
 }

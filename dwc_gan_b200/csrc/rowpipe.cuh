@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
     const int u = r0 * p.nseg + i;
     const int row = u / p.nseg, x0 = (u - row * p.nseg) * p.segw;
     if (MODE == RM_STATS) {
+#pragma unroll 4
       for (int q = tid; q < nchunks; q += 256) {
         float v[8];
         rp_unpack8(*reinterpret_cast<const uint4*>(sy + (size_t)q * 16), v);
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
         for (int e = 0; e < 8; ++e) { a0[e] += v[e]; a1[e] += v[e] * v[e]; }
       }
     } else if (MODE == RM_BRED) {
+#pragma unroll 4
       for (int q = tid; q < nchunks; q += 256) {
         float v[8], g[8];
         rp_unpack8(*reinterpret_cast<const uint4*>(sy + (size_t)q * 16), v);
@@ -313,22 +315,32 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
     } else if (MODE == RM_FWD) {
       bf16* ob = reinterpret_cast<bf16*>(p.o1.ptr);
       const int halo = p.o1.halo;
-      int Ys[3], ny = 0;
-      Ys[ny++] = row + halo;
-      if (halo > 0) {
-        if (row >= 1 && row <= halo) Ys[ny++] = halo - row;
-        if (row >= H - 1 - halo && row <= H - 2) Ys[ny++] = halo + 2 * (H - 1) - row;
-      }
+      // destination rows: the row itself and up to two reflections of it in the halo
+      const bool r1 = halo > 0 && row >= 1 && row <= halo, r2 = halo > 0 && row >= H - 1 - halo && row <= H - 2;
+      const int Ya = row + halo;
+      const int Yb = r1 ? halo - row : (r2 ? halo + 2 * (H - 1) - row : -1);
+      const int Yc = (r1 && r2) ? halo + 2 * (H - 1) - row : -1;
+      const int ny = 1 + (Yb >= 0) + (Yc >= 0);
       // Output addressing hoisted out of the chunk loop: per destination row Y the element offset of padded column
       // X is ybase[Y][X & pmask] + (X >> pshift) * C (plain layout: pmask = pshift = 0; parity planes: 1 / 1)
       const int pmask = p.o1.layout ? 1 : 0;
-      long long ybase[3][2];
-      for (int a = 0; a < ny; ++a) {
-        ybase[a][0] = p.o1.off_padded(n, Ys[a], 0) + c0;
-        ybase[a][1] = p.o1.layout ? p.o1.off_padded(n, Ys[a], 1) + c0 : ybase[a][0];
-      }
+      // (explicit scalars instead of small arrays: dynamically indexed arrays would live in local memory)
+      const long long ya0 = p.o1.off_padded(n, Ya, 0) + c0;
+      const long long ya1 = p.o1.layout ? p.o1.off_padded(n, Ya, 1) + c0 : ya0;
+      const long long yb0 = ny > 1 ? p.o1.off_padded(n, Yb, 0) + c0 : 0;
+      const long long yb1 = ny > 1 ? (p.o1.layout ? p.o1.off_padded(n, Yb, 1) + c0 : yb0) : 0;
+      const long long yc0 = ny > 2 ? p.o1.off_padded(n, Yc, 0) + c0 : 0;
+      const long long yc1 = ny > 2 ? (p.o1.layout ? p.o1.off_padded(n, Yc, 1) + c0 : yc0) : 0;
+      auto put = [&](int X, const uint4& o) {
+        const long long xo = (long long)(X >> pmask) * C;
+        const bool odd = (X & pmask) != 0;
+        *reinterpret_cast<uint4*>(ob + (odd ? ya1 : ya0) + xo) = o;
+        if (ny > 1) *reinterpret_cast<uint4*>(ob + (odd ? yb1 : yb0) + xo) = o;
+        if (ny > 2) *reinterpret_cast<uint4*>(ob + (odd ? yc1 : yc0) + xo) = o;
+      };
       const int pstep = 256 / cvs;                     // pixels between two chunks of this thread (cvs divides 256)
       int px = x0 + tid / cvs;
+#pragma unroll 4
       for (int q = tid; q < nchunks; q += 256, px += pstep) {
         float v[8];
         rp_unpack8(*reinterpret_cast<const uint4*>(sy + (size_t)q * 16), v);
@@ -341,16 +353,10 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
           for (int e = 0; e < 8; ++e) v[e] += r[e];
         }
         const uint4 o = rp_pack8(v);
-        int Xs[3], nx = 0;
-        Xs[nx++] = px + halo;
+        put(px + halo, o);
         if (halo > 0) {
-          if (px >= 1 && px <= halo) Xs[nx++] = halo - px;
-          if (px >= W - 1 - halo && px <= W - 2) Xs[nx++] = halo + 2 * (W - 1) - px;
-        }
-        for (int b = 0; b < nx; ++b) {
-          const int X = Xs[b];
-          const long long xo = (long long)(X >> pmask) * C;
-          for (int a = 0; a < ny; ++a) *reinterpret_cast<uint4*>(ob + ybase[a][X & pmask] + xo) = o;
+          if (px >= 1 && px <= halo) put(halo - px, o);
+          if (px >= W - 1 - halo && px <= W - 2) put(halo + 2 * (W - 1) - px, o);
         }
       }
     } else {
@@ -358,6 +364,7 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
       bf16* drb = p.has_o2 ? reinterpret_cast<bf16*>(p.o2.ptr) + p.o2.off(n, row, x0) + c0 : nullptr;
       const int pstep = 256 / cvs;
       int pl = tid / cvs;                               // pixel inside the segment
+#pragma unroll 4
       for (int q = tid; q < nchunks; q += 256, pl += pstep) {
         float v[8], g[8], o[8];
         const uint4 gu = *reinterpret_cast<const uint4*>(sd + d_off(q));
