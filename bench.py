@@ -128,9 +128,9 @@ one_step = train_step          # name used by tools/timeline_step.py, tools/prof
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at its in-step shape, from the
 # `ncu --set full` captures summarised under profiles/ (None where no capture exists for that batch).
-# n = 48: 29.71 MB read + 0.08 MB written (input 28.4 MB + weights 1.2 MB read exactly once; the 31.8 MB output was
-# still in the 126 MB L2 when the capture ended), profiles/r01g_ncu_g7_b48.md
-G7_TRAFFIC_BYTES = {48: 29794560}
+# n = 48: 29.66 MB read + 0.01 MB written (input 28.4 MB + weights 1.2 MB read exactly once; the 31.8 MB output was
+# still in the 126 MB L2 when the capture ended), profiles/r02_ncu_g7_b48.md (round 1: 29.79 MB, r01g_ncu_g7_b48.md)
+G7_TRAFFIC_BYTES = {48: 29671168}
 
 
 def conv_roofline(peaks, n):
