@@ -99,6 +99,10 @@ def lib():
                                    C.c_void_p, C.c_int, C.c_void_p]
         _lib.dwc_sgemm_ws.argtypes = list(_lib.dwc_sgemm.argtypes[:-1]) + [C.c_void_p, C.c_int64, C.c_void_p]
         _lib.dwc_sgemm_workspace_bytes.restype = C.c_int64
+        if hasattr(_lib, "dwc_post_bwd_cluster"):          # parked kernel, only in a DWC_EXPERIMENTAL=1 build
+            _lib.dwc_post_bwd_cluster_ok.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+            _lib.dwc_post_bwd_cluster.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.dwc_gemm_tf32.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                        C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
         _lib.dwc_gemm_tf32_ok.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,

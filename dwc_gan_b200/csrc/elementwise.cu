@@ -1959,4 +1959,3 @@ extern "C" int dwc_post_bwd_reduce(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, 
   DWC_LAUNCH_CHECK();
   return 0;
 }
-

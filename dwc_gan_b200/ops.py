@@ -49,6 +49,8 @@ class Runtime:
         self.conv7_which = os.environ.get("DWC_CONV7", "1")          # diagnostics: "h" heads only, "d" dgrad only
         self.use_fused_norm = os.environ.get("DWC_FUSED_NORM", "0") != "0"   # opt-in: the row-streaming passes are faster
         self.epi_stats = os.environ.get("DWC_EPI_STATS", "1") != "0"        # norm statistics from the conv epilogue
+        # parked experiment (csrc/experimental/normbwd_cluster.cu, DWC_EXPERIMENTAL=1 builds only): one-pass cluster backward
+        self.norm_cluster = os.environ.get("DWC_NORM_CLUSTER", "0") != "0"
         self.wgrad_hook = None       # data parallel: callable(weight name) after a layer's weight gradient is enqueued
 
     def set_mode(self, mode: str):
@@ -653,6 +655,16 @@ class PostFn(torch.autograd.Function):
                 dnw = torch.empty(n, c, dtype=torch.float32, device=dev)
                 dnb = torch.empty(n, c, dtype=torch.float32, device=dev)
             _call("dwc_post_fused_bwd", C.byref(ds), C.byref(ys), L.ptr(coef), kind, act, L.ptr(nw), L.ptr(dnw),
+                  L.ptr(dnb), C.byref(dys), C.byref(drs) if drs is not None else None, L.stream())
+        elif RT.norm_cluster and kind in (NORM_IN, NORM_ADAIN) and hasattr(L.lib(), "dwc_post_bwd_cluster") and \
+                L.lib().dwc_post_bwd_cluster_ok(
+                C.byref(ds), C.byref(ys), kind, C.byref(dys), C.byref(drs) if drs is not None else None):
+            # a whole sample fits the shared memory of an 8-CTA cluster (the 256-channel 32x32 residual blocks): halo
+            # fold, reductions, coefficients and apply in ONE launch and one read of dout and y
+            if kind == NORM_ADAIN:
+                dnw = torch.empty(n, c, dtype=torch.float32, device=dev)
+                dnb = torch.empty(n, c, dtype=torch.float32, device=dev)
+            _call("dwc_post_bwd_cluster", C.byref(ds), C.byref(ys), L.ptr(coef), kind, act, L.ptr(nw), L.ptr(dnw),
                   L.ptr(dnb), C.byref(dys), C.byref(drs) if drs is not None else None, L.stream())
         else:
             # fold the reflect-halo gradient once, in place: the streaming passes then read whole interior rows

@@ -366,6 +366,21 @@ int dwc_pack_weights_batch(const dwc_pack_entry_t* table_dev, int count, dwc_str
 int dwc_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t count, dwc_stream_t stream);
 int dwc_fill(void* dst, int dtype, float value, int64_t count, dwc_stream_t stream);
 
+#ifdef DWC_EXPERIMENTAL   /* parked kernels, csrc/experimental/ (not in the default library) */
+/* One-pass backward of an InstanceNorm (kind 1) / AdaIN (kind 2) site with a whole sample held in the shared memory of
+ * a thread-block cluster (8 CTAs, partial sums exchanged through distributed shared memory): reflect-halo fold of
+ * `dout` (halo <= 1, not modified), per-channel reductions, coefficients, dy (zero halo), optional residual gradient
+ * `dres` and the AdaIN parameter gradients in ONE launch and one read of dout and y.  Same arithmetic as
+ * dwc_fold_halo + dwc_post_bwd_reduce + dwc_post_bwd_apply_norm (networks.py:545,693-722 backward).
+ * dwc_post_bwd_cluster_ok() says whether a site qualifies (bf16, plain layouts, H %% 8 == 0, rows fit shared memory:
+ * the 256-channel 32x32 residual blocks). */
+int dwc_post_bwd_cluster_ok(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, int kind, const dwc_hbuf_t* dy,
+                            const dwc_hbuf_t* dres);
+int dwc_post_bwd_cluster(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, int kind, int act,
+                         const float* weight, float* dweight, float* dbias, const dwc_hbuf_t* dy,
+                         const dwc_hbuf_t* dres, dwc_stream_t stream);
+#endif
+
 #ifdef __cplusplus
 }
 #endif

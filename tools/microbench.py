@@ -210,6 +210,13 @@ def bench_post(n, c, hw, kind, peaks, halo_out=1, halo_dy=2):
     def b_app(i):
         L.check(lib.dwc_post_bwd_apply(S(douts[i]), S(ys[i]), L.ptr(coef), L.ptr(bco), 1, S(dys[i]), None, 1, st()))
     f_stats(0); f_fin(0); b_red(0); b_fin(0)
+    dres = [HB.empty(n, hw, hw, c, halo_out, 0, bt, "cuda") for _ in range(nbuf)]
+    cluster_ok = kind in (1, 2) and hasattr(lib, "dwc_post_bwd_cluster") and \
+        bool(lib.dwc_post_bwd_cluster_ok(S(douts[0]), S(ys[0]), kind, S(dys[0]), None))       # experimental builds only
+
+    def b_cluster(i):
+        L.check(lib.dwc_post_bwd_cluster(S(douts[i]), S(ys[i]), L.ptr(coef), kind, 1, L.ptr(nw), L.ptr(gw), L.ptr(gb),
+                                         S(dys[i]), None, st()))
     rows = []
     name = "%s %dx%dx%d" % ({1: "IN", 2: "AdaIN", 3: "LN"}[kind], c, hw, hw)
     tot = {"fwd": 0.0, "bwd": 0.0}
@@ -221,6 +228,11 @@ def bench_post(n, c, hw, kind, peaks, halo_out=1, halo_dy=2):
         tot[grp] += t
         rows.append(dict(layer=name, op=op, n=n, us=round(t * 1e6, 1), gbs=round(byts / t / 1e9, 1),
                          frac_of_hbm=round(byts / t / 1e9 / peaks["hbm"], 3)))
+    if cluster_ok:
+        t = timeit([(lambda i=i: b_cluster(i)) for i in range(nbuf)])
+        rows.append(dict(layer=name, op="SITE bwd, one-pass cluster kernel (parked experiment)", n=n,
+                         us=round(t * 1e6, 1), gbs=round(3 * E * 2 / t / 1e9, 1),
+                         frac_of_hbm=round(3 * E * 2 / t / 1e9 / peaks["hbm"], 3)))
     # product path since round 2: the statistics come out of the producing convolution's epilogue (dwc_gconv_t.stats) and
     # the coefficients are computed inside the apply kernel, so a forward site is the post_fwd pass alone
     t_fused = [r for r in rows if r["op"] == "post_fwd"][0]["us"] * 1e-6
