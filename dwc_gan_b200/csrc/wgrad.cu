@@ -23,6 +23,7 @@ struct WgradDev {
   int ngroup;          // taps per item on the N operand (1 = classic); > 1: N boxes are the SAME channels of `ngroup`
                        // taps, read at pixel - tap (the M operand is untapped and the tiles walk ITS pixel grid)
   int ntaps_total;     // real tap count (items cover ceil(ntaps_total / ngroup) groups)
+  int debug;           // diagnostics (DWC_WGRAD_DEBUG): 1 = no MMAs (memory pipeline only), 2 = no loads after the first ring fill
   int grp_plus;        // grouped mode, which side carries the taps: 0 = the N operand is read at pixel - tap (operands
                        // swapped, M = untapped padded input); 1 = the N operand IS the tapped input, read at pixel + tap
                        // (incl. its parity plane), M = untapped dY and the tiles walk dY's grid
@@ -193,6 +194,14 @@ __global__ void __launch_bounds__(WG_THREADS)
         int x0, y0, n0;
         wg_tile_origin(p, tile, &x0, &y0, &n0);
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (p.debug == 2 && tile >= tile_begin + Cfg::STAGES) {       // diagnostics: MMA pipeline without memory traffic
+          mbar_arrive(&full_bar[stage]);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         mbar_expect_tx(&full_bar[stage], Cfg::STAGE);
         uint8_t* s = smem + stage * Cfg::STAGE;
 #pragma unroll
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(WG_THREADS)
           // MN-major SW128: 64-channel atoms LBO apart, 8-pixel groups SBO = 1024 B apart
           uint64_t da = umma_desc_sw128(m_addr + k * 2048, WG_BOX_BYTES, 1024);
           uint64_t db = umma_desc_sw128(n_addr + k * 2048, WG_BOX_BYTES, 1024);
-          umma_bf16(tmem_base, da, db, idesc, first ? 0u : 1u);
+          if (p.debug != 1) umma_bf16(tmem_base, da, db, idesc, first ? 0u : 1u);
           first = 0;
         }
         umma_commit(&empty_bar[stage]);
@@ -573,6 +582,14 @@ extern "C" int dwc_wgrad(const dwc_wgrad_t* g, dwc_stream_t stream) {
   d.ntiles = pl.ntiles; d.splits = pl.splits; d.tiles_per_split = pl.tiles_per_split;
   d.ntaps = pl.ngroup > 1 ? cdiv(g->ntaps, pl.ngroup) : g->ntaps;
   d.ngroup = pl.ngroup;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("DWC_WGRAD_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    d.debug = dbg;
+  }
   d.grp_plus = pl.grp_plus;
   d.ntaps_total = g->ntaps;
   d.ws = g->workspace;

@@ -103,6 +103,8 @@ def side_launch(fn, keep, name=None):
 
 
 def _side_launch(fn, keep):
+    if os.environ.get("DWC_ABLATE_WGRAD"):       # diagnostics only (tools/ablate_step.sh): what the weight gradients cost
+        return None
     if not RT.use_side_stream:
         return fn()
     dev = torch.cuda.current_device()
