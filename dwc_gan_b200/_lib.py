@@ -38,6 +38,8 @@ class GConv(C.Structure):
         ("out_dtype", C.c_int32), ("accumulate", C.c_int32),
         ("nphase", C.c_int32), ("reserved0", C.c_int32), ("phase_w_off", C.c_int64), ("phase_out_off", C.c_int64),
         ("stats", C.c_void_p),
+        ("out2", C.c_void_p), ("out2_halo", C.c_int32), ("out2_layout", C.c_int32), ("out2_act", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 

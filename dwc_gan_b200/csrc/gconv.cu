@@ -118,7 +118,7 @@ template <int BN> struct TcCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, (BN >= 256 ? 1 : 2))
     gconv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ GConvDev p) {
   using Cfg = TcCfg<BN>;
@@ -136,9 +136,18 @@ __global__ void __launch_bounds__(TC_THREADS)
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
   const int col0 = blockIdx.y * BN;
-  const int ph = blockIdx.z;                       // phase: weights ph*ncols_padded rows down, output ph*phase_out_off on
+  // Split K (few tiles, long K: the 4x4 stride-2 layers on 16x16 .. 4x4 maps, where one CTA per tile is bound by what
+  // ONE SM can pull out of L2): the ksplit CTAs of a cluster (1,1,ksplit) each accumulate a contiguous share of the
+  // (tap, channel block) iterations in their own TMEM, park the fp32 partial tile in their idle pipeline shared
+  // memory, and each finishes 1/ksplit of the tile's columns from everybody's partial sums (reduce-scatter through
+  // distributed shared memory, added in rank order: deterministic).
+  const int ks = p.ksplit;
+  const int ph = blockIdx.z / ks;                  // phase: weights ph*ncols_padded rows down, output ph*phase_out_off on
+  const int kr = blockIdx.z - ph * ks;             // == %cluster_ctarank
   const int cblocks = p.C / TC_BK;
-  const int num_kb = p.debug == 3 ? 0 : p.ntaps * cblocks;
+  const int all_kb = p.debug == 3 ? 0 : p.ntaps * cblocks;
+  const int kb0 = all_kb / ks * kr;
+  const int num_kb = all_kb / ks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -166,18 +175,21 @@ __global__ void __launch_bounds__(TC_THREADS)
       const int x0 = tx * p.box_x, y0 = ty * p.box_y, n0 = tn * p.box_n;
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < (p.debug == 3 ? 0 : p.ntaps); ++t) {
+      int t = kb0 / cblocks, cb = kb0 - t * cblocks;
+      for (int kb = 0; kb < num_kb; ++kb) {
         const int cx = x0 + p.taps[t][0], cy = y0 + p.taps[t][1], cz = p.taps[t][2];
-        for (int cb = 0; cb < cblocks; ++cb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-          tma_load_5d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * TC_BK, cx, cy, cz, n0);
-          tma_load_2d(sB + stage * Cfg::B_BYTES_AL, &tmB, &full_bar[stage], t * p.C + cb * TC_BK,
-                      col0 + ph * p.ncols_padded);
-          if (++stage == Cfg::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+        tma_load_5d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * TC_BK, cx, cy, cz, n0);
+        tma_load_2d(sB + stage * Cfg::B_BYTES_AL, &tmB, &full_bar[stage], t * p.C + cb * TC_BK,
+                    col0 + ph * p.ncols_padded);
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++cb == cblocks) {
+          cb = 0;
+          ++t;
         }
       }
     }
@@ -214,12 +226,116 @@ __global__ void __launch_bounds__(TC_THREADS)
     long long off = 0;
     const bool valid = out_offset(p, rc, &off);
     off += ph * p.phase_out_off;
+    long long d2off[4] = {0, 0, 0, 0};
+    const int d2n = p.out2 ? out2_dests(p, rc, valid, d2off) : 0;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     constexpr int CHUNK = BN >= 32 ? 32 : 16;
     const bool staged = BN >= 64 && p.out_dtype == DWC_BF16 && (p.ncols & 7) == 0 && col0 + BN <= p.ncols &&
                         p.debug == 0;
-    if (staged) {
+    if (BN >= 64 && ks > 1) {
+      // ---- split K: park the fp32 partial tile, [column][row], in the idle stage buffers ...
+      float* part = reinterpret_cast<float*>(smem);
+      {
+        const int cw0 = ((warp - 2) >> 2) * (BN / 2);
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 2; cc += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cw0 + cc), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part[(cw0 + cc + j) * TC_BM + r] = __uint_as_float(v[j]);
+        }
+      }
+      cluster_arrive_release();                            // every CTA's partial tile is complete and visible
+      cluster_wait_acquire();
+      // ---- ... then rank kr finishes columns [kr * BN/ks, (kr+1) * BN/ks) of the tile: the partial sums of all ranks,
+      // added in rank order (deterministic), through distributed shared memory (~20 B/clk per SM, hence a slice each
+      // instead of everything into one CTA).  Thread = one row x half of the slice's columns.
+      const int SL = BN / ks;                              // >= 16
+      const int et = threadIdx.x - 64;
+      const int row = et & (TC_BM - 1), chalf = et >> 7;
+      const int nc = SL >> 1;                              // this thread's columns, a multiple of 8
+      const int sc0 = kr * SL + chalf * nc;                // first of them, inside the tile
+      const RowCoord rc2 = tile_row(p, tile, row);
+      long long off2 = 0;
+      const bool valid2 = out_offset(p, rc2, &off2);
+      off2 += ph * p.phase_out_off;
+      long long e2off[4] = {0, 0, 0, 0};
+      const int e2n = p.out2 ? out2_dests(p, rc2, valid2, e2off) : 0;
+      float2* sst = reinterpret_cast<float2*>(smem + BN * TC_BM * 4);      // [4 row quarters][SL]
+      uint32_t peer[8];
+#pragma unroll
+      for (int pr = 0; pr < 8; ++pr) peer[pr] = cluster_map_shared(smem_u32(smem), pr < ks ? pr : 0);
+#pragma unroll 1
+      for (int g8 = 0; g8 < nc; g8 += 8) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        const uint32_t eoff = ((sc0 + g8) * TC_BM + row) * 4;
+#pragma unroll
+        for (int pr = 0; pr < 8; ++pr) {
+          if (pr < ks) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += ld_cluster_f32(peer[pr] + eoff + e * TC_BM * 4);
+          }
+        }
+        const int cg = col0 + sc0 + g8;                    // global output column
+        if (p.bias) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cg));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cg + 4));
+          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+          f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+        }
+        uint4 sv;
+        if (valid2) {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + off2 + cg;
+          if (p.accumulate) {
+            float old[8];
+            Vec8<bf16>::load(o, old);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += old[e];
+          }
+          Vec8<bf16>::store(reinterpret_cast<bf16*>(&sv), f);
+          *reinterpret_cast<uint4*>(o) = sv;
+          if (p.out2) {
+            const uint4 av = act8_bf16(sv, p.o2_act);
+            bf16* o2 = reinterpret_cast<bf16*>(p.out2) + cg;
+            for (int d = 0; d < e2n; ++d) *reinterpret_cast<uint4*>(o2 + e2off[d]) = av;
+          }
+        } else {
+          Vec8<bf16>::store(reinterpret_cast<bf16*>(&sv), f);
+        }
+        if (p.stats) {
+          // {sum, sum of squares} of the stored values over this warp's 32 rows, per column
+          float rs[8];
+          Vec8<bf16>::load(reinterpret_cast<const bf16*>(&sv), rs);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float a = valid2 ? rs[e] : 0.f, b = a * a;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              a += __shfl_xor_sync(0xffffffffu, a, o);
+              b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (lane == 0) sst[((row >> 5) * SL) + chalf * nc + g8 + e] = make_float2(a, b);
+          }
+        }
+      }
+      if (p.stats) {
+        epi_bar_sync();
+        const int tpi = p.tiles_x * p.tiles_y, n_img = tile / tpi, t_img = tile - n_img * tpi;
+        if (et < SL) {
+          float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) {
+            const float2 u = sst[w4 * SL + et];
+            t.x += u.x; t.y += u.y;
+          }
+          p.stats[((long long)n_img * tpi + t_img) * p.ncols + col0 + kr * SL + et] = t;
+        }
+      }
+    } else if (staged) {
       // Coalesced epilogue.  A thread owns one accumulator row, so storing straight from registers puts the 32 lanes
       // of every store instruction on 32 different output rows (16 bytes each, >= 512 bytes apart).  Instead each
       // warp stages its 32 rows x BN/2 columns (bf16, XOR-swizzled 16-byte pieces) in the now idle pipeline shared
@@ -296,6 +412,17 @@ __global__ void __launch_bounds__(TC_THREADS)
             *dst = dv;
           }
         }
+        if (p.out2) {
+          // activated copy into the next block's reflect-haloed input buffer: the row's (up to 4) destinations
+          const uint4 av = act8_bf16(dv, p.o2_act);
+          bf16* o2 = reinterpret_cast<bf16*>(p.out2) + col0 + cw0 + piece * 8;
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const long long doff = __shfl_sync(0xffffffffu, d2off[d], rl);
+            const int dn = __shfl_sync(0xffffffffu, d2n, rl);
+            if (d < dn) *reinterpret_cast<uint4*>(o2 + doff) = av;
+          }
+        }
       }
     } else if (warp < 6) {
 #pragma unroll 1
@@ -345,6 +472,16 @@ __global__ void __launch_bounds__(TC_THREADS)
       }
     }
     }
+  }
+  if (ks > 1) {
+    // first cluster barrier: partial tiles written (the epilogue warps passed it before reading them); second: every
+    // rank has read its slice, the peers' shared memory may go away
+    if (warp < 2) {
+      cluster_arrive_release();
+      cluster_wait_acquire();
+    }
+    cluster_arrive_release();
+    cluster_wait_acquire();
   }
   tc_fence_before();
   __syncthreads();
@@ -493,6 +630,8 @@ __global__ void __launch_bounds__(TC_THREADS, (BN >= 256 ? 1 : 2))     // narrow
       long long off = 0;
       const bool valid = out_offset(p, rc, &off);
       off += ph * p.phase_out_off;
+      long long d2off[4] = {0, 0, 0, 0};
+      const int d2n = p.out2 ? out2_dests(p, rc, valid, d2off) : 0;
       mbar_wait(&tmem_full[acc], (li >> 1) & 1);
       tc_fence_after();
       // fused statistics (BN >= 64): per-warp column sums in shared memory, double-buffered over items
@@ -549,7 +688,14 @@ __global__ void __launch_bounds__(TC_THREADS, (BN >= 256 ? 1 : 2))     // narrow
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] += old[e];
               }
-              Vec8<bf16>::store(o + j, f);
+              uint4 sv;
+              Vec8<bf16>::store(reinterpret_cast<bf16*>(&sv), f);
+              *reinterpret_cast<uint4*>(o + j) = sv;
+              if (p.out2) {                              // activated copy into the next block's reflect-haloed input
+                const uint4 av = act8_bf16(sv, p.o2_act);
+                bf16* o2 = reinterpret_cast<bf16*>(p.out2) + cbase + j;
+                for (int d = 0; d < d2n; ++d) *reinterpret_cast<uint4*>(o2 + d2off[d]) = av;
+              }
             }
           } else {
             for (int j = 0; j < CHUNK; ++j) {
@@ -630,8 +776,60 @@ static int launch_tc(const dwc_gconv_t* g, const GConvDev& d, cudaStream_t st) {
     DWC_CUDA(cudaFuncSetAttribute(gconv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
+  // split K over a cluster when the launch fills only a fraction of the SMs (see the kernel)
+  GConvDev dd = d;
+  dd.ksplit = 1;
+  static int ksmax = -1;
+  if (ksmax < 0) {
+    const char* e = getenv("DWC_KSPLIT");
+    ksmax = e ? atoi(e) : 8;
+  }
+  const int ctas = d.tiles_x * d.tiles_y * d.tiles_n * cdiv(g->ncols_padded, BN) * d.nphase;
+  const int all_kb = d.ntaps * (d.C / TC_BK);
   dim3 grid(d.tiles_x * d.tiles_y * d.tiles_n, cdiv(g->ncols_padded, BN), d.nphase);
-  gconv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, d);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 1;
+  attr.val.clusterDim.y = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  if (BN >= 64 && d.out_dtype == DWC_BF16 && g->ncols % BN == 0 && d.debug == 0 && all_kb >= 32) {
+    // a split pays when the K loop it removes (~0.25 us per iteration of one CTA) outweighs the reduction (~5 us):
+    // at least 8 iterations left per CTA, and all clusters co-resident (one wave)
+    static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = ksmax; k >= 2; k >>= 1) {
+      if (k > 8 || all_kb % k || all_kb / k < 8 || BN / k < 16 || ctas * k > dwc_num_sms()) continue;
+      if (max_clusters[k] == 0) {
+        cfg.gridDim = dim3(k * 16, 1, 1);
+        attr.val.clusterDim.z = 1;
+        attr.val.clusterDim.x = k;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, gconv_tc_kernel<BN>, &cfg) != cudaSuccess) {
+          cudaGetLastError();
+          nc = -1;
+        }
+        attr.val.clusterDim.x = 1;
+        max_clusters[k] = nc > 0 ? nc : -1;
+      }
+      if (ctas <= max_clusters[k]) {
+        dd.ksplit = k;
+        break;
+      }
+    }
+  }
+  grid.z = d.nphase * dd.ksplit;
+  if (dd.ksplit == 1) {
+    gconv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, dd);
+  } else {
+    cfg.gridDim = grid;
+    attr.val.clusterDim.z = dd.ksplit;
+    DWC_CUDA(cudaLaunchKernelEx(&cfg, gconv_tc_kernel<BN>, tmA, tmB, dd));
+  }
   DWC_LAUNCH_CHECK();
   return 0;
 }
@@ -673,6 +871,18 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
   d.out_dtype = g->out_dtype; d.accumulate = g->accumulate;
   d.nphase = nphase; d.phase_out_off = g->phase_out_off;
   d.stats = reinterpret_cast<float2*>(g->stats);
+  d.out2 = g->out2; d.o2_halo = g->out2_halo; d.o2_layout = g->out2_layout; d.o2_act = g->out2_act;
+  if (g->out2) {
+    const int npp = g->ncols_padded;
+    const int bn = npp % 256 == 0 ? 256 : (npp % 128 == 0 ? 128 : 64);
+    DWC_CHECK(g->backend == DWC_TC && g->dtype == DWC_BF16 && g->out_dtype == DWC_BF16 && !g->flat && nphase == 1 &&
+                  g->ncols % 64 == 0 && g->ncols == g->ncols_padded && g->ncols % bn == 0 && !g->accumulate &&
+                  (g->out2_act == 1 || g->out2_act == 2) && g->out2_halo >= 0 &&
+                  (g->out2_halo == 0 || (g->valid[0] >= 2 * g->out2_halo + 2 && g->valid[1] >= 2 * g->out2_halo + 2)) &&
+                  (g->out2_layout == 0 || (((g->valid[0] + 2 * g->out2_halo) & 1) == 0 && ((g->valid[1] + 2 * g->out2_halo) & 1) == 0)),
+              "dwc_gconv: the activated second output needs the tcgen05 backend, bf16, ncols %% 64 == 0 and a haloed "
+              "destination with at most one mirror image per axis");
+  }
   if (g->stats) {
     DWC_CHECK(g->backend == DWC_TC && g->dtype == DWC_BF16 && g->out_dtype == DWC_BF16 && !g->flat && nphase == 1 &&
                   g->box[2] == 1 && g->ncols % 64 == 0 && g->ncols == g->ncols_padded && !g->accumulate,
@@ -707,7 +917,7 @@ extern "C" int dwc_gconv(const dwc_gconv_t* g, dwc_stream_t stream) {
       const char* e = getenv("DWC_CG2");
       cg2 = e ? atoi(e) : 0;
     }
-    if (cg2 && ntiles >= 2 && !g->stats) {
+    if (cg2 && ntiles >= 2 && !g->stats && !g->out2) {
       const int rc = dwc_launch_gconv_tc2(g, d, st);
       if (rc >= 0) return rc;
     }

@@ -310,14 +310,17 @@ class Conv2dBlock(nn.Module):
             res_box=None) -> HB:
         """xp: reflect-haloed input (halo == padding, parity planes if stride 2).  skip_box / res_box: see ResBlock."""
         assert xp.halo == self.padding and xp.layout == self.in_layout() and xp.c == self.cin
-        y = _ConvProxy.conv(xp, self, skip_box)
+        epi = (_ACT[self.act_name], out_halo, out_layout) if not raw and res is None and self.norm_kind == NORM_NONE \
+            else None
+        y = _ConvProxy.conv(xp, self, skip_box, epi)
         if raw:
             return y
         return self.finish(y, out_halo, out_layout, res, res_box)
 
     def run_first(self, img, rows_t, pool, out_halo=0, out_layout=0, raw=False) -> HB:
         """First layer of a network: img NCHW fp32 (3 channels), rows_t = ops.image_rows(img, pool, self)."""
-        y = ops.first_conv(img, rows_t, self, pool)
+        epi = (_ACT[self.act_name], out_halo, out_layout) if not raw and self.norm_kind == NORM_NONE else None
+        y = ops.first_conv(img, rows_t, self, pool, epi)
         return y if raw else self.finish(y, out_halo, out_layout, None)
 
     def finish(self, y: HB, out_halo=0, out_layout=0, res: Optional[HB] = None, res_box=None) -> HB:
@@ -352,8 +355,8 @@ class Conv2dBlock(nn.Module):
 
 class _ConvProxy:
     @staticmethod
-    def conv(xp: HB, layer: Conv2dBlock, skip_box=None) -> HB:
-        return ops.conv(xp, layer, skip_box)
+    def conv(xp: HB, layer: Conv2dBlock, skip_box=None, epi=None) -> HB:
+        return ops.conv(xp, layer, skip_box, epi)
 
 
 class ResBlock(nn.Module):

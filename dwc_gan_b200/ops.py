@@ -49,6 +49,10 @@ class Runtime:
         self.conv7_which = os.environ.get("DWC_CONV7", "1")          # diagnostics: "h" heads only, "d" dgrad only
         self.use_fused_norm = os.environ.get("DWC_FUSED_NORM", "0") != "0"   # opt-in: the row-streaming passes are faster
         self.epi_stats = os.environ.get("DWC_EPI_STATS", "1") != "0"        # norm statistics from the conv epilogue
+        # activation + reflect halo of the norm-less blocks from the conv epilogue (dwc_gconv_t.out2): bit-identical to
+        # the separate pass and 35 launches fewer per step, but measured 0.4% SLOWER on the training step (the extra
+        # scattered epilogue stores cost what the streaming pass did, profiles/r02f) - opt-in
+        self.epi_act = os.environ.get("DWC_EPI_ACT", "0") == "1"
         # parked experiment (csrc/experimental/normbwd_cluster.cu, DWC_EXPERIMENTAL=1 builds only): one-pass cluster backward
         self.norm_cluster = os.environ.get("DWC_NORM_CLUSTER", "0") != "0"
         self.wgrad_hook = None       # data parallel: callable(weight name) after a layer's weight gradient is enqueued
@@ -193,7 +197,7 @@ class ConvFn(torch.autograd.Function):
     (networks.py:577-580 and aten::convolution_backward)."""
 
     @staticmethod
-    def forward(ctx, xp_t, weight, layer, xp: HB, skip_box=None):
+    def forward(ctx, xp_t, weight, layer, xp: HB, skip_box=None, epi=None):
         _require_cuda(xp_t)
         ctx.skip_box = skip_box
         k, s, cout = layer.k, layer.stride, layer.total_cout()
@@ -205,6 +209,8 @@ class ConvFn(torch.autograd.Function):
         pl = P.plan_conv_fwd(HB(xp_t, xp.n, xp.h, xp.w, xp.c, xp.halo, xp.layout), wf, cout, rows_p, layer.bias_f32(),
                              y, k, s, L.TC if tc else L.SIMT)
         stats = _attach_stats(pl, layer, xp.n, cout, xp_t.device)
+        if stats is None:
+            stats = _attach_act_out(pl, layer, epi, xp.n, ho, wo, cout, xp_t.dtype, xp_t.device)
         RT.launches += 1
         pl.launch()
         ctx.layer, ctx.xp_meta, ctx.y_meta = layer, (xp.n, xp.h, xp.w, xp.c, xp.halo, xp.layout), (ho, wo, hy)
@@ -272,7 +278,7 @@ class ConvFn(torch.autograd.Function):
                 wp = P.plan_conv_wgrad(dy, xp, gw, gb, k, s, L.TC if tc else L.SIMT, accumulate=True)
                 side_launch(lambda: wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device)), (dy.t, xp_t),
                             name=layer._names()[1])
-        return dxp_t, None, None, None, None
+        return dxp_t, None, None, None, None, None
 
 
 def _pad_channels(hb: HB, c_new: int) -> HB:
@@ -308,18 +314,42 @@ def _attach_stats(pl, layer, n, cout, device):
     return pl.stats
 
 
-def _hb_with_stats(out, n, ho, wo, cout, halo):
+def _attach_act_out(pl, layer, epi, n, ho, wo, cout, dtype, device):
+    """Ask the convolution's epilogue to also write act(y) into the next block's reflect-haloed input buffer (layers
+    without a norm: style encoder, discriminator), so that the forward needs no separate activation / pad pass.
+    epi = (act, out_halo, out_layout) of the consumer; returns the buffer or None when the launch cannot do it."""
+    if epi is None or not RT.epi_act or pl.backend != L.TC or dtype != torch.bfloat16:
+        return None
+    act, halo, layout = epi
+    if getattr(layer, "norm_kind", NORM_NONE) != NORM_NONE or act not in (1, 2) or cout % 64 or \
+            pl.ncols != pl.ncols_padded or pl.flat[0] or pl.nphase != 1:
+        return None
+    if halo and (ho < 2 * halo + 2 or wo < 2 * halo + 2):
+        return None
+    if cout % 256 and cout > 128 and cout % 128:
+        return None
+    o = HB.empty(n, ho, wo, cout, halo, layout, dtype, device)
+    pl.out2 = (o.t, act, halo, layout)
+    return o.t
+
+
+def _hb_with_stats(out, n, ho, wo, cout, halo, epi=None):
     if isinstance(out, tuple):
-        t, stats = out
-        return HB(t, n, ho, wo, cout, halo, 0, stats=(stats, stats.numel() // (2 * n * cout)))
+        t, extra = out
+        if epi is not None:
+            return HB(t, n, ho, wo, cout, halo, 0, act_out=(extra,) + tuple(epi))
+        return HB(t, n, ho, wo, cout, halo, 0, stats=(extra, extra.numel() // (2 * n * cout)))
     return HB(out, n, ho, wo, cout, halo, 0)
 
 
-def conv(xp: HB, layer, skip_box=None) -> HB:
+def conv(xp: HB, layer, skip_box=None, epi=None) -> HB:
+    """epi = (act, out_halo, out_layout) of the consumer when the layer has no norm and no residual: the epilogue then
+    also writes the activated, haloed tensor (HB.act_out) that PostFn.forward would otherwise produce."""
     k, s = layer.k, layer.stride
     ho, wo = P.out_size(xp, k, s)
-    out = ConvFn.apply(xp.t, layer.weight_param, layer, xp, skip_box)
-    return _hb_with_stats(out, xp.n, ho, wo, layer.total_cout(), k - 1 if s == 1 else 1)
+    out = ConvFn.apply(xp.t, layer.weight_param, layer, xp, skip_box, epi)
+    return _hb_with_stats(out, xp.n, ho, wo, layer.total_cout(), k - 1 if s == 1 else 1,
+                          epi if isinstance(out, tuple) and getattr(layer, "norm_kind", NORM_NONE) == NORM_NONE else None)
 
 
 def image_rows(img, pool, layer):
@@ -341,7 +371,7 @@ class FirstConvFn(torch.autograd.Function):
     k-tap, 64-channel gconv / wgrad.  Backward to the image (generated images only) is a regular dgrad."""
 
     @staticmethod
-    def forward(ctx, img, weight, layer, rows_t, pool):
+    def forward(ctx, img, weight, layer, rows_t, pool, epi=None):
         n, c, h, w = img.shape
         k, s, p, cout = layer.k, layer.stride, layer.padding, layer.cout
         hi, wi = h // pool, w // pool
@@ -354,6 +384,8 @@ class FirstConvFn(torch.autograd.Function):
         pl = P.plan_first_conv_fwd(rows_t, n, hp, wo, ho, k, s, layer.packed_rows(rows_t.dtype, 3), cout, layer.bias_f32(),
                                    y, be)
         stats = _attach_stats(pl, layer, n, cout, rows_t.device)
+        if stats is None:
+            stats = _attach_act_out(pl, layer, epi, n, ho, wo, cout, rows_t.dtype, rows_t.device)
         pl.launch()
         ctx.layer, ctx.meta = layer, (n, c, h, w, pool, hp, ho, wo, hy)
         ctx.save_for_backward(rows_t)
@@ -398,15 +430,16 @@ class FirstConvFn(torch.autograd.Function):
             wp = P.plan_first_conv_wgrad(dy, rows_t, n, hp, wo, k, s, c, gw, gb, be)
             side_launch(lambda: wp.launch(lambda nbytes: RT.workspace(nbytes, dy_t.device)), (dy.t, rows_t),
                         name=layer._names()[1])
-        return dimg, None, None, None, None
+        return dimg, None, None, None, None, None
 
 
-def first_conv(img, rows_t, layer, pool) -> HB:
+def first_conv(img, rows_t, layer, pool, epi=None) -> HB:
     n, c, h, w = img.shape
     k, s, p = layer.k, layer.stride, layer.padding
     ho, wo = (h // pool + 2 * p - k) // s + 1, (w // pool + 2 * p - k) // s + 1
-    out = FirstConvFn.apply(img.contiguous().float(), layer.weight_param, layer, rows_t, pool)
-    return _hb_with_stats(out, n, ho, wo, layer.cout, k - 1 if s == 1 else 1)
+    out = FirstConvFn.apply(img.contiguous().float(), layer.weight_param, layer, rows_t, pool, epi)
+    return _hb_with_stats(out, n, ho, wo, layer.cout, k - 1 if s == 1 else 1,
+                          epi if isinstance(out, tuple) and layer.norm_kind == NORM_NONE else None)
 
 
 def conv7_few(x_t, n, hin, win, w_master, w_base, s_o, s_ky, s_kx, s_i, bias, cout, out_t, out_str):
@@ -604,6 +637,16 @@ class PostFn(torch.autograd.Function):
         splits = _stats_splits(hw, n)
         fused = kind in (NORM_IN, NORM_ADAIN) and RT.use_fused_norm and \
             bool(L.lib().dwc_post_fused_ok(c, hw, L.dt(y_t)))
+        ready = y.act_out is not None and kind == NORM_NONE and res is None and \
+            tuple(y.act_out[1:]) == (act, out_halo, out_layout)
+        if ready:
+            # the producing convolution's epilogue already wrote act(y) + reflect halo (+ parity planes): nothing to
+            # launch; backward is the usual activation backward on the saved pre-activation y
+            ctx.fused = False
+            ctx.meta = (y.n, y.h, y.w, y.c, y.halo, kind, act, out_halo, out_layout, eps, splits, None)
+            ctx.ln_mod = ln_mod
+            ctx.save_for_backward(y_t, None, None)
+            return y.act_out[0]
         out = HB.empty(n, y.h, y.w, c, out_halo, out_layout, y_t.dtype, dev)
         ys, os_ = yh.struct(), out.struct()
         rs = HB(res_t, res.n, res.h, res.w, res.c, res.halo, res.layout).struct() if res is not None else None

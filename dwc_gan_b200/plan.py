@@ -39,11 +39,12 @@ class HB:
     """Haloed NHWC activation buffer.  layout 0: [N, H+2h, W+2h, C]; layout 1: four parity planes
     [N, 4, (H+2h)/2, (W+2h)/2, C] (input of a stride-2 conv)."""
 
-    __slots__ = ("t", "n", "h", "w", "c", "halo", "layout", "stats")
+    __slots__ = ("t", "n", "h", "w", "c", "halo", "layout", "stats", "act_out")
 
-    def __init__(self, t, n, h, w, c, halo, layout=0, stats=None):
+    def __init__(self, t, n, h, w, c, halo, layout=0, stats=None, act_out=None):
         self.t, self.n, self.h, self.w, self.c, self.halo, self.layout = t, n, h, w, c, halo, layout
         self.stats = stats            # (partial sums tensor, splits) written by the producing convolution's epilogue
+        self.act_out = act_out        # (tensor, act, halo, layout): activated + haloed copy written by the same epilogue
 
     @staticmethod
     def shape_of(n, h, w, c, halo, layout=0):
@@ -118,6 +119,7 @@ class GConvPlan:
     accumulate: bool = False
     backend: int = L.SIMT
     stats: Optional[torch.Tensor] = None   # fused per-(n, tile, column) {sum, sumsq} partials (see dwc_b200.h)
+    out2: Optional[Tuple] = None   # (tensor, act, halo, layout): activated, reflect-haloed second output (dwc_b200.h)
     nphase: int = 1                # independent problems sharing A / tiling / taps (stride-2 dgrad parity phases)
     phase_w_off: int = 0           # element offset of phase ph's weights: w_off + ph * phase_w_off
     phase_out_off: int = 0         # element offset of phase ph's output: out_off + ph * phase_out_off
@@ -147,6 +149,8 @@ class GConvPlan:
         g.accumulate = int(self.accumulate)
         g.nphase, g.phase_w_off, g.phase_out_off = self.nphase, self.phase_w_off, self.phase_out_off
         g.stats = self.stats.data_ptr() if self.stats is not None else None
+        if self.out2 is not None:
+            g.out2, g.out2_act, g.out2_halo, g.out2_layout = (self.out2[0].data_ptr(),) + tuple(self.out2[1:])
         L.check(L.lib().dwc_gconv(C.byref(g), L.stream()), "gconv")
 
 

@@ -90,6 +90,13 @@ typedef struct {
    * t = ty * tiles[0] + tx - the first half of InstanceNorm / AdaIN / LayerNorm (networks.py:545,706-719,736-752)
    * without re-reading the convolution's output (same layout as dwc_nc_stats).  NULL = off. */
   float* stats;
+  /* Optional second, ACTIVATED output (same restrictions as `stats`, plus ncols a multiple of the column tile): the
+   * epilogue also writes act(stored value) - act 1 ReLU, 2 LeakyReLU(0.1) - into the haloed buffer `out2` of interior
+   * extent valid[1] x valid[0], `out2_halo` reflect-halo pixels (written from the interior pixel they mirror) and layout
+   * 0 / 1 (dwc_hbuf_t conventions, channels = ncols): activation + nn.ReflectionPad2d of the NEXT Conv2dBlock for the
+   * norm-less layers (style encoder, discriminator: networks.py:531,556-567) without a separate pass.  NULL = off. */
+  void* out2;
+  int32_t out2_halo, out2_layout, out2_act, reserved1;
 } dwc_gconv_t;
 
 int dwc_gconv(const dwc_gconv_t* p, dwc_stream_t stream);

@@ -52,6 +52,12 @@ CASES = [
     (2, 16, 16, 64, 4, 7, 1, 3),
     (2, 16, 16, 128, 64, 5, 1, 2),      # G9 geometry: tap-grouped weight gradient (N = 4 taps x 64 channels)
     (3, 20, 12, 128, 64, 3, 1, 1),
+    # few tiles, long K: the one-wave kernel splits K over a cluster (DSMEM reduction), 8 / 8 / 4 / 4 / 2 ways
+    (16, 8, 8, 512, 512, 4, 2, 1),
+    (4, 16, 16, 128, 128, 4, 2, 1),
+    (4, 16, 16, 64, 64, 4, 2, 1),
+    (16, 32, 32, 256, 256, 4, 2, 1),
+    (8, 16, 16, 256, 256, 3, 1, 1),
 ]
 MODES = [("simt", torch.float32), ("simt", torch.bfloat16), ("tc", torch.bfloat16)]
 
@@ -160,6 +166,7 @@ def test_conv7_few(n, hin, win, cout, flip):
                                                   (2, 64, 64, 256, 128, 5, 1, 2),      # BN 128
                                                   (24, 64, 64, 64, 128, 4, 2, 1),      # persistent, BN 128, stride 2
                                                   (3, 20, 12, 128, 64, 3, 1, 1),       # partial tiles, BN 64
+                                                  (2, 32, 32, 256, 256, 4, 2, 1),      # one-wave, K split 8 ways
                                                   (12, 64, 64, 128, 64, 5, 1, 2)])     # persistent, BN 64
 def test_conv_fused_statistics(n, h, w, cin, cout, k, s, p):
     """The tcgen05 epilogue's per-(image, tile, channel) {sum, sum of squares} of the STORED bf16 outputs
@@ -194,3 +201,44 @@ def test_conv_fused_statistics(n, h, w, cin, cout, k, s, p):
             ref = torch.stack([blk.sum((1, 2)), (blk * blk).sum((1, 2))], -1)
             got = st[:, ty * pl.tiles[0] + tx]
             assert float((got - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), (tx, ty)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,s,p", [(2, 16, 16, 64, 64, 3, 1, 1),        # one-wave kernel, BN 64
+                                                  (4, 16, 16, 128, 128, 4, 2, 1),      # one-wave, K split 8 ways
+                                                  (3, 20, 12, 128, 128, 3, 1, 1),      # partial tiles, BN 128
+                                                  (2, 32, 32, 64, 256, 4, 2, 1),       # stride 2, BN 256
+                                                  (24, 64, 64, 64, 128, 4, 2, 1),      # persistent, BN 128, stride 2
+                                                  (12, 64, 64, 128, 64, 5, 1, 2),      # persistent, BN 64
+                                                  (40, 32, 32, 256, 512, 3, 1, 1)])    # persistent, BN 256
+@pytest.mark.parametrize("act,halo,layout", [(1, 1, 1), (2, 1, 1), (2, 0, 0), (1, 3, 0), (2, 2, 1)])
+def test_conv_activated_second_output(n, h, w, cin, cout, k, s, p, act, halo, layout):
+    """dwc_gconv_t.out2: the epilogue's activated, reflect-haloed (parity-plane) copy of the output equals, bit for
+    bit, what the separate activation + pad pass (dwc_post_fwd) makes of the stored output - the fusion of the
+    norm-less Conv2dBlocks of the style encoder / discriminator (networks.py:531,556-567)."""
+    import ctypes as C
+    dtype = torch.bfloat16
+    torch.manual_seed(4)
+    x = torch.randn(n, cin, h, w).to(dtype).double()
+    wt = (torch.randn(cout, cin, k, k) * (1.0 / (cin * k * k) ** 0.5)).to(dtype).double()
+    bias = torch.randn(cout)
+    in_layout, hy = (0, k - 1) if s == 1 else (1, 1)
+    ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    w_krsc = wt.permute(0, 2, 3, 1).contiguous().float().cuda()
+    xp = emu.make_padded(x, p, in_layout, dtype)
+    xp = xp.like(xp.t.cuda())
+    wf = pack(w_krsc, 0, dtype, cout, cout, k, cin)
+    y = HB.empty(n, ho, wo, cout, hy, 0, dtype, "cuda", zero=True)
+    pl = P.plan_conv_fwd(xp, wf, cout, cout, bias.cuda(), y, k, s, L.TC)
+    o2 = HB.empty(n, ho, wo, cout, halo, layout, dtype, "cuda")
+    o2.t.fill_(float("nan"))
+    pl.out2 = (o2.t, act, halo, layout)
+    pl.launch()
+    y2 = HB.empty(n, ho, wo, cout, hy, 0, dtype, "cuda", zero=True)
+    P.plan_conv_fwd(xp, wf, cout, cout, bias.cuda(), y2, k, s, L.TC).launch()
+    ref = HB.empty(n, ho, wo, cout, halo, layout, dtype, "cuda")
+    ys, rs = y2.struct(), ref.struct()
+    L.check(L.lib().dwc_post_fwd(C.byref(ys), None, act, None, C.byref(rs), L.stream()), "post_fwd")
+    torch.cuda.synchronize()
+    assert torch.equal(y.t, y2.t)                                  # the primary output is unchanged by the option
+    assert not bool(torch.isnan(o2.t.float()).any())               # every halo / plane element was written
+    assert torch.equal(o2.t, ref.t)
