@@ -47,6 +47,9 @@ CONFIGS = {
 REF_BUDGET_S = 240.0          # wall-clock target of a whole --impl reference run
 
 
+PRIME_STEPS = 4
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -322,7 +325,7 @@ def our_config_dict(name, conf, B, world, mode):
             "parallelism": "dp%d" % world if conf["train"] else "replicas%d" % world,
             "l2": "inputs larger than L2: one step streams > 2 GB of activations per GPU" if conf["train"] else
                   "one call streams ~1.7 GB of activations (> 126 MB L2); weights (41 MB bf16) stay L2-resident as in serving",
-            "mode": mode}
+            "mode": mode, "graph_prime_steps": PRIME_STEPS}
 
 
 def main():
@@ -383,7 +386,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing
+    # The Solver runs each (phase, shape, attention status) eagerly twice before it captures the phase as a CUDA graph,
+    # and the attention status changes after iteration 0: PRIME_STEPS untimed steps put the capture (seconds of host
+    # work) in front of the W warm-up steps whatever W is, so that warm-up and timed steps are the steady-state program.
     it = 0
+    for _ in range(PRIME_STEPS):
+        step(resident, it)
+        it += 1
     for _ in range(args.warmup):
         step(resident, it)
         it += 1

@@ -69,8 +69,12 @@ extern "C" int dwc_gmm_kl(const float* mu, const float* lv, const float* c, floa
 }
 
 // ---------------------------------------------------------------------------------------------------
-// scalar losses.  Forward kernels atomically add block partial sums into loss[0] (caller zeroes it).
+// scalar losses.  The L1 forward is a two-level sum with a fixed order (bit-reproducible): every block parks its
+// partial sum in the caller's zeroed scratch, the block that draws the last ticket adds them by index.
+// loss[0] result, loss[1] ticket, loss[DWC_L1_SCRATCH_OFF + block] partial sums.
 // ---------------------------------------------------------------------------------------------------
+constexpr int L1_MAX_BLOCKS = 592;
+constexpr int L1_PART_OFF = 8;
 template <typename TA, typename TB>
 __global__ void l1_fwd_kernel(const TA* __restrict__ a, const TB* __restrict__ b, long long count, float inv,
                               float* __restrict__ loss) {
@@ -78,7 +82,19 @@ __global__ void l1_fwd_kernel(const TA* __restrict__ a, const TB* __restrict__ b
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     s += fabsf(to_f<TA>(a[i]) - to_f<TB>(b[i]));
   s = block_sum_f(s);
-  if (threadIdx.x == 0) atomicAdd(loss, s * inv);
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __stcg(loss + L1_PART_OFF + blockIdx.x, s);
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned int*>(loss + 1), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(loss + L1_PART_OFF + i);
+  t = block_sum_f(t);
+  if (threadIdx.x == 0) loss[0] = t * inv;
 }
 template <typename TA, typename TB>
 __global__ void l1_bwd_kernel(const TA* __restrict__ a, const TB* __restrict__ b, long long count, float inv,
@@ -94,7 +110,7 @@ __global__ void l1_bwd_kernel(const TA* __restrict__ a, const TB* __restrict__ b
 extern "C" int dwc_l1_loss_fwd(const void* a, int a_dtype, const void* b, int b_dtype, int64_t count, float* loss,
                                dwc_stream_t stream) {
   const float inv = 1.f / (float)count;
-  int g = grid1d(count) > 592 ? 592 : grid1d(count);
+  int g = grid1d(count) > L1_MAX_BLOCKS ? L1_MAX_BLOCKS : grid1d(count);
   cudaStream_t st = as_stream(stream);
   if (a_dtype == DWC_F32 && b_dtype == DWC_F32)
     l1_fwd_kernel<float, float><<<g, 256, 0, st>>>((const float*)a, (const float*)b, count, inv, loss);

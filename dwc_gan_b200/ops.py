@@ -1001,10 +1001,10 @@ class L1Fn(torch.autograd.Function):
     def forward(ctx, a, b):
         _require_cuda(a)
         assert a.shape == b.shape and _same_layout(a, b), (a.shape, b.shape, a.stride(), b.stride())
-        loss = torch.zeros(1, dtype=torch.float32, device=a.device)
+        loss = torch.zeros(600, dtype=torch.float32, device=a.device)      # DWC_L1_SCRATCH: result + ordered partials
         _call("dwc_l1_loss_fwd", L.ptr(a), L.dt(a), L.ptr(b), L.dt(b), L.i64(a.numel()), L.ptr(loss), L.stream())
         ctx.save_for_backward(a, b)
-        return loss.squeeze(0)
+        return loss[0]
 
     @staticmethod
     def backward(ctx, g):

@@ -317,8 +317,11 @@ int dwc_gmm_sample(const float* mu, const float* eps, float stddev, float* z, in
  * mu, lv [B, ncls*cdim]; also writes dmu, dlv (gradient of the loss, unscaled). */
 int dwc_gmm_kl(const float* mu, const float* lv, const float* c, float sigma, float* loss, float* dmu,
                float* dlv, int b, int ncls, int cdim, dwc_stream_t stream);
-/* loss[0] += mean |a-b| (caller zeroes loss; a,b flat of a_dtype/b_dtype)  (solver.py:113-114,127-132).
+/* loss[0] = mean |a-b| (a,b flat of a_dtype/b_dtype)  (solver.py:113-114,127-132).  `loss` is a ZEROED scratch of
+ * DWC_L1_SCRATCH floats: [0] the result, the rest a ticket and per-block partial sums added in a fixed order, so the
+ * value is bit-reproducible.
  * Backward: da = gscale[0]*sign(a-b)/count, db = -da; either may be NULL; gscale is a device scalar. */
+#define DWC_L1_SCRATCH 600
 int dwc_l1_loss_fwd(const void* a, int a_dtype, const void* b, int b_dtype, int64_t count, float* loss,
                     dwc_stream_t stream);
 int dwc_l1_loss_bwd(const void* a, int a_dtype, const void* b, int b_dtype, int64_t count, const float* gscale,

@@ -37,3 +37,13 @@ def test_epilogue_activation_matches_separate_pass():
     assert la == lb, (la, lb)
     assert torch.equal(gda, gdb)
     assert torch.equal(gga, ggb)
+
+
+def test_step_is_bit_reproducible():
+    """Two runs of the same D+G step from the same seeds: identical losses and gradients, bit for bit (every reduction
+    - split-K weight gradients, cluster split-K convolutions, loss sums - has a fixed order)."""
+    la, gda, gga, _ = _grads(False)
+    lb, gdb, ggb, _ = _grads(False)
+    assert la == lb, (la, lb)
+    assert torch.equal(gda, gdb)
+    assert torch.equal(gga, ggb)
