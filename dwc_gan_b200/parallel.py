@@ -61,6 +61,11 @@ class GradSync:
         self.bytes_reduced = 0
         self.bucket_prefixes = buckets or {}        # {id(net): [(prefix, ...), ...]}
         self.use_buckets = os.environ.get("DWC_DP_BUCKETS", "1") != "0"
+        # optional bf16 wire format in bf16 mode (DWC_DP_BF16=1; fp32 mode always exchanges fp32): halves the bytes, but
+        # measured without effect at 2 and 8 GPUs (20.71 vs 20.73 ms at 8) - the exchange is bound by the latency of the
+        # collectives left at the end of a phase and by rank skew, not by bytes (profiles/r02c_scaling.md) - so off
+        self.bf16_wire = os.environ.get("DWC_DP_BF16", "0") == "1"
+        self._wire = {}
         self.plans = {}                             # (id(net), key) -> {"need": {name: count}, "buckets": [...]}
         self.cur = None
         self.collectives = 0
@@ -107,7 +112,10 @@ class GradSync:
         self.collectives += 1
         if g.is_cuda and self.async_stream:
             if self.stream is None:
-                self.stream = torch.cuda.Stream(device=g.device)
+                # high priority: the collective's CTAs are placed ahead of the next compute kernel's when SMs free up
+                # at a kernel boundary (they cannot share an SM with a one-CTA-per-SM persistent kernel)
+                prio = int(os.environ.get("DWC_DP_PRIO", "-1"))
+                self.stream = torch.cuda.Stream(device=g.device, priority=prio)
             cur = torch.cuda.current_stream(g.device)
             self.stream.wait_stream(cur)
             if also_side:
@@ -116,7 +124,20 @@ class GradSync:
                 if side is not None:
                     self.stream.wait_stream(side)
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+                self._all_reduce(g)
+        else:
+            self._all_reduce(g)
+
+    def _all_reduce(self, g):
+        from . import ops
+        if self.bf16_wire and g.is_cuda and g.dtype == torch.float32 and ops.RT.dtype == torch.bfloat16:
+            key = (g.data_ptr(), g.numel())
+            buf = self._wire.get(key)
+            if buf is None:
+                buf = self._wire[key] = torch.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
+            buf.copy_(g)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            g.copy_(buf)
         else:
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
 

@@ -9,8 +9,13 @@ from torch.profiler import profile, ProfilerActivity
 
 conf = bench.CONFIGS[sys.argv[2] if len(sys.argv) > 2 else "train128"]
 B = int(sys.argv[1]) if len(sys.argv) > 1 and int(sys.argv[1]) > 0 else conf["batch"]
-dev = torch.device("cuda", 0)
+from dwc_gan_b200 import parallel
+rank, world, local = parallel.init_from_env()        # under torchrun: data-parallel step, rank 0 reports
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
 s, cfg = bench.build_solver(dev, "bf16", conf["overrides"])
+if world > 1:
+    parallel.attach(s)
 b = {k: v.to(dev) for k, v in bench.make_host_batch(B, conf["size"], 0).items()}
 if conf["train"]:
     step = lambda it: bench.one_step(s, cfg, b, it)
@@ -26,6 +31,9 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(6)
     torch.cuda.synchronize()
+if rank != 0:
+    torch.cuda.synchronize()
+    os._exit(0)
 path = "/tmp/trace.json"
 prof.export_chrome_trace(path)
 ev = json.load(open(path))["traceEvents"]
@@ -64,3 +72,14 @@ tot = sum(v[1] for v in agg.values())
 print("sum of activity durations %.2f ms" % (tot / 1e3))
 for nm, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print("%6.2f%% %9.1f us %5d x %8.1f us  %s" % (100 * d / tot, d, c, d / c, nm))
+if world > 1:
+    # where the collectives sit: start / end relative to the step, and what else runs at that time
+    print("collectives (ms from the start of the step):")
+    for e in ks:
+        if "nccl" in e["name"].lower():
+            a, c = e["ts"], e["ts"] + e["dur"]
+            others = sum(min(c, o["ts"] + o["dur"]) - max(a, o["ts"]) for o in ks
+                         if o is not e and o["ts"] < c and o["ts"] + o["dur"] > a)
+            print("  %8.3f .. %8.3f  (%7.1f us)  other kernels in flight meanwhile: %7.1f us  %s" % (
+                (a - t0) / 1e3, (c - t0) / 1e3, e["dur"], others, e["name"][:60]))
+    os._exit(0)
