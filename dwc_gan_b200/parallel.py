@@ -66,6 +66,7 @@ class GradSync:
         # collectives left at the end of a phase and by rank skew, not by bytes (profiles/r02c_scaling.md) - so off
         self.bf16_wire = os.environ.get("DWC_DP_BF16", "0") == "1"
         self._wire = {}
+        self.coalesce = os.environ.get("DWC_DP_COALESCE", "1") != "0" and hasattr(dist, "_coalescing_manager")
         self.plans = {}                             # (id(net), key) -> {"need": {name: count}, "buckets": [...]}
         self.cur = None
         self.collectives = 0
@@ -108,7 +109,11 @@ class GradSync:
                 self._reduce(cur["net"].ensure_flat().grad[b["start"]:b["end"]], also_side=True)
 
     def _reduce(self, g, also_side=False):
-        self.bytes_reduced += g.numel() * 4
+        """g: one range of the flat gradient buffer, or a list of ranges reduced as ONE coalesced collective (the
+        end-of-phase leftovers: one launch latency instead of one per piece)."""
+        pieces = list(g) if isinstance(g, (list, tuple)) else [g]
+        g = pieces[0]
+        self.bytes_reduced += sum(t.numel() for t in pieces) * 4
         self.collectives += 1
         if g.is_cuda and self.async_stream:
             if self.stream is None:
@@ -124,9 +129,18 @@ class GradSync:
                 if side is not None:
                     self.stream.wait_stream(side)
             with torch.cuda.stream(self.stream):
-                self._all_reduce(g)
+                self._all_reduce_many(pieces)
         else:
-            self._all_reduce(g)
+            self._all_reduce_many(pieces)
+
+    def _all_reduce_many(self, pieces):
+        if len(pieces) == 1 or self.bf16_wire or not self.coalesce or dist.get_backend(self.group) != "nccl":
+            for t in pieces:
+                self._all_reduce(t)
+            return
+        with dist._coalescing_manager(group=self.group, device=pieces[0].device, async_ops=False):
+            for t in pieces:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def _all_reduce(self, g):
         from . import ops
@@ -167,11 +181,13 @@ class GradSync:
             self.plans[(id(net), cur["key"])] = dict(buckets=buckets)
         else:
             done = sorted((plan["buckets"][i]["start"], plan["buckets"][i]["end"]) for i in cur["fired"])
-            pos = 0
+            pos, rest = 0, []
             for s, e in done + [(flat.total, flat.total)]:
                 if s - pos >= 64:                       # (shorter gaps are alignment padding: nothing to reduce)
-                    self._reduce(g[pos:s])
+                    rest.append(g[pos:s])
                 pos = max(pos, e)
+            if rest:
+                self._reduce(rest)
         if g.is_cuda and self.async_stream and self.stream is not None:
             torch.cuda.current_stream(g.device).wait_stream(self.stream)
 

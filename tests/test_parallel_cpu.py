@@ -111,8 +111,9 @@ def _bucket_worker(rank, world, port, out):
             pad[flat.offsets[nme]:flat.offsets[nme] + flat.numels[nme]] = False
         assert torch.equal(flat.grad[~pad], expect[~pad]), it          # every parameter element reduced exactly once
         n = sync.collectives - c0
-        # first call: learn (one whole-buffer reduce); afterwards two buckets + the pieces in front of and behind them
-        assert n == (1 if it == 0 else 4), (it, n)
+        # first call: learn (one whole-buffer reduce); afterwards two buckets + ONE coalesced collective for the pieces
+        # in front of and behind them
+        assert n == (1 if it == 0 else 3), (it, n)
     out.put((rank, sync.bytes_reduced))
     dist.destroy_process_group()
 

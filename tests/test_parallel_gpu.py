@@ -127,14 +127,14 @@ def _worker(rank, world, port, ngpu, q):
                     f0, f1 = O.blend(f0, a0, x, True), O.blend(f1, a1, x, True)
                 (O.dis_loss(D, f0, x, batch["label_src"]) + O.dis_loss(D, f1, x, batch["label_src"])).backward()
                 g_local, state, params, net = {k: v.grad for k, v in D.items()}, orc.d_state, orc.D, s.dis
-                want = 2 + 3                      # two early buckets + the pieces in front of, between and behind them
+                want = 2 + 1                      # two early buckets + the pieces in front of, between and behind them as ONE collective
             else:
                 eps["gen1"], eps["gen2"] = torch.randn(1, 8, B, 8), torch.randn(1, 8, B, 8)
                 s.gen_update(*args)
                 G = orc._leaf(orc.G)
                 O.gen_phase_losses(G, orc.D, batch, eps["gen1"], eps["gen2"], True, orc.ds_w)["loss_gen_total"].backward()
                 g_local, state, params, net = {k: v.grad for k, v in G.items()}, orc.g_state, orc.G, s.gen
-                want = 1 + 2                      # the decoder bucket + encoders in front, text encoder / MLP behind
+                want = 1 + 1                      # the decoder bucket + (encoders in front, text encoder / MLP behind) coalesced
             assert sync.collectives - c0 == want, (phase, sync.collectives - c0, want)
             mine = {k: (g / world if g is not None else None) for k, g in grads_of(net).items()}
             g_avg = averaged(g_local)
