@@ -410,23 +410,71 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = dwc_gan_b200.RT.launches - l0
     sampler.stop_flag = True
-    # ---- end to end through the public API: pinned host batch -> device every step, result read back every step
+    # ---- end to end through the public API: pinned host batch -> device every step, result read back every step.
+    # The loop is the double-buffered input pipeline a training / serving script runs (the reference's DataLoader with
+    # pin_memory + non_blocking copies does the same): the H2D copy of step i+1 is issued on a copy stream while step i
+    # computes, step i's result goes device -> pinned host asynchronously and is consumed (checked) one step later.
+    # Every step's H2D copy and D2H read happen inside the timed region.  DWC_BENCH_E2E_SERIAL=1: strictly serial loop.
     h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in keys)
+    serial = os.environ.get("DWC_BENCH_E2E_SERIAL", "0") == "1"
+    main_stream = torch.cuda.current_stream(dev)
+    in_stream, out_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    dbuf = [{k: torch.empty_like(pinned[k], device=dev) for k in keys} for _ in range(2)]
+    if conf["train"]:
+        res_host = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+    else:
+        res_host = [torch.empty(B, 3, conf["size"], conf["size"], dtype=torch.float32).pin_memory() for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        with torch.cuda.stream(in_stream):
+            in_stream.wait_event(ev_free[i & 1])             # the step that last read this buffer has been issued and run
+            for k in keys:
+                dbuf[i & 1][k].copy_(pinned[k], non_blocking=True)
+            ev_in[i & 1].record(in_stream)
+
+    def consume(i):
+        ev_out[i & 1].synchronize()
+        assert torch.isfinite(res_host[i & 1]).all()
+
     barrier()
+    for e in ev_free:
+        e.record(main_stream)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    d2h = 0
-    for _ in range(args.steps):
-        b = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
-        out = step(b, it)
+    d2h = res_host[0].numel() * 4
+    upload(0)
+    for i in range(args.steps):
+        cur = i & 1
+        if i + 1 < args.steps and not serial:
+            upload(i + 1)
+        main_stream.wait_event(ev_in[cur])
+        out = step(dbuf[cur], it)
         it += 1
+        ev_free[cur].record(main_stream)
         if conf["train"]:
-            result = torch.stack([s.loss_gen_total.detach().float(), s.loss_dis_all.detach().float()]).cpu()
+            res_host[cur].copy_(torch.stack([s.loss_gen_total.detach().float(), s.loss_dis_all.detach().float()]),
+                                non_blocking=True)
+            ev_out[cur].record(main_stream)
         else:
-            out_host.copy_(out.float(), non_blocking=True)            # the translated images are the result
-            torch.cuda.current_stream().synchronize()
-            result = out_host
-        d2h = result.numel() * 4
+            done = torch.cuda.Event()
+            done.record(main_stream)
+            with torch.cuda.stream(out_stream):
+                out_stream.wait_event(done)
+                res_host[cur].copy_(out.float(), non_blocking=True)   # the translated images are the result
+                ev_out[cur].record(out_stream)
+            out.record_stream(out_stream)
+        if serial:
+            consume(i)
+            if i + 1 < args.steps:
+                upload(i + 1)
+        elif i > 0:
+            consume(i - 1)
+    if not serial:
+        consume(args.steps - 1)
+    result = res_host[(args.steps - 1) & 1]
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -452,7 +500,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode.startswith("bf16") else "f32",
             "data": "synthetic", "config": our_config_dict(args.config, conf, B, world, args.mode),
-            "e2e": {"value": round(e2e, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": round(e2e, 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "loop": "serial" if serial else "double-buffered: H2D of step i+1 and D2H of step i-1 overlap step i"},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof}
     if per_rank is not None:
         line["ms_per_step_by_rank"] = per_rank
