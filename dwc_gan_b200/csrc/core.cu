@@ -1,5 +1,6 @@
 // Error plumbing, device queries and TMA descriptor construction (host side).
 #include "common.cuh"
+#include <stdlib.h>
 #include <stdarg.h>
 #include <cudaTypedefs.h>
 
@@ -14,6 +15,15 @@ void dwc_set_error(const char* fmt, ...) {
 
 extern "C" const char* dwc_last_error(void) { return g_err; }
 extern "C" int dwc_abi_version(void) { return 1; }
+
+int dwc_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DWC_PDL");
+    on = e ? atoi(e) : 0;          // measured: +1.2 % step time when on (profiles/r02f), so opt-in
+  }
+  return on;
+}
 
 int dwc_num_sms() {
   static int sms = 0;

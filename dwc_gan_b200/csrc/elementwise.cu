@@ -1154,6 +1154,7 @@ extern "C" int dwc_post_fused_bwd(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, c
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) fold_halo_kernel(HB d) {
+  pdl_prologue();
   const int cvs = d.c >> 3;
   const int nb = 2 * d.halo;                       // band rows (and band columns)
   const int row_part = nb * d.w, col_part = (d.h - nb) * nb;
@@ -1188,7 +1189,10 @@ extern "C" int dwc_fold_halo(const dwc_hbuf_t* d, dwc_stream_t stream) {
   HB hd(*d);
   const int nb = 2 * d->halo;
   long long total = (long long)d->n * (nb * d->w + (d->h - nb) * nb) * (d->c / 8);
-  DISPATCH_T(d->dtype, (fold_halo_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(hd)));
+  if (d->dtype == DWC_F32)
+    DWC_CUDA(dwc_launch_pdl(fold_halo_kernel<float>, dim3(ew_grid(total)), dim3(256), 0, as_stream(stream), 1, hd));
+  else
+    DWC_CUDA(dwc_launch_pdl(fold_halo_kernel<bf16>, dim3(ew_grid(total)), dim3(256), 0, as_stream(stream), 1, hd));
   DWC_LAUNCH_CHECK();
   return 0;
 }

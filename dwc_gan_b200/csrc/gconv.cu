@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(TC_THREADS, (BN >= 256 ? 1 : 2))
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  pdl_prologue();                     // everything above is CTA-local; the previous kernel's data from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -549,6 +550,7 @@ __global__ void __launch_bounds__(TC_THREADS, (BN >= 256 ? 1 : 2))     // narrow
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  pdl_prologue();                     // everything above is CTA-local; the previous kernel's data from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -757,7 +759,7 @@ static int launch_tcp(const dwc_gconv_t* g, const GConvDev& d, int nitems, cudaS
   }
   const int slots = dwc_num_sms() * Cfg::CTAS_PER_SM;
   const int grid = nitems < slots ? nitems : slots;
-  gconv_tcp_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, d);
+  DWC_CUDA(dwc_launch_pdl(gconv_tcp_kernel<BN>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, st, 1, tmA, tmB, d));
   DWC_LAUNCH_CHECK();
   return 0;
 }
@@ -823,13 +825,7 @@ static int launch_tc(const dwc_gconv_t* g, const GConvDev& d, cudaStream_t st) {
     }
   }
   grid.z = d.nphase * dd.ksplit;
-  if (dd.ksplit == 1) {
-    gconv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, dd);
-  } else {
-    cfg.gridDim = grid;
-    attr.val.clusterDim.z = dd.ksplit;
-    DWC_CUDA(cudaLaunchKernelEx(&cfg, gconv_tc_kernel<BN>, tmA, tmB, dd));
-  }
+  DWC_CUDA(dwc_launch_pdl(gconv_tc_kernel<BN>, grid, dim3(TC_THREADS), Cfg::SMEM, st, dd.ksplit, tmA, tmB, dd));
   DWC_LAUNCH_CHECK();
   return 0;
 }

@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
     fence_barrier_init();
   }
+  pdl_prologue();
   __syncthreads();
   auto issue = [&](int i) {
     const int u = r0 * p.nseg + i;
@@ -461,7 +462,7 @@ static int rowpipe_launch(RowP& p, int nb, int row_splits, int n, cudaStream_t s
     if (row_splits > p.y.h) row_splits = p.y.h;
     if (row_splits < 1) row_splits = 1;
   }
-  row_kernel<MODE><<<dim3(row_splits, n), 256, smem, st>>>(p);
+  DWC_CUDA(dwc_launch_pdl(row_kernel<MODE>, dim3(row_splits, n), dim3(256), smem, st, 1, p));
   DWC_LAUNCH_CHECK();
   return 0;
 }

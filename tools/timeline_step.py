@@ -72,6 +72,29 @@ tot = sum(v[1] for v in agg.values())
 print("sum of activity durations %.2f ms" % (tot / 1e3))
 for nm, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print("%6.2f%% %9.1f us %5d x %8.1f us  %s" % (100 * d / tot, d, c, d / c, nm))
+# Approximate critical path: walk back from the last activity; the predecessor of an activity is the one (any stream)
+# that ended last before it started - the dependency that released it, or the previous kernel of its own stream.
+ends = sorted(ks, key=lambda e: e["ts"] + e["dur"])
+import bisect
+end_ts = [e["ts"] + e["dur"] for e in ends]
+cur = ends[-1]
+path = []
+while cur is not None:
+    path.append(cur)
+    i = bisect.bisect_right(end_ts, cur["ts"] + 0.5) - 1          # last activity that ended before `cur` started
+    while i >= 0 and ends[i] is cur:
+        i -= 1
+    cur = ends[i] if i >= 0 else None
+cp = collections.defaultdict(lambda: [0, 0.0])
+busy_cp = 0.0
+for e in path:
+    cp[e["name"][:70]][0] += 1
+    cp[e["name"][:70]][1] += e["dur"]
+    busy_cp += e["dur"]
+print("critical path (approximate): %d activities, %.2f ms of kernels + %.2f ms of gaps between them" % (
+    len(path), busy_cp / 1e3, (t1 - t0 - busy_cp) / 1e3))
+for nm, (c, d) in sorted(cp.items(), key=lambda kv: -kv[1][1])[:25]:
+    print("   cp %6.2f%% %9.1f us %5d x %8.1f us  %s" % (100 * d / max(busy_cp, 1e-9), d, c, d / c, nm))
 if world > 1:
     # where the collectives sit: start / end relative to the step, and what else runs at that time
     print("collectives (ms from the start of the step):")
