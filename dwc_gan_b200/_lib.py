@@ -20,6 +20,11 @@ MAX_TAPS = 64
 _lib = None
 
 
+class AdvTerm(C.Structure):           # dwc_adv_term_t
+    _fields_ = [("kind", C.c_int32), ("row0", C.c_int32), ("row1", C.c_int32), ("target", C.c_float),
+                ("weight", C.c_float)]
+
+
 class GConv(C.Structure):
     _fields_ = [
         ("dtype", C.c_int32), ("backend", C.c_int32),
@@ -78,7 +83,7 @@ EXPORTS = [
     "dwc_post_bwd_apply", "dwc_post_fwd_norm", "dwc_post_bwd_apply_norm", "dwc_fold_halo", "dwc_post_fused_ok", "dwc_post_fused_fwd", "dwc_post_fused_bwd", "dwc_upsample_pad_fwd", "dwc_upsample_pad_bwd", "dwc_image_pad_fwd", "dwc_image_pad_bwd",
     "dwc_heads_fwd", "dwc_heads_bwd", "dwc_image_rows_fwd", "dwc_heads_bwd_rows", "dwc_blend_fwd", "dwc_blend_bwd", "dwc_relu_gap_fwd", "dwc_relu_gap_bwd",
     "dwc_sgemm", "dwc_sgemm_ws", "dwc_sgemm_workspace_bytes", "dwc_gemm_tf32", "dwc_gemm_tf32_ok", "dwc_set_tf32", "dwc_get_tf32", "dwc_colsum", "dwc_relu_bwd", "dwc_mul", "dwc_embed_concat_fwd", "dwc_embed_concat_bwd",
-    "dwc_lstm_workspace_bytes", "dwc_lstm_layer_fwd", "dwc_lstm_layer_bwd", "dwc_transpose", "dwc_gmm_sample", "dwc_gmm_kl", "dwc_l1_loss_fwd", "dwc_l1_loss_bwd",
+    "dwc_lstm_workspace_bytes", "dwc_lstm_layer_fwd", "dwc_lstm_layer_bwd", "dwc_transpose", "dwc_gmm_sample", "dwc_gmm_kl", "dwc_l1_loss_fwd", "dwc_l1_loss_bwd", "dwc_adv_loss_fwd", "dwc_adv_loss_bwd",
     "dwc_mse_const_loss_fwd", "dwc_mse_const_loss_bwd", "dwc_bce_logits_loss_fwd", "dwc_bce_logits_loss_bwd",
     "dwc_adam_step", "dwc_ema_step", "dwc_pack_weights", "dwc_pack_weights_batch", "dwc_conv7_few", "dwc_cast", "dwc_fill",
 ]

@@ -184,6 +184,93 @@ extern "C" int dwc_bce_logits_loss_bwd(const float* x, const float* y, int64_t c
 }
 
 // ---------------------------------------------------------------------------------------------------
+// One discriminator scale's adversarial terms in one kernel per direction: up to 8 weighted terms, each the mean over
+// a row range of either (src - target)^2 (LSGAN) or BCE-with-logits(cls, labels) - instead of a slice copy, a loss
+// kernel, a zero-fill, a slice scatter and a gradient add per term (networks.py:116-170, solver.py:206-207,333-334).
+// ---------------------------------------------------------------------------------------------------
+struct AdvTerms {
+  int n;
+  dwc_adv_term_t t[DWC_ADV_MAX_TERMS];
+};
+__global__ void __launch_bounds__(256) adv_loss_fwd_kernel(const float* __restrict__ src, int src_cols,
+                                                           const float* __restrict__ cls, int cls_cols,
+                                                           const float* __restrict__ labels, const AdvTerms T,
+                                                           float* __restrict__ loss) {
+  float total = 0.f;
+  for (int k = 0; k < T.n; ++k) {                      // single block, fixed order: deterministic
+    const dwc_adv_term_t t = T.t[k];
+    const int cols = t.kind == 0 ? src_cols : cls_cols;
+    const long long count = (long long)(t.row1 - t.row0) * cols;
+    const float* x = (t.kind == 0 ? src : cls) + (long long)t.row0 * cols;
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < count; i += blockDim.x) {
+      const float v = x[i];
+      if (t.kind == 0) s += (v - t.target) * (v - t.target);
+      else s += fmaxf(v, 0.f) - v * labels[i] + log1pf(expf(-fabsf(v)));
+    }
+    s = block_sum_f(s);
+    total += t.weight * (s / (float)count);
+  }
+  if (threadIdx.x == 0) loss[0] = total;
+}
+__global__ void __launch_bounds__(256) adv_loss_bwd_kernel(const float* __restrict__ src, int src_rows, int src_cols,
+                                                           const float* __restrict__ cls, int cls_rows, int cls_cols,
+                                                           const float* __restrict__ labels, const AdvTerms T,
+                                                           const float* __restrict__ gscale, float* __restrict__ dsrc,
+                                                           float* __restrict__ dcls) {
+  const float g = gscale[0];
+  const long long ns = (long long)src_rows * src_cols, nc = (long long)cls_rows * cls_cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ns + nc; i += (long long)gridDim.x * blockDim.x) {
+    const bool is_src = i < ns;
+    const long long j = is_src ? i : i - ns;
+    const int cols = is_src ? src_cols : cls_cols;
+    const int row = (int)(j / cols);
+    const float v = is_src ? src[j] : cls[j];
+    float d = 0.f;
+    for (int k = 0; k < T.n; ++k) {
+      const dwc_adv_term_t t = T.t[k];
+      if ((t.kind == 0) != is_src || row < t.row0 || row >= t.row1) continue;
+      const float gk = g * t.weight / (float)((long long)(t.row1 - t.row0) * cols);
+      d += t.kind == 0 ? 2.f * (v - t.target) * gk
+                       : (1.f / (1.f + expf(-v)) - labels[j - (long long)t.row0 * cols]) * gk;
+    }
+    if (is_src) dsrc[j] = d;
+    else dcls[j] = d;
+  }
+}
+static int adv_terms(const dwc_adv_term_t* terms, int nterms, int src_rows, int cls_rows, AdvTerms* T) {
+  DWC_CHECK(terms && nterms > 0 && nterms <= DWC_ADV_MAX_TERMS, "dwc_adv_loss: 1..%d terms", DWC_ADV_MAX_TERMS);
+  T->n = nterms;
+  for (int k = 0; k < nterms; ++k) {
+    T->t[k] = terms[k];
+    const int rows = terms[k].kind == 0 ? src_rows : cls_rows;
+    DWC_CHECK((terms[k].kind == 0 || terms[k].kind == 1) && terms[k].row0 >= 0 && terms[k].row1 > terms[k].row0 &&
+                  terms[k].row1 <= rows, "dwc_adv_loss: bad term %d", k);
+  }
+  return 0;
+}
+extern "C" int dwc_adv_loss_fwd(const float* src, int src_rows, int src_cols, const float* cls, int cls_rows, int cls_cols,
+                                const float* labels, const dwc_adv_term_t* terms, int nterms, float* loss,
+                                dwc_stream_t stream) {
+  AdvTerms T;
+  if (adv_terms(terms, nterms, src_rows, cls_rows, &T)) return 1;
+  adv_loss_fwd_kernel<<<1, 256, 0, as_stream(stream)>>>(src, src_cols, cls, cls_cols, labels, T, loss);
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int dwc_adv_loss_bwd(const float* src, int src_rows, int src_cols, const float* cls, int cls_rows, int cls_cols,
+                                const float* labels, const dwc_adv_term_t* terms, int nterms, const float* gscale,
+                                float* dsrc, float* dcls, dwc_stream_t stream) {
+  AdvTerms T;
+  if (adv_terms(terms, nterms, src_rows, cls_rows, &T)) return 1;
+  const long long total = (long long)src_rows * src_cols + (long long)cls_rows * cls_cols;
+  adv_loss_bwd_kernel<<<grid1d(total), 256, 0, as_stream(stream)>>>(src, src_rows, src_cols, cls, cls_rows, cls_cols, labels,
+                                                                     T, gscale, dsrc, dcls);
+  DWC_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Adam (coupled L2) and EMA over flat fp32 buffers
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

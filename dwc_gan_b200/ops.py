@@ -1083,3 +1083,40 @@ class BceLogitsFn(torch.autograd.Function):
 
 def bce_logits(x, y):
     return BceLogitsFn.apply(x, y)
+
+
+class AdvLossFn(torch.autograd.Function):
+    """All adversarial terms of one discriminator scale in one kernel per direction (dwc_adv_loss_fwd/bwd): spec is a
+    tuple of (kind, row0, row1, target, weight) - kind 0: weight * mean (src[row0:row1] - target)^2, kind 1: weight *
+    mean BCE-with-logits(cls[row0:row1], labels) (networks.py:116-170 as the Solver batches the passes)."""
+
+    @staticmethod
+    def forward(ctx, src, cls, labels, spec):
+        _require_cuda(src)
+        assert src.dtype == torch.float32 and cls.dtype == torch.float32 and src.is_contiguous() and cls.is_contiguous()
+        n = src.shape[0]
+        labels = labels.contiguous().float()
+        terms = (L.AdvTerm * len(spec))(*[L.AdvTerm(int(k), int(a), int(b), float(t), float(w)) for k, a, b, t, w in spec])
+        loss = torch.empty(1, dtype=torch.float32, device=src.device)
+        _call("dwc_adv_loss_fwd", L.ptr(src), n, src.numel() // n, L.ptr(cls), cls.shape[0], cls.numel() // cls.shape[0],
+              L.ptr(labels), terms, len(spec), L.ptr(loss), L.stream())
+        ctx.spec = spec
+        ctx.save_for_backward(src, cls, labels)
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        src, cls, labels = ctx.saved_tensors
+        spec = ctx.spec
+        n = src.shape[0]
+        terms = (L.AdvTerm * len(spec))(*[L.AdvTerm(int(k), int(a), int(b), float(t), float(w)) for k, a, b, t, w in spec])
+        dsrc, dcls = torch.empty_like(src), torch.empty_like(cls)
+        gs = g.reshape(1).float().contiguous()
+        _call("dwc_adv_loss_bwd", L.ptr(src), n, src.numel() // n, L.ptr(cls), cls.shape[0], cls.numel() // cls.shape[0],
+              L.ptr(labels), terms, len(spec), L.ptr(gs), L.ptr(dsrc), L.ptr(dcls), L.stream())
+        return dsrc, dcls, None, None
+
+
+def adv_loss(src, cls, labels, spec):
+    """src: the discriminator's patch output [N, 1, h, w] (any shape with N first), cls [N, num_cls]."""
+    return AdvLossFn.apply(src, cls, labels, tuple(spec))

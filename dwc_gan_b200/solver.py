@@ -363,10 +363,10 @@ class Solver(nn.Module):
     def _adv_terms(self, x_gen, label_trg, configs, B):
         """D(x_fake) and D(x_fake1) (two calc_gen_loss calls, solver.py:206-207) as one 2B pass."""
         adv = []
+        gw, cw = configs['gan_w'], configs['cls_w']
         for src, cls in self.dis.forward(x_gen):
-            for i in range(2):
-                adv.append((ops.mse_const(src[i * B:(i + 1) * B], 1.0), configs['gan_w']))
-                adv.append((ops.bce_logits(cls[i * B:(i + 1) * B], label_trg), configs['cls_w']))
+            spec = ((0, 0, B, 1.0, gw), (1, 0, B, 0.0, cw), (0, B, 2 * B, 1.0, gw), (1, B, 2 * B, 0.0, cw))
+            adv.append((ops.adv_loss(src, cls, label_trg, spec), 1.0))
         return ops.weighted_sum(adv)
 
     def _gen_update_tail(self, x_real, x3, x_real_rec, c_src, c_trg, label_trg, content_real, mu_real, lv_real, mu_txt,
@@ -468,9 +468,10 @@ class Solver(nn.Module):
         # D(x_real), D(x_fake), D(x_fake1) as one 3B pass; rows [0,B) real, [B,2B) x_fake, [2B,3B) x_fake1
         terms = []
         for src, cls in dis.forward(torch.cat([x_real, fakes], dim=0)):
-            terms += [(ops.mse_const(src[B:2 * B], 0.0), gw), (ops.mse_const(src[2 * B:], 0.0), gw)]
-            # real-branch terms appear once per calc_dis_loss call, i.e. twice (solver.py:333-334)
-            terms += [(ops.mse_const(src[:B], 1.0), 2.0 * gw), (ops.bce_logits(cls[:B], label_src), 2.0 * cw)]
+            # real-branch terms appear once per calc_dis_loss call, i.e. twice (solver.py:333-334); one fused kernel per
+            # scale and direction instead of slice / loss / scatter / add kernels per term
+            spec = ((0, B, 2 * B, 0.0, gw), (0, 2 * B, 3 * B, 0.0, gw), (0, 0, B, 1.0, 2.0 * gw), (1, 0, B, 0.0, 2.0 * cw))
+            terms.append((ops.adv_loss(src, cls, label_src, spec), 1.0))
         self.loss_dis = ops.weighted_sum(terms)
         self.loss_dis_all = self.loss_dis
         self.loss_dis_all.backward()

@@ -335,6 +335,22 @@ int dwc_bce_logits_loss_fwd(const float* x, const float* y, int64_t count, float
 int dwc_bce_logits_loss_bwd(const float* x, const float* y, int64_t count, const float* gscale, float* dx,
                             dwc_stream_t stream);
 
+/* One discriminator scale's adversarial terms fused (MsImageDis.calc_dis_loss / calc_gen_loss, networks.py:116-170, as
+ * the Solver batches them, solver.py:206-207,333-334): loss[0] = sum_k weight_k * mean over rows [row0,row1) of
+ *   kind 0: (src - target)^2          src [src_rows, src_cols] fp32 (the 1-channel patch output)
+ *   kind 1: BCE-with-logits(cls, y)   cls [cls_rows, cls_cols] fp32, y = labels [row1-row0, cls_cols] (same for all terms)
+ * Backward writes the FULL gradients dsrc / dcls (zero outside every term's rows), scaled by the device scalar gscale. */
+#define DWC_ADV_MAX_TERMS 8
+typedef struct {
+  int32_t kind, row0, row1;
+  float target, weight;
+} dwc_adv_term_t;
+int dwc_adv_loss_fwd(const float* src, int src_rows, int src_cols, const float* cls, int cls_rows, int cls_cols,
+                     const float* labels, const dwc_adv_term_t* terms, int nterms, float* loss, dwc_stream_t stream);
+int dwc_adv_loss_bwd(const float* src, int src_rows, int src_cols, const float* cls, int cls_rows, int cls_cols,
+                     const float* labels, const dwc_adv_term_t* terms, int nterms, const float* gscale, float* dsrc,
+                     float* dcls, dwc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Optimizer: torch.optim.Adam with coupled L2 (solver.py:65-68) + EMA (utils.py:52-54) on flat
  * buffers, chunked.  chunk table entries: {offset, length, active}.  hyper (device, float[8]):

@@ -72,6 +72,24 @@ tot = sum(v[1] for v in agg.values())
 print("sum of activity durations %.2f ms" % (tot / 1e3))
 for nm, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print("%6.2f%% %9.1f us %5d x %8.1f us  %s" % (100 * d / tot, d, c, d / c, nm))
+# Time during which nothing substantial runs (only kernels shorter than 10 us, or nothing at all): loss glue, launch chains
+big = sorted((e["ts"], e["ts"] + e["dur"]) for e in ks if e["dur"] >= 10.0)
+cov, cs, ce = 0.0, big[0][0], big[0][1]
+holes = []
+for a, c in big[1:]:
+    if a > ce:
+        cov += ce - cs
+        holes.append((cs if False else ce, a))
+        cs, ce = a, c
+    else:
+        ce = max(ce, c)
+cov += ce - cs
+print("time with no kernel >= 10 us in flight: %.2f ms of %.2f ms" % ((t1 - t0 - cov) / 1e3, (t1 - t0) / 1e3))
+for a, c in sorted(holes, key=lambda h: h[0] - h[1])[:12]:
+    inside = [e for e in ks if e["ts"] >= a - 0.5 and e["ts"] + e["dur"] <= c + 0.5]
+    names = collections.Counter(e["name"][:40] for e in inside)
+    print("   hole at %8.3f ms, %7.1f us, %3d small kernels: %s" % ((a - t0) / 1e3, c - a, len(inside),
+                                                                ", ".join("%dx %s" % (v, k) for k, v in names.most_common(4))))
 # Approximate critical path: walk back from the last activity; the predecessor of an activity is the one (any stream)
 # that ended last before it started - the dependency that released it, or the previous kernel of its own stream.
 ends = sorted(ks, key=lambda e: e["ts"] + e["dur"])
