@@ -95,6 +95,7 @@ class Solver(nn.Module):
         # phase (forward, backward, gradient all-reduce, Adam) is captured once and replayed afterwards.
         self.use_cuda_graphs = os.environ.get("DWC_CUDA_GRAPHS", "1") != "0"
         self.graph_warmup = 2
+        self._static_in, self._static_src = {}, {}         # static graph inputs shared by the phases (see _feed_static)
         self._graphs = {}
         self._last_phase = None
         self._ds_w_dev = None
@@ -227,8 +228,7 @@ class Solver(nn.Module):
             return impl(*tensors, configs, iters)
         self._last_phase = phase
         for st, t in zip(ent["static"], tensors):
-            if st.data_ptr() != t.data_ptr():
-                st.copy_(t, non_blocking=True)
+            self._feed_static(st, t)
         opt.graph_prepare(ent["adam"])
         ent["graph"].replay()
         opt.graph_finish(ent["adam"])
@@ -252,9 +252,30 @@ class Solver(nn.Module):
                     m.bias = m.bias.detach()
         gc.collect()
 
+    def _feed_static(self, st, t):
+        """Copy a step input into the graph's static buffer unless it already holds exactly this tensor's current value:
+        dis_update and gen_update of one iteration receive the same batch (train.py:95-99) and share their static
+        inputs, so the second phase copies nothing.  The source is identified by object identity + in-place version
+        counter, and kept referenced so that its storage cannot be recycled for a different tensor in between."""
+        if st.data_ptr() == t.data_ptr():
+            return
+        rec = self._static_src.get(id(st))
+        if rec is not None and rec[0] is t and rec[1] == t._version:
+            return
+        st.copy_(t, non_blocking=True)
+        self._static_src[id(st)] = (t, t._version)
+
+    def _static_for(self, i, t):
+        key = (i, tuple(t.shape), t.dtype, t.device)
+        st = self._static_in.get(key)
+        if st is None:
+            st = self._static_in[key] = torch.empty_like(t)
+        self._feed_static(st, t)
+        return st
+
     def _capture(self, ent, impl, opt, tensors, configs, iters):
         self._release_autograd()
-        static = [t.clone() for t in tensors]
+        static = [self._static_for(i, t) for i, t in enumerate(tensors)]
         opt.graph_buffers()
         # Packed bf16 weights are shared between the phases (rewritten in place, networks.Conv2dBlock._pack_buffer):
         # this phase packs exactly the networks whose optimizer stepped since their last packing.  That is a
