@@ -72,6 +72,11 @@ tot = sum(v[1] for v in agg.values())
 print("sum of activity durations %.2f ms" % (tot / 1e3))
 for nm, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print("%6.2f%% %9.1f us %5d x %8.1f us  %s" % (100 * d / tot, d, c, d / c, nm))
+if os.environ.get("DWC_TL_TAIL"):
+    # the last N activities of the step: what the optimizer is waiting for
+    for e in sorted(ks, key=lambda e: e["ts"] + e["dur"])[-int(os.environ["DWC_TL_TAIL"]):]:
+        print("   tail %8.3f .. %8.3f ms  stream %-4s %7.1f us  %s" % ((e["ts"] - t0) / 1e3, (e["ts"] + e["dur"] - t0) / 1e3,
+                                                                   e["args"].get("stream"), e["dur"], e["name"][:60]))
 # Time during which nothing substantial runs (only kernels shorter than 10 us, or nothing at all): loss glue, launch chains
 big = sorted((e["ts"], e["ts"] + e["dur"]) for e in ks if e["dur"] >= 10.0)
 cov, cs, ce = 0.0, big[0][0], big[0][1]
