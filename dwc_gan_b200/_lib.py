@@ -79,7 +79,7 @@ class PackEntry(C.Structure):
 
 EXPORTS = [
     "dwc_last_error", "dwc_abi_version", "dwc_tc_available", "dwc_gconv", "dwc_wgrad_workspace_bytes", "dwc_wgrad",
-    "dwc_nc_stats", "dwc_norm_finalize", "dwc_post_fwd", "dwc_post_bwd_reduce", "dwc_norm_bwd_finalize",
+    "dwc_nc_stats", "dwc_norm_finalize", "dwc_post_fwd", "dwc_post_bwd_reduce", "dwc_post_bwd_reduce_folds", "dwc_post_bwd_reduce_can_fold", "dwc_norm_bwd_finalize",
     "dwc_post_bwd_apply", "dwc_post_fwd_norm", "dwc_post_bwd_apply_norm", "dwc_fold_halo", "dwc_post_fused_ok", "dwc_post_fused_fwd", "dwc_post_fused_bwd", "dwc_upsample_pad_fwd", "dwc_upsample_pad_bwd", "dwc_image_pad_fwd", "dwc_image_pad_bwd",
     "dwc_heads_fwd", "dwc_heads_bwd", "dwc_image_rows_fwd", "dwc_heads_bwd_rows", "dwc_blend_fwd", "dwc_blend_bwd", "dwc_relu_gap_fwd", "dwc_relu_gap_bwd",
     "dwc_sgemm", "dwc_sgemm_ws", "dwc_sgemm_workspace_bytes", "dwc_gemm_tf32", "dwc_gemm_tf32_ok", "dwc_set_tf32", "dwc_get_tf32", "dwc_colsum", "dwc_relu_bwd", "dwc_mul", "dwc_embed_concat_fwd", "dwc_embed_concat_bwd",

@@ -34,6 +34,9 @@ struct RowP {
   float neps;
   int dbytes;      // bytes of the second operand per stage (0: none).  d in parity-plane layout: the two plane rows of the
   int d_planes;    // padded row (even X, odd X), wq*C elements each, loaded whole (nseg == 1)
+  int d_fold;      // RM_BRED: d still carries the gradient of its reflect halo; the kernel loads whole PADDED rows, folds
+                   // the mirror images into the band pixels on the fly (same order and bf16 rounding as dwc_fold_halo)
+                   // and writes the folded band back, so that the apply pass reads a folded buffer (nseg == 1, plain d)
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -228,78 +231,57 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
         bulk_load_1d(dst + p.segbytes, db + p.d.off_padded(n, Y, 0), (uint32_t)(p.dbytes >> 1), &full[s]);
         bulk_load_1d(dst + p.segbytes + (p.dbytes >> 1), db + p.d.off_padded(n, Y, 1), (uint32_t)(p.dbytes >> 1),
                      &full[s]);
-      } else {
-        bulk_load_1d(dst + p.segbytes, db + p.d.off(n, row, x0), (uint32_t)p.segbytes, &full[s]);
+      } else if (MODE == RM_BRED && p.d_fold) {
+      // d row = whole padded row [X = 0 .. W + 2h); interior pixel px sits at X = px + h.
+      // Phase 1: the band pixels (h columns next to each edge; the whole row when it is a band row) take the sum of
+      // their mirror images, in dwc_fold_halo's order and rounding, in the staged row AND in global memory.
+      // Phase 2: the plain reduction over the (now folded) staged row.
+      const int h = p.d.halo;
+      const int Ym = (row >= 1 && row <= h) ? h - row : ((row >= H - 1 - h && row <= H - 2) ? h + 2 * (H - 1) - row : -1);
+      bf16* dg = reinterpret_cast<bf16*>(p.d.ptr);
+      const long long rowY = p.d.off_padded(n, row + h, 0);
+      const long long rowM = Ym >= 0 ? p.d.off_padded(n, Ym, 0) : 0;
+      uint8_t* sdw = const_cast<uint8_t*>(sd);
+      const int nband = Ym >= 0 ? W * cvs : 2 * h * cvs;
+      for (int j = tid; j < nband; j += 256) {
+        const int bp = j / cvs, bc = (j - bp * cvs) * 8;
+        const int px = Ym >= 0 ? bp : (bp < h ? 1 + bp : W - 1 - h + (bp - h));
+        const int xm = (px >= 1 && px <= h) ? h - px : ((px >= W - 1 - h && px <= W - 2) ? h + 2 * (W - 1) - px : -1);
+        float g[8], t[8];
+        uint8_t* slot = sdw + ((size_t)(px + h) * C + bc) * 2;
+        rp_unpack8(*reinterpret_cast<const uint4*>(slot), g);
+        if (xm >= 0) {
+          rp_unpack8(*reinterpret_cast<const uint4*>(sd + ((size_t)xm * C + bc) * 2), t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] += t[e];
+        }
+        if (Ym >= 0) {
+          rp_unpack8(__ldg(reinterpret_cast<const uint4*>(dg + rowM + (long long)(px + h) * C + bc)), t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] += t[e];
+          if (xm >= 0) {
+            rp_unpack8(__ldg(reinterpret_cast<const uint4*>(dg + rowM + (long long)xm * C + bc)), t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] += t[e];
+          }
+        }
+        const uint4 folded = rp_pack8(g);
+        *reinterpret_cast<uint4*>(slot) = folded;
+        *reinterpret_cast<uint4*>(dg + rowY + (long long)(px + h) * C + bc) = folded;
       }
-    }
-  };
-  // shared-memory byte offset (inside the d part of a stage) of chunk q = (pixel q / cvs, channel group cv)
-  auto d_off = [&](int q) -> size_t {
-    if (!p.d_planes) return (size_t)q * 16;
-    const int X = q / cvs + p.d.halo;
-    return ((size_t)((X & 1) * (p.d.wp >> 1) + (X >> 1)) * C + c0) * 2;
-  };
-  if (tid == 0)
-    for (int i = 0; i < S - 1 && i < cnt; ++i) issue(i);
-
-  // per-channel coefficients of this thread's 8 channels
-  float sc[8], sh[8], ba[8], bb[8], bc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    sc[e] = 1.f; sh[e] = 0.f; ba[e] = 1.f; bb[e] = 0.f; bc[e] = 0.f;
-  }
-  __shared__ float4 s_co[512];                          // in-kernel coefficients (C <= 512)
-  __shared__ double s_d[256];
-  if (MODE == RM_FWD && p.nstats) {
-    rp_fwd_coef(p, n, C, reinterpret_cast<float2*>(s_co), s_d, blockIdx.x == 0);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float2 q = reinterpret_cast<const float2*>(s_co)[c0 + e];
-      sc[e] = q.x; sh[e] = q.y;
-    }
-  } else if (MODE != RM_STATS && p.coef) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float4 q = __ldg(p.coef + (long long)n * C + c0 + e);
-      sc[e] = q.x; sh[e] = q.y;
-    }
-  }
-  if (MODE == RM_BAPPLY && p.nstats) {
-    rp_bwd_coef(p, n, C, s_co, s_d, blockIdx.x == 0);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float4 q = s_co[c0 + e];
-      ba[e] = q.x; bb[e] = q.y; bc[e] = q.z;
-    }
-  } else if (MODE == RM_BAPPLY && p.bco) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float4 q = __ldg(p.bco + (long long)n * C + c0 + e);
-      ba[e] = q.x; bb[e] = q.y; bc[e] = q.z;
-    }
-  }
-  float a0[8], a1[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) a0[e] = a1[e] = 0.f;
-
-  const int nchunks = p.segbytes >> 4;
-  const int act = p.act;
-  for (int i = 0; i < cnt; ++i) {
-    __syncthreads();                                   // everyone is done with unit i-1: its stage may be refilled
-    if (tid == 0 && i + S - 1 < cnt) issue(i + S - 1);
-    const int s = i % S;
-    mbar_wait(&full[s], (uint32_t)((i / S) & 1));
-    const uint8_t* sy = rsm + (size_t)s * stage_bytes;
-    const uint8_t* sd = sy + p.segbytes;
-    const int u = r0 * p.nseg + i;
-    const int row = u / p.nseg, x0 = (u - row * p.nseg) * p.segw;
-    if (MODE == RM_STATS) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes to a stage the bulk copies refill later
+      __syncthreads();
+      const uint8_t* sdi = sd + (size_t)h * C * 2;       // interior part of the padded row
 #pragma unroll 4
       for (int q = tid; q < nchunks; q += 256) {
-        float v[8];
+        float v[8], g[8];
         rp_unpack8(*reinterpret_cast<const uint4*>(sy + (size_t)q * 16), v);
+        rp_unpack8(*reinterpret_cast<const uint4*>(sdi + (size_t)q * 16), g);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { a0[e] += v[e]; a1[e] += v[e] * v[e]; }
+        for (int e = 0; e < 8; ++e) {
+          const float dz = g[e] * rp_act_grad(sc[e] * v[e] + sh[e], act);
+          a0[e] += dz; a1[e] += dz * v[e];
+        }
       }
     } else if (MODE == RM_BRED) {
 #pragma unroll 4
@@ -441,6 +423,7 @@ static int rowpipe_launch(RowP& p, int nb, int row_splits, int n, cudaStream_t s
     p.d_planes = 1;
     p.dbytes = p.d.wp * p.d.c * 2;
   }
+  if (MODE == RM_BRED && p.d_fold) p.dbytes = p.d.wp * p.d.c * 2;      // whole padded rows of d
   const int stage_bytes = p.segbytes + p.dbytes;
   int stages = 103000 / stage_bytes;                   // 2 CTAs per SM next to ~11 KB of static shared memory
   if (stages > 4) stages = 4;

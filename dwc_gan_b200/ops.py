@@ -713,11 +713,13 @@ class PostFn(torch.autograd.Function):
                   L.ptr(dnb), C.byref(dys), C.byref(drs) if drs is not None else None, L.stream())
         else:
             # fold the reflect-halo gradient once, in place: the streaming passes then read whole interior rows
-            pre = _prefold(dout)
+            # (norm sites whose reduction streams whole padded rows fold it inside that pass: no separate launch)
+            in_reduce = kind != NORM_NONE and bool(L.lib().dwc_post_bwd_reduce_folds(C.byref(ds), C.byref(ys)))
+            pre = 1 if in_reduce else _prefold(dout)
             if kind != NORM_NONE:
                 red = torch.empty(n * splits * c * 2, dtype=torch.float32, device=dev)
-                _call("dwc_post_bwd_reduce", C.byref(ds), C.byref(ys), L.ptr(coef), act, splits, L.ptr(red), pre,
-                      L.stream())
+                _call("dwc_post_bwd_reduce", C.byref(ds), C.byref(ys), L.ptr(coef), act, splits, L.ptr(red),
+                      2 if in_reduce else pre, L.stream())
                 bco = torch.empty(n * c * 4, dtype=torch.float32, device=dev)
                 if kind == NORM_ADAIN:
                     dnw = torch.empty(n, c, dtype=torch.float32, device=dev)

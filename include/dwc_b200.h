@@ -164,6 +164,10 @@ int dwc_post_fwd(const dwc_hbuf_t* y, const float* coef, int act, const dwc_hbuf
                  const dwc_hbuf_t* out, dwc_stream_t stream);
 
 /* Backward, pass 1: red[(n*splits+s)*C+c] = {sum dz, sum dz*y} with dz = fold(dout) * act'(scale*y+shift). */
+/* 1 if dwc_post_bwd_reduce(..., prefolded = 2, ...) can fold dout's reflect-halo gradient into the interior itself, in place
+ * and bit-identically to dwc_fold_halo, while it streams dout for the reduction (one launch less per norm site). */
+int dwc_post_bwd_reduce_can_fold(const dwc_hbuf_t* dout, const dwc_hbuf_t* y);   /* geometry allows it */
+int dwc_post_bwd_reduce_folds(const dwc_hbuf_t* dout, const dwc_hbuf_t* y);      /* ... and DWC_FOLD_IN_REDUCE=1 (measured slower: off) */
 int dwc_post_bwd_reduce(const dwc_hbuf_t* dout, const dwc_hbuf_t* y, const float* coef, int act, int splits,
                         float* red, int prefolded, dwc_stream_t stream);
 /* Backward, pass 1b: per-(n,c) coefficients bco = {a, b, c, 0} so that dy = a*dz + b*y + c,

@@ -211,3 +211,32 @@ def test_heads_blend_gap(mode):
     gp.backward(dd.float().cuda())
     g2 = y2h.t.grad[:, 1:5, 1:5, :].permute(0, 3, 1, 2).double().cpu()
     assert (g2 - y2r.grad).abs().max() < tol * 4 * y2r.grad.abs().max()
+
+
+@pytest.mark.parametrize("n,h,w,c,halo", [(3, 32, 32, 256, 1), (2, 64, 64, 128, 2), (2, 128, 128, 64, 3), (2, 20, 24, 128, 1)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_halo_fold_inside_the_backward_reduction(n, h, w, c, halo, act):
+    """dwc_post_bwd_reduce(prefolded=2) folds the reflect-halo gradient while it streams dout: the partial sums and the
+    folded buffer equal, bit for bit, what dwc_fold_halo followed by the plain reduction leaves."""
+    import ctypes as C
+    from dwc_gan_b200 import _lib as L
+    from dwc_gan_b200.plan import HB
+    torch.manual_seed(7)
+    dt = torch.bfloat16
+    y = HB.empty(n, h, w, c, 0, 0, dt, "cuda")
+    y.t.copy_(torch.randn(y.t.shape, device="cuda"))
+    d1 = HB.empty(n, h, w, c, halo, 0, dt, "cuda")
+    d1.t.copy_(torch.randn(d1.t.shape, device="cuda"))
+    d2 = d1.like(d1.t.clone())
+    coef = torch.randn(n * c, 4, device="cuda")
+    splits = 8
+    ys, s1, s2 = y.struct(), d1.struct(), d2.struct()
+    assert L.lib().dwc_post_bwd_reduce_can_fold(C.byref(s2), C.byref(ys))
+    r1 = torch.full((n * splits * c * 2,), float("nan"), device="cuda")
+    r2 = torch.full((n * splits * c * 2,), float("nan"), device="cuda")
+    L.check(L.lib().dwc_fold_halo(C.byref(s1), L.stream()), "fold")
+    L.check(L.lib().dwc_post_bwd_reduce(C.byref(s1), C.byref(ys), L.ptr(coef), act, splits, L.ptr(r1), 1, L.stream()), "red")
+    L.check(L.lib().dwc_post_bwd_reduce(C.byref(s2), C.byref(ys), L.ptr(coef), act, splits, L.ptr(r2), 2, L.stream()), "red")
+    torch.cuda.synchronize()
+    assert torch.equal(d1.t, d2.t)
+    assert torch.equal(r1, r2)
