@@ -232,6 +232,81 @@ __global__ void __launch_bounds__(256) row_kernel(const __grid_constant__ RowP p
         bulk_load_1d(dst + p.segbytes + (p.dbytes >> 1), db + p.d.off_padded(n, Y, 1), (uint32_t)(p.dbytes >> 1),
                      &full[s]);
       } else if (MODE == RM_BRED && p.d_fold) {
+        bulk_load_1d(dst + p.segbytes, db + p.d.off_padded(n, row + p.d.halo, 0), (uint32_t)p.dbytes, &full[s]);
+      } else {
+        bulk_load_1d(dst + p.segbytes, db + p.d.off(n, row, x0), (uint32_t)p.segbytes, &full[s]);
+      }
+    }
+  };
+  // shared-memory byte offset (inside the d part of a stage) of chunk q = (pixel q / cvs, channel group cv)
+  auto d_off = [&](int q) -> size_t {
+    if (!p.d_planes) return (size_t)q * 16;
+    const int X = q / cvs + p.d.halo;
+    return ((size_t)((X & 1) * (p.d.wp >> 1) + (X >> 1)) * C + c0) * 2;
+  };
+  if (tid == 0)
+    for (int i = 0; i < S - 1 && i < cnt; ++i) issue(i);
+
+  // per-channel coefficients of this thread's 8 channels
+  float sc[8], sh[8], ba[8], bb[8], bc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = 1.f; sh[e] = 0.f; ba[e] = 1.f; bb[e] = 0.f; bc[e] = 0.f;
+  }
+  __shared__ float4 s_co[512];                          // in-kernel coefficients (C <= 512)
+  __shared__ double s_d[256];
+  if (MODE == RM_FWD && p.nstats) {
+    rp_fwd_coef(p, n, C, reinterpret_cast<float2*>(s_co), s_d, blockIdx.x == 0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float2 q = reinterpret_cast<const float2*>(s_co)[c0 + e];
+      sc[e] = q.x; sh[e] = q.y;
+    }
+  } else if (MODE != RM_STATS && p.coef) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float4 q = __ldg(p.coef + (long long)n * C + c0 + e);
+      sc[e] = q.x; sh[e] = q.y;
+    }
+  }
+  if (MODE == RM_BAPPLY && p.nstats) {
+    rp_bwd_coef(p, n, C, s_co, s_d, blockIdx.x == 0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float4 q = s_co[c0 + e];
+      ba[e] = q.x; bb[e] = q.y; bc[e] = q.z;
+    }
+  } else if (MODE == RM_BAPPLY && p.bco) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float4 q = __ldg(p.bco + (long long)n * C + c0 + e);
+      ba[e] = q.x; bb[e] = q.y; bc[e] = q.z;
+    }
+  }
+  float a0[8], a1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a0[e] = a1[e] = 0.f;
+
+  const int nchunks = p.segbytes >> 4;
+  const int act = p.act;
+  for (int i = 0; i < cnt; ++i) {
+    __syncthreads();                                   // everyone is done with unit i-1: its stage may be refilled
+    if (tid == 0 && i + S - 1 < cnt) issue(i + S - 1);
+    const int s = i % S;
+    mbar_wait(&full[s], (uint32_t)((i / S) & 1));
+    const uint8_t* sy = rsm + (size_t)s * stage_bytes;
+    const uint8_t* sd = sy + p.segbytes;
+    const int u = r0 * p.nseg + i;
+    const int row = u / p.nseg, x0 = (u - row * p.nseg) * p.segw;
+    if (MODE == RM_STATS) {
+#pragma unroll 4
+      for (int q = tid; q < nchunks; q += 256) {
+        float v[8];
+        rp_unpack8(*reinterpret_cast<const uint4*>(sy + (size_t)q * 16), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a0[e] += v[e]; a1[e] += v[e] * v[e]; }
+      }
+    } else if (MODE == RM_BRED && p.d_fold) {
       // d row = whole padded row [X = 0 .. W + 2h); interior pixel px sits at X = px + h.
       // Phase 1: the band pixels (h columns next to each edge; the whole row when it is a band row) take the sum of
       // their mirror images, in dwc_fold_halo's order and rounding, in the staged row AND in global memory.
